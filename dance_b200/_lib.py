@@ -1,0 +1,79 @@
+"""ctypes binding of ``libdance_b200.so`` (the C-ABI declared in ``include/dance_b200.h``).
+
+There is no CPU fallback: if the shared library is missing, :func:`lib` raises and tells
+the user to run ``python -m dance_b200.build``.  Tensors cross the boundary as raw
+device pointers + sizes; the CUDA stream is torch's current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libdance_b200.so"
+_lib = None
+
+c_i32, c_i64, c_f32, c_vp, c_sz = C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/dance_b200.h declaration by declaration
+_SIGNATURES = {
+    "b2_last_error": (C.c_char_p, []),
+    "b2_version": (C.c_int, []),
+    "b2_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "b2_spmm_csr_f32": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32, C.c_int, C.c_int, c_vp]),
+    "b2_csr_transpose_workspace_bytes": (c_sz, [c_i32, c_i32, c_i64]),
+    "b2_csr_transpose": (C.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "b2_gemm_workspace_bytes": (c_sz, [C.c_int] * 6),
+    "b2_gemm_f32": (C.c_int, [c_vp, c_i64, C.c_int, c_vp, c_i64, C.c_int, c_vp, c_i64, C.c_int, C.c_int, C.c_int,
+                              c_vp, C.c_int, c_vp, c_i64, c_f32, C.c_int, c_vp, c_sz, c_vp]),
+    "b2_colsum_f32": (C.c_int, [c_vp, c_i64, C.c_int, C.c_int, c_vp, c_f32, c_vp]),
+    "b2_mse_sum_loss_grad_f32": (C.c_int, [c_vp, c_vp, c_vp, c_f32, C.c_int, c_vp, c_vp, c_i64, c_vp]),
+    "b2_gae_loss_workspace_bytes": (c_sz, [c_i32, c_i32]),
+    "b2_gae_loss_grad_f32": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_f32, c_f32, C.c_int,
+                                       c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
+    "b2_adam_step_f32": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_vp]),
+    "b2_relu_bwd_f32": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "b2_reparam_fwd_f32": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_vp]),
+    "b2_reparam_bwd_f32": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp]),
+    "b2_knn_workspace_bytes": (c_sz, [c_i32, c_i32, c_i32, c_i32]),
+    "b2_knn_l2_f32": (C.c_int, [c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, C.c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "b2_pairwise_l2_dense_f32": (C.c_int, [c_vp, c_i64, c_i32, c_i32, c_vp, c_i64, c_vp]),
+    "b2_knn_graph_workspace_bytes": (c_sz, [c_i32, c_i32]),
+    "b2_knn_graph_build": (C.c_int, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64, C.POINTER(c_i64), c_vp, c_sz, c_vp]),
+    "b2_normalize_total_workspace_bytes": (c_sz, [c_i32, c_i32]),
+    "b2_normalize_total_log1p_f32": (C.c_int, [c_vp, c_i64, c_i32, c_i32, c_f32, c_f32, C.c_int, C.c_int, c_f32, c_vp,
+                                               c_sz, c_vp]),
+}
+
+
+class B2Error(RuntimeError):
+    """A C-ABI call returned a negative status."""
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def declared_symbols():
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    """Return the loaded shared library (loads it on first use; no fallback if absent)."""
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise B2Error(f"{_LIB_PATH} not found: build the CUDA extension first with "
+                          "`python -m dance_b200.build` (there is no CPU fallback).")
+        handle = C.CDLL(str(_LIB_PATH))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(status: int, what: str = ""):
+    if status != 0:
+        msg = lib().b2_last_error().decode("utf-8", "replace")
+        raise B2Error(f"{what or 'dance_b200'} failed with status {status}: {msg}")

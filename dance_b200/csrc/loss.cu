@@ -1,0 +1,271 @@
+// Loss kernels of the scGNN path: value + gradient in one pass.
+//   - Feature-AE reconstruction loss  (reference scgnn2.py:1298-1328)
+//   - Graph-AE inner-product-decoder BCE + KLD, matrix-free
+//     (reference scgnn2.py:423-426, 603-619): the N×N logits z zᵀ and the
+//     dense label matrix (scgnn2.py:557) are never materialised.
+#include "common.cuh"
+
+namespace b2 {
+
+// ---------------------------------------------------------------------------
+// Feature-AE loss
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mse_loss_grad_kernel(const float* __restrict__ recon, const float* __restrict__ target,
+                     const float* __restrict__ ltmg, float regu, int relu_mask, float* __restrict__ grad,
+                     float* __restrict__ loss_out, int64_t n) {
+  double local = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float r = recon[i];
+    const float d = r - target[i];
+    // loss = (1-s)·d² + s·d²·T   ("LTMG", scgnn2.py:1313-1315);  "noregu" is s = 0.
+    // A NULL regulariser matrix means T = 0 (the reference driver passes an all-zero TRS, scgnn2.py:40).
+    const float w = (1.f - regu) + (ltmg ? regu * ltmg[i] : 0.f);
+    local += (double)(w * d * d);
+    float g = 2.f * w * d;
+    if (relu_mask && !(r > 0.f)) g = 0.f;  // final decoder ReLU (scgnn2.py:362)
+    grad[i] = g;
+  }
+  local = warp_sum(local);
+  __shared__ double sred[8];
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sred[i];
+    // per-block partials are reduced in fp64; the running total is the reference's fp32 `train_loss +=`
+    atomicAdd(loss_out, (float)t);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Graph-AE loss.
+//   S = Σ_{ij} softplus(x_ij)  +  Σ_{(i,j)∈L} h(x_ij),   x_ij = z_i·z_j
+//   h(x) = pw·softplus(-x) - softplus(x)   (pos-weighted BCE, pos_weight = L·pw)
+//        = -x                              (plain BCE, use_pos_weight = 0)
+//   cost = c · S,  c = norm / n²   (mean over all n² logits, scgnn2.py:604)
+//   L symmetric ⇒ dS/dz_i = 2·Σ_j σ(x_ij) z_j + 2·Σ_{j∈L_i} h'(x_ij) z_j
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float softplus_f(float x) {
+  // max(x,0) + log1p(exp(-|x|)) — the same stable form ATen uses for BCE-with-logits
+  return fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x)));
+}
+__device__ __forceinline__ float sigmoid_f(float x) {
+  const float e = __expf(-fabsf(x));
+  const float s = 1.f / (1.f + e);
+  return x >= 0.f ? s : e * s;
+}
+
+constexpr int GL_ROWS = 128;   // rows of z owned by one CTA (one per thread)
+constexpr int GL_JT = 128;     // j-tile staged in shared memory
+
+template <int D>
+__global__ void __launch_bounds__(GL_ROWS)
+gae_allpairs_kernel(const float* __restrict__ z, int64_t ldz, int32_t n, int32_t j_chunk, float coef,
+                    float* __restrict__ dz, double* __restrict__ loss_acc) {
+  __shared__ __align__(16) float zj[GL_JT][D];
+  const int i = blockIdx.x * GL_ROWS + threadIdx.x;
+  const bool live = i < n;
+  float zi[D], acc[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    zi[d] = live ? z[(int64_t)i * ldz + d] : 0.f;
+    acc[d] = 0.f;
+  }
+  const int j_begin = blockIdx.y * j_chunk;
+  const int j_end = min(n, j_begin + j_chunk);
+  double loss = 0.0;
+  for (int j0 = j_begin; j0 < j_end; j0 += GL_JT) {
+    const int cnt = min(GL_JT, j_end - j0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < GL_JT * D; t += GL_ROWS) {
+      const int jj = t / D, d = t % D;
+      zj[jj][d] = (jj < cnt) ? z[(int64_t)(j0 + jj) * ldz + d] : 0.f;
+    }
+    __syncthreads();
+    float tile_loss = 0.f;
+    for (int jj = 0; jj < cnt; ++jj) {
+      float x = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) x = fmaf(zi[d], zj[jj][d], x);
+      const float e = __expf(-fabsf(x));
+      const float inv = 1.f / (1.f + e);
+      const float s = x >= 0.f ? inv : e * inv;         // sigmoid(x)
+      tile_loss += fmaxf(x, 0.f) + __logf(1.f + e);     // softplus(x); e in (0,1]
+#pragma unroll
+      for (int d = 0; d < D; ++d) acc[d] = fmaf(s, zj[jj][d], acc[d]);
+    }
+    if (live) loss += (double)tile_loss;
+  }
+  if (live) {
+    const float c2 = 2.f * coef;
+    if (gridDim.y == 1) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) dz[(int64_t)i * D + d] += c2 * acc[d];
+    } else {
+#pragma unroll
+      for (int d = 0; d < D; ++d) atomicAdd(dz + (int64_t)i * D + d, c2 * acc[d]);
+    }
+  }
+  loss = warp_sum(loss);
+  __shared__ double sred[GL_ROWS / 32];
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = loss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < GL_ROWS / 32; ++w) t += sred[w];
+    atomicAdd(loss_acc, t * (double)coef);
+  }
+}
+
+// edge (label) correction: one warp per row i, lanes stride over the row's entries
+template <int D>
+__global__ void __launch_bounds__(256)
+gae_edges_kernel(const float* __restrict__ z, int64_t ldz, const int32_t* __restrict__ rowptr,
+                 const int32_t* __restrict__ colidx, int32_t n, float coef, float pw, int use_pw,
+                 float* __restrict__ dz, double* __restrict__ loss_acc) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  double loss = 0.0;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    float zi[D], acc[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) { zi[d] = __ldg(z + i * ldz + d); acc[d] = 0.f; }
+    const int32_t s = rowptr[i], e = rowptr[i + 1];
+    for (int32_t p = s + lane; p < e; p += 32) {
+      const int32_t j = colidx[p];
+      float zjv[D];
+      float x = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) { zjv[d] = __ldg(z + (int64_t)j * ldz + d); x = fmaf(zi[d], zjv[d], x); }
+      float hval, hgrad;
+      if (use_pw) {
+        const float sg = sigmoid_f(x);
+        hval = pw * softplus_f(-x) - softplus_f(x);
+        hgrad = -pw * (1.f - sg) - sg;
+      } else {
+        hval = -x;
+        hgrad = -1.f;
+      }
+      loss += (double)hval;
+#pragma unroll
+      for (int d = 0; d < D; ++d) acc[d] = fmaf(hgrad, zjv[d], acc[d]);
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) acc[d] = warp_sum(acc[d]);
+    if (lane == 0) {
+      const float c2 = 2.f * coef;
+#pragma unroll
+      for (int d = 0; d < D; ++d) dz[i * D + d] += c2 * acc[d];
+    }
+  }
+  loss = warp_sum(loss);
+  if (lane == 0 && loss != 0.0) atomicAdd(loss_acc, loss * (double)coef);
+}
+
+// KLD = -0.5/n · mean_i Σ_d (1 + 2·lv - mu² - exp(lv)²)        (scgnn2.py:614)
+__global__ void __launch_bounds__(256)
+gae_kld_kernel(const float* __restrict__ mu, const float* __restrict__ logvar, int64_t ldm, int32_t n, int32_t d,
+               float* __restrict__ dmu, float* __restrict__ dlogvar, int64_t ldd, double* __restrict__ loss_acc) {
+  const double c = -0.5 / ((double)n * (double)n);
+  const float cf = (float)c;
+  double local = 0.0;
+  const int64_t total = (int64_t)n * d;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / d;
+    const int dd = (int)(t % d);
+    const float m = mu[i * ldm + dd], lv = logvar[i * ldm + dd];
+    const float ev = expf(lv);
+    local += (double)(1.f + 2.f * lv - m * m - ev * ev);
+    dmu[i * ldd + dd] = cf * (-2.f * m);
+    dlogvar[i * ldd + dd] = cf * (2.f - 2.f * ev * ev);
+  }
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0 && local != 0.0) atomicAdd(loss_acc, local * c);
+}
+
+__global__ void gae_finish_kernel(const double* acc, float* loss_out) { loss_out[0] = (float)acc[0]; }
+
+template <int D>
+static int launch_gae(const float* z, int64_t ldz, const int32_t* rp, const int32_t* ci, int32_t n, float coef,
+                      float pw, int use_pw, float* dz, double* acc, cudaStream_t st) {
+  const int row_blocks = ceil_div(n, GL_ROWS);
+  // split the j range so that small graphs still fill the machine
+  int j_splits = 1;
+  const int target = sm_count() * 4;
+  if (row_blocks < target) j_splits = min(ceil_div(target, row_blocks), ceil_div(n, GL_JT));
+  if (j_splits < 1) j_splits = 1;
+  if (j_splits > 65535) j_splits = 65535;
+  int j_chunk = ceil_div(ceil_div(n, j_splits), GL_JT) * GL_JT;
+  j_splits = ceil_div(n, j_chunk);
+  dim3 grid(row_blocks, j_splits);
+  gae_allpairs_kernel<D><<<grid, GL_ROWS, 0, st>>>(z, ldz, n, j_chunk, coef, dz, acc);
+  B2_CHECK_LAUNCH("gae_allpairs_kernel");
+  int64_t blocks = ceil_div<int64_t>(n, 8);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  gae_edges_kernel<D><<<(unsigned)blocks, 256, 0, st>>>(z, ldz, rp, ci, n, coef, pw, use_pw, dz, acc);
+  B2_CHECK_LAUNCH("gae_edges_kernel");
+  return B2_OK;
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int b2_mse_sum_loss_grad_f32(const float* recon, const float* target, const float* ltmg_regu,
+                                        float regu_strength, int relu_mask, float* grad, float* loss_out,
+                                        int64_t n_elem, void* stream) {
+  B2_REQUIRE(recon && target && grad && loss_out && n_elem >= 0, "b2_mse_sum_loss_grad_f32: bad arguments");
+  if (n_elem == 0) return B2_OK;
+  cudaStream_t st = as_stream(stream);
+  int64_t blocks = ceil_div<int64_t>(n_elem, 256 * 8);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  mse_loss_grad_kernel<<<(unsigned)blocks, 256, 0, st>>>(recon, target, ltmg_regu, regu_strength, relu_mask, grad,
+                                                         loss_out, n_elem);
+  B2_CHECK_LAUNCH("mse_loss_grad_kernel");
+  return B2_OK;
+}
+
+extern "C" size_t b2_gae_loss_workspace_bytes(int32_t n, int32_t d) { return 256; }
+
+extern "C" int b2_gae_loss_grad_f32(const float* z, int64_t ldz, const float* mu, const float* logvar, int64_t ldm,
+                                    const int32_t* lab_rowptr, const int32_t* lab_colidx, int32_t n, int32_t d,
+                                    float norm, float pos_weight, int use_pos_weight, float* dz, float* dmu,
+                                    float* dlogvar, int64_t ldd, float* loss_out, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  B2_REQUIRE(z && lab_rowptr && lab_colidx && dz && loss_out, "b2_gae_loss_grad_f32: null pointer");
+  B2_REQUIRE(n > 0 && d > 0 && ldz >= d, "b2_gae_loss_grad_f32: bad shape");
+  B2_REQUIRE(workspace && workspace_bytes >= 256, "b2_gae_loss_grad_f32: workspace too small");
+  B2_REQUIRE((mu == nullptr) == (logvar == nullptr), "b2_gae_loss_grad_f32: mu/logvar must both be given or both NULL");
+  if (mu) B2_REQUIRE(dmu && dlogvar && ldm >= d && ldd >= d, "b2_gae_loss_grad_f32: dmu/dlogvar required with mu/logvar");
+  cudaStream_t st = as_stream(stream);
+  double* acc = reinterpret_cast<double*>(workspace);
+  B2_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), st));
+  B2_CHECK_CUDA(cudaMemsetAsync(dz, 0, sizeof(float) * (size_t)n * d, st));
+  const float coef = (use_pos_weight ? norm : 1.f) / ((float)n * (float)n);
+  int rc;
+  switch (d) {
+    case 8: rc = launch_gae<8>(z, ldz, lab_rowptr, lab_colidx, n, coef, pos_weight, use_pos_weight, dz, acc, st); break;
+    case 16: rc = launch_gae<16>(z, ldz, lab_rowptr, lab_colidx, n, coef, pos_weight, use_pos_weight, dz, acc, st); break;
+    case 32: rc = launch_gae<32>(z, ldz, lab_rowptr, lab_colidx, n, coef, pos_weight, use_pos_weight, dz, acc, st); break;
+    case 64: rc = launch_gae<64>(z, ldz, lab_rowptr, lab_colidx, n, coef, pos_weight, use_pos_weight, dz, acc, st); break;
+    default:
+      set_error("b2_gae_loss_grad_f32: embedding size %d unsupported (8, 16, 32, 64)", d);
+      return B2_ERR_UNSUPPORTED;
+  }
+  if (rc != B2_OK) return rc;
+  if (mu) {
+    int64_t blocks = ceil_div<int64_t>((int64_t)n * d, 256);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    gae_kld_kernel<<<(unsigned)blocks, 256, 0, st>>>(mu, logvar, ldm, n, d, dmu, dlogvar, ldd, acc);
+    B2_CHECK_LAUNCH("gae_kld_kernel");
+  }
+  gae_finish_kernel<<<1, 1, 0, st>>>(acc, loss_out);
+  B2_CHECK_LAUNCH("gae_finish_kernel");
+  return B2_OK;
+}

@@ -1,0 +1,56 @@
+// Error plumbing + device queries for the C-ABI.
+#include "common.cuh"
+
+#include <string.h>
+
+namespace b2 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return B2_ERR_CUDA;
+}
+
+int sm_count() {
+  static int cached[16] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev < 0 || dev >= 16) dev = 0;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+const char* last_error() { return g_err; }
+
+}  // namespace b2
+
+extern "C" {
+
+const char* b2_last_error(void) { return b2::last_error(); }
+
+int b2_version(void) { return 100; }
+
+int b2_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  B2_CHECK_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  B2_CHECK_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  return B2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,263 @@
+"""Explicit forward/backward/optimiser engines of the scGNN hot path.
+
+No autograd: every step is a fixed sequence of C-ABI kernel launches on torch's current
+stream (capturable in a CUDA graph).  Parameters, gradients and Adam moments live in ONE
+flat fp32 buffer each, so the optimiser is a single launch and — under cell-sharded data
+parallelism — the gradient all-reduce is a single NCCL call on one bucket.
+
+Reference being replaced:
+  * Feature_AE + train_handler + loss_function_graph   scgnn2.py:338-370, 1217-1328
+  * Graph_AE (GCN branch) + graph_AE_handler loop + gae_loss_function
+                                                       scgnn2.py:373-412, 479-502, 555-615
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+from .ops import CSR
+
+
+class FlatParams:
+    """Named fp32 parameters carved out of one flat buffer (+ grads and Adam state)."""
+
+    def __init__(self, shapes: List[Tuple[str, Tuple[int, ...]]], device):
+        self.names = [n for n, _ in shapes]
+        self.shapes = dict(shapes)
+        # every tensor starts on a 16-byte boundary so that TMA / float4 paths apply
+        offs, total = {}, 0
+        for n, shp in shapes:
+            numel = 1
+            for s in shp:
+                numel *= s
+            offs[n] = (total, numel)
+            total += (numel + 3) // 4 * 4
+        self.total = total
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=device)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=device)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=device)
+        self.step = 0
+        self.p: Dict[str, torch.Tensor] = {}
+        self.g: Dict[str, torch.Tensor] = {}
+        for n, shp in shapes:
+            o, numel = offs[n]
+            self.p[n] = self.flat[o:o + numel].view(*shp)
+            self.g[n] = self.grad[o:o + numel].view(*shp)
+
+    def adam_step(self, lr: float, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
+        self.step += 1
+        ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.step, lr, betas[0], betas[1], eps,
+                      weight_decay)
+
+
+def _linear_init_(w: torch.Tensor, b: torch.Tensor, gen: Optional[torch.Generator] = None):
+    """nn.Linear.reset_parameters: kaiming_uniform(a=sqrt(5)) ⇒ U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for both."""
+    fan_in = w.shape[1]
+    bound = 1.0 / fan_in**0.5
+    w.copy_((torch.rand(w.shape, generator=gen) * 2 - 1) * bound)
+    b.copy_((torch.rand(b.shape, generator=gen) * 2 - 1) * bound)
+
+
+class FeatureAEEngine:
+    """Feature_AE (dim→512→128→512→dim, ReLU everywhere) with explicit backward and Adam.
+
+    ``state_dict`` keys match the reference module (fc1.weight … fc4.bias, scgnn2.py:352-355)
+    so reference checkpoints load unchanged.
+    """
+
+    HID, EMB = 512, 128
+
+    def __init__(self, dim: int, device="cuda", lr: float = 1e-3, precision: Optional[str] = None, seed: Optional[int] = None):
+        self.dim, self.device, self.lr, self.precision = dim, torch.device(device), lr, precision
+        H, E = self.HID, self.EMB
+        self.params = FlatParams([("fc1.weight", (H, dim)), ("fc1.bias", (H, )), ("fc2.weight", (E, H)), ("fc2.bias", (E, )),
+                                  ("fc3.weight", (H, E)), ("fc3.bias", (H, )), ("fc4.weight", (dim, H)), ("fc4.bias", (dim, ))],
+                                 self.device)
+        gen = torch.Generator().manual_seed(seed) if seed is not None else None
+        for i in (1, 2, 3, 4):
+            _linear_init_(self.params.p[f"fc{i}.weight"], self.params.p[f"fc{i}.bias"], gen)
+        self._bufs = {}
+        self.loss_acc = torch.zeros(1, dtype=torch.float32, device=self.device)
+        # hook called between backward and the optimiser step (gradient all-reduce under data parallelism)
+        self.grad_hook: Optional[Callable[[torch.Tensor], None]] = None
+
+    # -- checkpoint interface -------------------------------------------------
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return {k: v.detach().clone() for k, v in self.params.p.items()}
+
+    def load_state_dict(self, sd):
+        for k, v in sd.items():
+            self.params.p[k].copy_(torch.as_tensor(v, dtype=torch.float32))
+
+    # -- buffers ----------------------------------------------------------------
+    def _buffers(self, B: int):
+        bufs = self._bufs.get(B)
+        if bufs is None:
+            H, E, D = self.HID, self.EMB, self.dim
+            mk = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
+            bufs = dict(h1=mk(B, H), z=mk(B, E), h3=mk(B, H), r=mk(B, D), dr=mk(B, D), dh3=mk(B, H), dz=mk(B, E), dh1=mk(B, H))
+            self._bufs[B] = bufs
+        return bufs
+
+    # -- forward ----------------------------------------------------------------
+    def forward(self, x: torch.Tensor, bufs=None):
+        """Returns (z, recon) like Feature_AE.forward (scgnn2.py:368-370)."""
+        P, pr = self.params.p, self.precision
+        b = bufs or self._buffers(x.shape[0])
+        ops.gemm(x, P["fc1.weight"], transB=True, bias=P["fc1.bias"], act="relu", out=b["h1"], precision=pr)
+        ops.gemm(b["h1"], P["fc2.weight"], transB=True, bias=P["fc2.bias"], act="relu", out=b["z"], precision=pr)
+        ops.gemm(b["z"], P["fc3.weight"], transB=True, bias=P["fc3.bias"], act="relu", out=b["h3"], precision=pr)
+        ops.gemm(b["h3"], P["fc4.weight"], transB=True, bias=P["fc4.bias"], act="relu", out=b["r"], precision=pr)
+        return b["z"], b["r"]
+
+    # -- one optimiser step -------------------------------------------------------
+    def train_step(self, x: torch.Tensor, ltmg: Optional[torch.Tensor] = None, regu_strength: float = 0.9,
+                   regularizer_type: str = "noregu"):
+        """One mini-batch of train_handler (scgnn2.py:1256-1281): forward, loss_function_graph
+        ('noregu' | 'LTMG'), backward, Adam.  The batch loss is accumulated into ``self.loss_acc``.
+        Returns (z, recon) views into the engine's buffers (valid until the next call with the same batch size)."""
+        P, G, pr = self.params.p, self.params.g, self.precision
+        B = x.shape[0]
+        b = self._buffers(B)
+        z, r = self.forward(x, b)
+        if regularizer_type == "noregu":
+            ops.mse_sum_loss_grad(r, x, None, 0.0, relu_mask=True, grad=b["dr"], loss_out=self.loss_acc)
+        elif regularizer_type == "LTMG":
+            # ltmg=None ⇔ the all-zero TRS matrix of the reference driver (scgnn2.py:40)
+            ops.mse_sum_loss_grad(r, x, ltmg, regu_strength, relu_mask=True, grad=b["dr"], loss_out=self.loss_acc)
+        else:
+            raise ValueError(f"unsupported regularizer_type {regularizer_type!r}")
+        # layer 4:  r = relu(h3 W4ᵀ + b4)
+        ops.gemm(b["dr"], b["h3"], transA=True, out=G["fc4.weight"], precision=pr)
+        ops.colsum(b["dr"], out=G["fc4.bias"])
+        ops.gemm(b["dr"], P["fc4.weight"], mask=b["h3"], out=b["dh3"], precision=pr)
+        # layer 3
+        ops.gemm(b["dh3"], b["z"], transA=True, out=G["fc3.weight"], precision=pr)
+        ops.colsum(b["dh3"], out=G["fc3.bias"])
+        ops.gemm(b["dh3"], P["fc3.weight"], mask=b["z"], out=b["dz"], precision=pr)
+        # layer 2
+        ops.gemm(b["dz"], b["h1"], transA=True, out=G["fc2.weight"], precision=pr)
+        ops.colsum(b["dz"], out=G["fc2.bias"])
+        ops.gemm(b["dz"], P["fc2.weight"], mask=b["h1"], out=b["dh1"], precision=pr)
+        # layer 1
+        ops.gemm(b["dh1"], x, transA=True, out=G["fc1.weight"], precision=pr)
+        ops.colsum(b["dh1"], out=G["fc1.bias"])
+        if self.grad_hook is not None:
+            self.grad_hook(self.params.grad)
+        self.params.adam_step(self.lr)
+        return z, r
+
+    def train_epoch(self, X: torch.Tensor, batch_size: int, regularizer_type: str = "noregu", regu_strength: float = 0.9,
+                    ltmg: Optional[torch.Tensor] = None, z_out: Optional[torch.Tensor] = None,
+                    recon_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One epoch over device-resident X in order (DataLoader without shuffle, scgnn2.py:299).
+        Optionally gathers the per-batch embeddings / reconstructions (the reference's ``torch.cat``
+        of all batches, scgnn2.py:1284-1291).  Returns the device scalar of summed batch losses."""
+        self.loss_acc.zero_()
+        n = X.shape[0]
+        for b0 in range(0, n, batch_size):
+            xb = X[b0:b0 + batch_size]
+            z, r = self.train_step(xb, None if ltmg is None else ltmg[b0:b0 + batch_size], regu_strength, regularizer_type)
+            if z_out is not None:
+                z_out[b0:b0 + xb.shape[0]].copy_(z)
+            if recon_out is not None:
+                recon_out[b0:b0 + xb.shape[0]].copy_(r)
+        return self.loss_acc
+
+
+def _xavier_uniform_(w: torch.Tensor, gen: Optional[torch.Generator] = None):
+    fan_in, fan_out = w.shape[0], w.shape[1]  # GraphConvolution.weight is [in, out]; xavier is symmetric in the two
+    bound = (6.0 / (fan_in + fan_out))**0.5
+    w.copy_((torch.rand(w.shape, generator=gen) * 2 - 1) * bound)
+
+
+class GraphAEEngine:
+    """Graph_AE, GCN branch: gc1 (dim→32, ReLU), gc2/gc3 (32→emb, identity) sharing hidden1,
+    reparameterise, inner-product decoder, pos-weighted BCE + KLD — all matrix-free.
+
+    gc2 and gc3 are evaluated as ONE projection + ONE SpMM over the packed weight
+    ``[W2 | W3]`` (F = 2·emb): both read the same hidden1 and the same Â (scgnn2.py:389-391).
+    """
+
+    HID = 32
+
+    def __init__(self, dim: int, embedding_size: int = 16, device="cuda", lr: float = 1e-2, precision: Optional[str] = None,
+                 seed: Optional[int] = None):
+        self.dim, self.emb, self.device, self.lr, self.precision = dim, embedding_size, torch.device(device), lr, precision
+        self.params = FlatParams([("gc1.weight", (dim, self.HID)), ("gc23.weight", (self.HID, 2 * embedding_size))], self.device)
+        gen = torch.Generator().manual_seed(seed) if seed is not None else None
+        w1 = torch.empty(dim, self.HID)
+        w2 = torch.empty(self.HID, embedding_size)
+        w3 = torch.empty(self.HID, embedding_size)
+        for w in (w1, w2, w3):
+            _xavier_uniform_(w, gen)
+        self.load_state_dict({"gc1.weight": w1, "gc2.weight": w2, "gc3.weight": w3})
+        self._bufs = {}
+        self.loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.grad_hook: Optional[Callable[[torch.Tensor], None]] = None
+
+    def state_dict(self):
+        e = self.emb
+        w23 = self.params.p["gc23.weight"]
+        return {"gc1.weight": self.params.p["gc1.weight"].detach().clone(), "gc2.weight": w23[:, :e].detach().clone(),
+                "gc3.weight": w23[:, e:].detach().clone()}
+
+    def load_state_dict(self, sd):
+        e = self.emb
+        self.params.p["gc1.weight"].copy_(torch.as_tensor(sd["gc1.weight"], dtype=torch.float32))
+        self.params.p["gc23.weight"][:, :e].copy_(torch.as_tensor(sd["gc2.weight"], dtype=torch.float32))
+        self.params.p["gc23.weight"][:, e:].copy_(torch.as_tensor(sd["gc3.weight"], dtype=torch.float32))
+
+    def grads(self):
+        e = self.emb
+        g23 = self.params.g["gc23.weight"]
+        return {"gc1.weight": self.params.g["gc1.weight"], "gc2.weight": g23[:, :e], "gc3.weight": g23[:, e:]}
+
+    def _buffers(self, n: int):
+        b = self._bufs.get(n)
+        if b is None:
+            H, e = self.HID, self.emb
+            mk = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
+            b = dict(s1=mk(n, H), h1=mk(n, H), s2=mk(n, 2 * e), ml=mk(n, 2 * e), z=mk(n, e), dz=mk(n, e), dml=mk(n, 2 * e),
+                     ds2=mk(n, 2 * e), dh1=mk(n, H), ds1=mk(n, H))
+            self._bufs[n] = b
+        return b
+
+    def forward(self, x: torch.Tensor, adj: CSR, eps: Optional[torch.Tensor] = None):
+        """Graph_AE.forward(use_GAT=False) (scgnn2.py:402-412): returns (z, mu, logvar); z = mu when eps is None."""
+        P, pr, e = self.params.p, self.precision, self.emb
+        b = self._buffers(x.shape[0])
+        ops.gemm(x, P["gc1.weight"], out=b["s1"], precision=pr)          # support = input @ W      (scgnn2.py:499)
+        ops.spmm(adj, b["s1"], act="relu", out=b["h1"])                  # act(spmm(adj, support))  (scgnn2.py:500-501)
+        ops.gemm(b["h1"], P["gc23.weight"], out=b["s2"], precision=pr)
+        ops.spmm(adj, b["s2"], out=b["ml"])
+        mu, logvar = b["ml"][:, :e], b["ml"][:, e:]
+        if eps is None:
+            return mu, mu, logvar
+        ops.reparam_fwd(mu, logvar, eps, out=b["z"])
+        return b["z"], mu, logvar
+
+    def train_step(self, x: torch.Tensor, adj: CSR, labels: CSR, norm: float, pos_weight: float, eps: torch.Tensor,
+                   adj_t: Optional[CSR] = None):
+        """One epoch of the graph_AE_handler loop (scgnn2.py:575-593): forward, gae_loss_function,
+        backward, Adam.  ``adj_t`` = Âᵀ for the backward SpMMs; defaults to Â itself (the
+        preprocess_graph output is symmetric, scgnn2.py:1196).  Loss is left in ``self.loss``."""
+        P, G, pr, e = self.params.p, self.params.g, self.precision, self.emb
+        adj_t = adj_t or adj
+        b = self._buffers(x.shape[0])
+        z, mu, logvar = self.forward(x, adj, eps)
+        dmu, dlv = b["dml"][:, :e], b["dml"][:, e:]
+        ops.gae_loss_grad(z, labels, norm, pos_weight, mu, logvar, True, dz=b["dz"], dmu=dmu, dlogvar=dlv, loss=self.loss)
+        ops.reparam_bwd(b["dz"], logvar, eps, dmu, dlv)                  # chain through z = mu + eps·exp(logvar)
+        ops.spmm(adj_t, b["dml"], out=b["ds2"])                          # d support2 = Âᵀ · d[mu|logvar]
+        ops.gemm(b["h1"], b["ds2"], transA=True, out=G["gc23.weight"], precision=pr)
+        ops.gemm(b["ds2"], P["gc23.weight"], transB=True, mask=b["h1"], out=b["dh1"], precision=pr)  # ⊙ relu'(hidden1)
+        ops.spmm(adj_t, b["dh1"], out=b["ds1"])
+        ops.gemm(x, b["ds1"], transA=True, out=G["gc1.weight"], precision=pr)
+        if self.grad_hook is not None:
+            self.grad_hook(self.params.grad)
+        self.params.adam_step(self.lr)
+        return z, mu, logvar

@@ -1,0 +1,329 @@
+"""Thin torch-tensor wrappers over the C-ABI (``include/dance_b200.h``).
+
+Every function takes CUDA tensors, hands raw pointers to the shared library on torch's
+current stream and returns CUDA tensors.  Nothing here computes on the CPU and nothing
+falls back to torch kernels: a missing library or a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from ._lib import B2Error, check, lib
+
+ACT = {"none": 0, None: 0, "relu": 1, "elu": 2, "tanh": 3}
+PREC = {"fp32": 0, "simt": 0, "tf32x3": 1, "tf32": 2}
+
+_DEFAULT_PRECISION = "tf32x3"
+
+
+def set_default_precision(p: str):
+    """GEMM precision used when a call does not name one: 'fp32' | 'tf32x3' | 'tf32'."""
+    global _DEFAULT_PRECISION
+    if p not in PREC:
+        raise ValueError(f"unknown precision {p!r}; choose from {sorted(PREC)}")
+    _DEFAULT_PRECISION = p
+
+
+def get_default_precision() -> str:
+    return _DEFAULT_PRECISION
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor, dtype, name: str, ndim: Optional[int] = None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise B2Error(f"{name}: expected a CUDA tensor (dance_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise B2Error(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if ndim is not None and t.dim() != ndim:
+        raise B2Error(f"{name}: expected {ndim}-D tensor, got shape {tuple(t.shape)}")
+
+
+def _rowmajor(t: torch.Tensor, name: str) -> int:
+    """Leading dimension of a 2-D row-major (possibly row-padded) tensor."""
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise B2Error(f"{name}: must be 2-D with unit inner stride, got strides {t.stride()}")
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    """Per-device grow-only scratch buffer (stream-ordered use only)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def device_info() -> Tuple[int, int, int]:
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    check(lib().b2_device_info(C.byref(a), C.byref(b), C.byref(c)), "b2_device_info")
+    return a.value, b.value, c.value
+
+
+# ----------------------------------------------------------------------------- CSR container
+class CSR:
+    """Device CSR matrix: int32 rowptr/colidx, optional fp32 values (None = all ones)."""
+
+    __slots__ = ("rowptr", "colidx", "vals", "shape", "_t")
+
+    def __init__(self, rowptr, colidx, vals, shape):
+        _chk(rowptr, torch.int32, "rowptr", 1)
+        _chk(colidx, torch.int32, "colidx", 1)
+        if vals is not None:
+            _chk(vals, torch.float32, "vals", 1)
+        self.rowptr, self.colidx, self.vals, self.shape = rowptr, colidx, vals, tuple(shape)
+        self._t = None
+
+    @property
+    def nnz(self) -> int:
+        return self.colidx.numel()
+
+    @classmethod
+    def from_scipy(cls, m, device="cuda", with_values=True):
+        m = m.tocsr()
+        m.sort_indices()
+        return cls(torch.from_numpy(m.indptr.astype("int32")).to(device),
+                   torch.from_numpy(m.indices.astype("int32")).to(device),
+                   torch.from_numpy(m.data.astype("float32")).to(device) if with_values else None, m.shape)
+
+    def to_scipy(self):
+        import numpy as np
+        import scipy.sparse as sp
+        vals = self.vals.cpu().numpy() if self.vals is not None else np.ones(self.nnz, dtype="float32")
+        return sp.csr_matrix((vals, self.colidx.cpu().numpy(), self.rowptr.cpu().numpy()), shape=self.shape)
+
+    def transpose(self) -> "CSR":
+        """Deterministic device transpose (cached)."""
+        if self._t is None:
+            self._t = csr_transpose(self)[0]
+        return self._t
+
+
+def spmm(A: CSR, X: torch.Tensor, reduce: str = "sum", act: Optional[str] = None,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``Y = act(A @ X)`` (reduce='sum') or row-mean (reduce='mean')."""
+    _chk(X, torch.float32, "X", 2)
+    ldx = _rowmajor(X, "X")
+    n_rows, n_cols = A.shape
+    if X.shape[0] != n_cols:
+        raise B2Error(f"spmm: A is {A.shape} but X has {X.shape[0]} rows")
+    F = X.shape[1]
+    if out is None:
+        out = torch.empty((n_rows, F), dtype=torch.float32, device=X.device)
+    _chk(out, torch.float32, "out", 2)
+    check(lib().b2_spmm_csr_f32(_p(A.rowptr), _p(A.colidx), _p(A.vals), _p(X), ldx, _p(out), _rowmajor(out, "out"),
+                                n_rows, n_cols, F, {"sum": 0, "mean": 1}[reduce], ACT[act], _stream()), "b2_spmm_csr_f32")
+    return out
+
+
+def csr_transpose(A: CSR) -> Tuple[CSR, torch.Tensor]:
+    n_rows, n_cols = A.shape
+    nnz = A.nnz
+    dev = A.rowptr.device
+    t_rowptr = torch.empty(n_cols + 1, dtype=torch.int32, device=dev)
+    t_colidx = torch.empty(nnz, dtype=torch.int32, device=dev)
+    t_vals = torch.empty(nnz, dtype=torch.float32, device=dev) if A.vals is not None else None
+    perm = torch.empty(nnz, dtype=torch.int32, device=dev)
+    nbytes = lib().b2_csr_transpose_workspace_bytes(n_rows, n_cols, nnz)
+    ws = _workspace(nbytes, dev)
+    check(lib().b2_csr_transpose(_p(A.rowptr), _p(A.colidx), _p(A.vals), n_rows, n_cols, nnz, _p(t_rowptr), _p(t_colidx),
+                                 _p(t_vals), _p(perm), _p(ws), ws.numel(), _stream()), "b2_csr_transpose")
+    return CSR(t_rowptr, t_colidx, t_vals, (n_cols, n_rows)), perm
+
+
+def gemm(A: torch.Tensor, B: torch.Tensor, *, transA: bool = False, transB: bool = False,
+         bias: Optional[torch.Tensor] = None, act: Optional[str] = None, mask: Optional[torch.Tensor] = None,
+         out: Optional[torch.Tensor] = None, accumulate: bool = False, precision: Optional[str] = None) -> torch.Tensor:
+    """``C = act(op(A) @ op(B) + bias) * (mask > 0)``; ``accumulate`` adds into ``out``."""
+    _chk(A, torch.float32, "A", 2)
+    _chk(B, torch.float32, "B", 2)
+    lda, ldb = _rowmajor(A, "A"), _rowmajor(B, "B")
+    M, K = (A.shape[1], A.shape[0]) if transA else A.shape
+    Kb, N = (B.shape[1], B.shape[0]) if transB else B.shape
+    if K != Kb:
+        raise B2Error(f"gemm: inner dimensions differ ({K} vs {Kb})")
+    if out is None:
+        if accumulate:
+            raise B2Error("gemm: accumulate=True needs `out`")
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    _chk(out, torch.float32, "out", 2)
+    if tuple(out.shape) != (M, N):
+        raise B2Error(f"gemm: out has shape {tuple(out.shape)}, expected {(M, N)}")
+    if bias is not None:
+        _chk(bias, torch.float32, "bias", 1)
+    ldmask = 0
+    if mask is not None:
+        _chk(mask, torch.float32, "mask", 2)
+        ldmask = _rowmajor(mask, "mask")
+    prec = PREC[precision or _DEFAULT_PRECISION]
+    nbytes = lib().b2_gemm_workspace_bytes(M, N, K, int(transA), int(transB), prec)
+    ws = _workspace(nbytes, A.device) if nbytes else None
+    check(lib().b2_gemm_f32(_p(A), lda, int(transA), _p(B), ldb, int(transB), _p(out), _rowmajor(out, "out"), M, N, K,
+                            _p(bias), ACT[act], _p(mask), ldmask, 1.0 if accumulate else 0.0, prec,
+                            _p(ws), ws.numel() if ws is not None else 0, _stream()), "b2_gemm_f32")
+    return out
+
+
+def colsum(X: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    _chk(X, torch.float32, "X", 2)
+    if out is None:
+        out = torch.empty(X.shape[1], dtype=torch.float32, device=X.device)
+    check(lib().b2_colsum_f32(_p(X), _rowmajor(X, "X"), X.shape[0], X.shape[1], _p(out), 1.0 if accumulate else 0.0,
+                              _stream()), "b2_colsum_f32")
+    return out
+
+
+def mse_sum_loss_grad(recon, target, ltmg_regu=None, regu_strength=0.0, relu_mask=False, grad=None, loss_out=None):
+    """Feature-AE loss; returns (loss_out[1] accumulated, grad wrt recon)."""
+    _chk(recon, torch.float32, "recon")
+    _chk(target, torch.float32, "target")
+    if not (recon.is_contiguous() and target.is_contiguous()):
+        raise B2Error("mse_sum_loss_grad: recon/target must be contiguous")
+    if grad is None:
+        grad = torch.empty_like(recon)
+    if loss_out is None:
+        loss_out = torch.zeros(1, dtype=torch.float32, device=recon.device)
+    check(lib().b2_mse_sum_loss_grad_f32(_p(recon), _p(target), _p(ltmg_regu), float(regu_strength), int(relu_mask),
+                                         _p(grad), _p(loss_out), recon.numel(), _stream()), "b2_mse_sum_loss_grad_f32")
+    return loss_out, grad
+
+
+def gae_loss_grad(z, labels: CSR, norm: float, pos_weight: float, mu=None, logvar=None, use_pos_weight=True,
+                  dz=None, dmu=None, dlogvar=None, loss=None):
+    """Matrix-free Graph-AE loss: returns (loss[1], dz, dmu, dlogvar).
+
+    ``dmu``/``dlogvar`` may be column slices of one packed [n, 2d] buffer (shared leading dimension).
+    """
+    _chk(z, torch.float32, "z", 2)
+    n, d = z.shape
+    if dz is None:
+        dz = torch.empty((n, d), dtype=torch.float32, device=z.device)
+    ldm = ldd = 0
+    if mu is not None:
+        _chk(mu, torch.float32, "mu", 2)
+        _chk(logvar, torch.float32, "logvar", 2)
+        ldm = _rowmajor(mu, "mu")
+        if _rowmajor(logvar, "logvar") != ldm:
+            raise B2Error("gae_loss_grad: mu and logvar must share a leading dimension")
+        if dmu is None:
+            dmu = torch.empty((n, d), dtype=torch.float32, device=z.device)
+            dlogvar = torch.empty((n, d), dtype=torch.float32, device=z.device)
+        ldd = _rowmajor(dmu, "dmu")
+        if _rowmajor(dlogvar, "dlogvar") != ldd:
+            raise B2Error("gae_loss_grad: dmu and dlogvar must share a leading dimension")
+    if loss is None:
+        loss = torch.empty(1, dtype=torch.float32, device=z.device)
+    ws = _workspace(256, z.device)
+    check(lib().b2_gae_loss_grad_f32(_p(z), _rowmajor(z, "z"), _p(mu), _p(logvar), ldm, _p(labels.rowptr),
+                                     _p(labels.colidx), n, d, float(norm), float(pos_weight), int(use_pos_weight),
+                                     _p(dz), _p(dmu), _p(dlogvar), ldd, _p(loss), _p(ws), ws.numel(), _stream()),
+          "b2_gae_loss_grad_f32")
+    return loss, dz, dmu, dlogvar
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, step: int, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0):
+    for t, nm in ((param, "param"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _chk(t, torch.float32, nm)
+        if not t.is_contiguous():
+            raise B2Error(f"adam_step: {nm} must be contiguous")
+    check(lib().b2_adam_step_f32(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), lr, beta1, beta2, eps,
+                                 weight_decay, step, _stream()), "b2_adam_step_f32")
+
+
+def relu_bwd(grad, y, out=None):
+    _chk(grad, torch.float32, "grad")
+    _chk(y, torch.float32, "y")
+    if out is None:
+        out = torch.empty_like(grad)
+    check(lib().b2_relu_bwd_f32(_p(grad), _p(y), _p(out), grad.numel(), _stream()), "b2_relu_bwd_f32")
+    return out
+
+
+def reparam_fwd(mu, logvar, eps, out=None):
+    n, d = mu.shape
+    z = out if out is not None else torch.empty((n, d), dtype=torch.float32, device=mu.device)
+    check(lib().b2_reparam_fwd_f32(_p(mu), _p(logvar), _rowmajor(mu, "mu"), _p(eps), _rowmajor(eps, "eps"), _p(z),
+                                   _rowmajor(z, "z"), n, d, _stream()), "b2_reparam_fwd_f32")
+    return z
+
+
+def reparam_bwd(dz, logvar, eps, dmu, dlogvar):
+    n, d = dz.shape
+    check(lib().b2_reparam_bwd_f32(_p(dz), _rowmajor(dz, "dz"), _p(logvar), _rowmajor(logvar, "logvar"), _p(eps),
+                                   _rowmajor(eps, "eps"), _p(dmu), _p(dlogvar), _rowmajor(dmu, "dmu"), n, d, _stream()),
+          "b2_reparam_bwd_f32")
+
+
+def knn(X: torch.Tensor, k: int, include_rank0: bool = False, q_begin: int = 0, q_end: Optional[int] = None,
+        return_dist: bool = True):
+    """Exact euclidean kNN of rows ``q_begin:q_end`` of X against all rows of X.
+
+    Returns ``(idx[int32, n_q×k], dist[float64, n_q×k] or None)`` ranked by (fp64 distance, index).
+    ``include_rank0=False`` drops sorted rank 0 — the reference's "self" slot (scgnn2.py:684-687).
+    """
+    _chk(X, torch.float32, "X", 2)
+    n, d = X.shape
+    q_end = n if q_end is None else q_end
+    nq = q_end - q_begin
+    idx = torch.empty((nq, k), dtype=torch.int32, device=X.device)
+    dist = torch.empty((nq, k), dtype=torch.float64, device=X.device) if return_dist else None
+    nbytes = lib().b2_knn_workspace_bytes(n, d, k, nq)
+    ws = _workspace(nbytes, X.device)
+    check(lib().b2_knn_l2_f32(_p(X), _rowmajor(X, "X"), n, d, k, q_begin, q_end, int(include_rank0), _p(idx), _p(dist),
+                              _p(ws), ws.numel(), _stream()), "b2_knn_l2_f32")
+    return idx, dist
+
+
+def pairwise_l2_dense(X: torch.Tensor) -> torch.Tensor:
+    _chk(X, torch.float32, "X", 2)
+    n, d = X.shape
+    D = torch.empty((n, n), dtype=torch.float32, device=X.device)
+    check(lib().b2_pairwise_l2_dense_f32(_p(X), _rowmajor(X, "X"), n, d, _p(D), n, _stream()), "b2_pairwise_l2_dense_f32")
+    return D
+
+
+def knn_graph_build(knn_idx: torch.Tensor) -> CSR:
+    """Union-symmetrised kNN adjacency + I with D^-1/2 (A+I) D^-1/2 values (scgnn2.py:650-672,1191-1198)."""
+    _chk(knn_idx, torch.int32, "knn_idx", 2)
+    if not knn_idx.is_contiguous():
+        raise B2Error("knn_graph_build: knn_idx must be contiguous")
+    n, k = knn_idx.shape
+    cap = 2 * n * k + n
+    dev = knn_idx.device
+    rowptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    colidx = torch.empty(cap, dtype=torch.int32, device=dev)
+    vals = torch.empty(cap, dtype=torch.float32, device=dev)
+    nnz = C.c_int64(0)
+    nbytes = lib().b2_knn_graph_workspace_bytes(n, k)
+    ws = _workspace(nbytes, dev)
+    check(lib().b2_knn_graph_build(_p(knn_idx), n, k, _p(rowptr), _p(colidx), _p(vals), cap, C.byref(nnz), _p(ws),
+                                   ws.numel(), _stream()), "b2_knn_graph_build")
+    m = nnz.value
+    return CSR(rowptr, colidx[:m].clone(), vals[:m].clone(), (n, n))
+
+
+def normalize_total_log1p_(X: torch.Tensor, target_sum: Optional[float] = None, max_fraction: float = 1.0,
+                           normalize: bool = True, log1p: bool = True, base: Optional[float] = None) -> torch.Tensor:
+    """In-place normalize_total (+log1p) on a dense CUDA matrix (cells × genes)."""
+    _chk(X, torch.float32, "X", 2)
+    n, g = X.shape
+    nbytes = lib().b2_normalize_total_workspace_bytes(n, g)
+    ws = _workspace(nbytes, X.device)
+    check(lib().b2_normalize_total_log1p_f32(_p(X), _rowmajor(X, "X"), n, g, float(target_sum or 0.0), float(max_fraction),
+                                             int(normalize), int(log1p), float(base or 0.0), _p(ws), ws.numel(),
+                                             _stream()), "b2_normalize_total_log1p_f32")
+    return X

@@ -1,0 +1,217 @@
+/*
+ * dance_b200 — C-ABI of the B200-native GNN message-passing hot path.
+ *
+ * This header is the drop-in boundary.  The reference
+ * (OmicsML/dance) has no FFI of its own: its hot path bottoms out in calls
+ * into torch / DGL / PyG / scanpy / scipy kernels.  Every entry point below
+ * names the reference call site(s) it replaces (paths relative to the
+ * reference repository root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - the library never allocates or frees caller-visible memory: scratch is
+ *     passed in, sized by the matching `*_workspace_bytes` query;
+ *   - `stream` is a `cudaStream_t` passed as `void*`; work is enqueued on it
+ *     and the call returns without synchronising (unless documented);
+ *   - return value 0 = success, negative = error; `b2_last_error()` returns
+ *     a thread-local human-readable message for the last failing call;
+ *   - matrices are row-major with an explicit leading dimension (in elements);
+ *   - index types: CSR `rowptr`/`colidx` are int32 (nnz < 2^31).
+ */
+#ifndef DANCE_B200_H_
+#define DANCE_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_OK 0
+#define B2_ERR_INVALID (-1)
+#define B2_ERR_CUDA (-2)
+#define B2_ERR_UNSUPPORTED (-3)
+#define B2_ERR_WORKSPACE (-4)
+
+/* activation codes shared by GEMM / SpMM epilogues */
+#define B2_ACT_NONE 0
+#define B2_ACT_RELU 1
+#define B2_ACT_ELU 2
+#define B2_ACT_TANH 3
+
+/* GEMM precision modes */
+#define B2_PREC_FP32_SIMT 0 /* CUDA-core FFMA, exact fp32 accumulate            */
+#define B2_PREC_TF32X3 1    /* tcgen05 kind::tf32, 3-product split, ~fp32 accuracy */
+#define B2_PREC_TF32 2      /* tcgen05 kind::tf32, single product                */
+
+const char* b2_last_error(void);
+int b2_version(void);
+/* Fills SM count and compute capability of the current device. */
+int b2_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------
+ * K1/K2  CSR SpMM  Y[n_rows,F] = act( rowscale ⊙ (A · X) )  (+ mean reduce)
+ * replaces: torch.spmm(adj, support)      scgnn2.py:500, spagcn.py:359,
+ *           scdsc.py:498; DGL update_all(u_mul_e, sum|mean)  gnn.py:90,
+ *           graphsc.py:463-465.
+ *   vals      : nnz edge weights, or NULL for an unweighted (0/1) graph
+ *   reduce    : 0 = sum, 1 = mean over the row's nnz (0 for empty rows)
+ *   act       : B2_ACT_* applied to the output row
+ *   F must be a multiple of 4; X/Y rows must be 16-byte aligned.
+ * ---------------------------------------------------------------------- */
+int b2_spmm_csr_f32(const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                    const float* X, int64_t ldx, float* Y, int64_t ldy,
+                    int32_t n_rows, int32_t n_cols, int32_t F,
+                    int reduce, int act, void* stream);
+
+/* CSR transpose (deterministic: entries of each output row ordered by source
+ * row).  Used to obtain Aᵀ for the SpMM backward of non-symmetric graphs
+ * (GAT edge lists, cell→gene / gene→cell halves of CellFeatureGraph).
+ * perm_out (optional, nnz int32): position of each transposed entry in the
+ * source arrays, so per-edge data can be permuted the same way. */
+size_t b2_csr_transpose_workspace_bytes(int32_t n_rows, int32_t n_cols, int64_t nnz);
+int b2_csr_transpose(const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                     int32_t n_rows, int32_t n_cols, int64_t nnz,
+                     int32_t* t_rowptr, int32_t* t_colidx, float* t_vals, int32_t* perm_out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * K5  dense projection GEMM with fused epilogue
+ *     C[M,N] = act( op(A)[M,K] · op(B)[K,N] + bias[N] ) ⊙ (mask > 0 ? 1 : 0)
+ * replaces: torch.mm / nn.Linear   scgnn2.py:352-355,364-370,499;
+ *           spagcn.py:358; gnn.py:57; scdeepsort.py:81; graphsci.py:41,73,81
+ *   transA = 0: A is [M,K] row-major (lda ≥ K); 1: A is stored [K,M] (lda ≥ M)
+ *   transB = 0: B is [K,N] row-major (ldb ≥ N); 1: B is stored [N,K] (ldb ≥ K)
+ *            (nn.Linear weight [out,in] is the transB = 1 case)
+ *   bias   : length N or NULL
+ *   mask   : optional [M,N] (ldmask) — output is zeroed where mask <= 0
+ *            (ReLU backward fused into the dX GEMM)
+ *   beta   : 0 overwrite, 1 accumulate into C (weight-gradient accumulation)
+ *   colsum : optional length-N output, += column sums of the epilogue result
+ *            is NOT provided here; see b2_colsum_f32.
+ * ---------------------------------------------------------------------- */
+size_t b2_gemm_workspace_bytes(int M, int N, int K, int transA, int transB, int precision);
+int b2_gemm_f32(const float* A, int64_t lda, int transA,
+                const float* B, int64_t ldb, int transB,
+                float* C, int64_t ldc, int M, int N, int K,
+                const float* bias, int act,
+                const float* mask, int64_t ldmask,
+                float beta, int precision,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* column sums: out[N] = (beta ? out : 0) + Σ_rows X[M,N]   (bias gradients) */
+int b2_colsum_f32(const float* X, int64_t ldx, int M, int N, float* out, float beta, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Losses (forward value + gradient w.r.t. the prediction, one pass)
+ * ---------------------------------------------------------------------- */
+/* Feature-AE reconstruction loss: loss_function_graph, scgnn2.py:1298-1328
+ *   regularizer "LTMG"  :  (1-s)·Σ(r-x)² + s·Σ (r-x)²·T    (T = LTMG_regu; NULL = all zeros)
+ *   regularizer "noregu":  Σ (r-x)²                       (pass s = 0)
+ * loss_out[0] += value (per-block fp64 partial sums, fp32 running total);
+ * grad = d loss / d recon, additionally masked by recon>0 when relu_mask!=0
+ * (the decoder's final ReLU, scgnn2.py:362). */
+int b2_mse_sum_loss_grad_f32(const float* recon, const float* target, const float* ltmg_regu,
+                             float regu_strength, int relu_mask,
+                             float* grad, float* loss_out, int64_t n_elem, void* stream);
+
+/* Graph-AE loss, exact and matrix-free: gae_loss_function, scgnn2.py:603-615
+ * with InnerProductDecoder scgnn2.py:423-426 (logits = z zᵀ never stored).
+ *   cost = norm · mean_{ij} BCEwithLogits(z_i·z_j, L_ij, pos_weight=L_ij·pw)
+ *   L = A + I given as CSR (rowptr/colidx, unit entries; diagonal included)
+ *   KLD  = -0.5/n · mean_i Σ_d (1 + 2·logvar - mu² - exp(logvar)²)
+ *   loss_out[0] = cost + KLD ; dz [n,d] dense, dmu/dlogvar [n,d] with leading
+ *   dimension ldd are OVERWRITTEN with d loss / d z (decoder part) and the KLD
+ *   parts respectively.  L must be symmetric (it always is: scgnn2.py:658-664).
+ *   mu/logvar may be NULL (plain GAE: cost only).
+ *   When use_pos_weight == 0 computes loss_function (scgnn2.py:618-619):
+ *   plain mean BCE (GAT branch), norm ignored. */
+size_t b2_gae_loss_workspace_bytes(int32_t n, int32_t d);
+int b2_gae_loss_grad_f32(const float* z, int64_t ldz, const float* mu, const float* logvar, int64_t ldm,
+                         const int32_t* lab_rowptr, const int32_t* lab_colidx,
+                         int32_t n, int32_t d, float norm, float pos_weight, int use_pos_weight,
+                         float* dz, float* dmu, float* dlogvar, int64_t ldd, float* loss_out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Optimiser: torch.optim.Adam semantics (scgnn2.py:301,573; default eps 1e-8,
+ * betas (0.9,0.999), no amsgrad, L2 weight_decay added to grad).
+ * `step` is the 1-based step count AFTER this update.
+ * ---------------------------------------------------------------------- */
+int b2_adam_step_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                     int64_t n, float lr, float beta1, float beta2, float eps,
+                     float weight_decay, int32_t step, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Elementwise helpers on the GCN path
+ * ---------------------------------------------------------------------- */
+/* out = grad ⊙ (y > 0)   (ReLU backward; in-place allowed) */
+int b2_relu_bwd_f32(const float* grad, const float* y, float* out, int64_t n, void* stream);
+/* z = mu + eps ⊙ exp(logvar)  (Graph_AE.reparameterize, scgnn2.py:394-400); [n,d] with leading dims */
+int b2_reparam_fwd_f32(const float* mu, const float* logvar, int64_t ldm, const float* eps, int64_t lde,
+                       float* z, int64_t ldz, int64_t n, int32_t d, void* stream);
+/* dmu += dz ; dlogvar += dz ⊙ eps ⊙ exp(logvar) */
+int b2_reparam_bwd_f32(const float* dz, int64_t lddz, const float* logvar, int64_t ldm, const float* eps, int64_t lde,
+                       float* dmu, float* dlogvar, int64_t ldd, int64_t n, int32_t d, void* stream);
+
+/* ------------------------------------------------------------------------
+ * K7  exact k-nearest-neighbour search (euclidean)
+ * replaces: calculateKNNgraphDistanceMatrixStatsSingleThread scgnn2.py:675-689
+ *           (scipy cdist in fp64 + argsort, ranks 1..k), NeighborGraph
+ *           (neighbor_graph.py:50-57), StagateGraph kNN (spatial_graph.py:147-149)
+ *   X [n,d] fp32 reference set (queries = rows q_begin..q_end of the same set)
+ *   idx_out  [n_q, k] int32 — neighbours sorted by (fp64 distance, index)
+ *   dist_out [n_q, k] fp64 euclidean distances (may be NULL)
+ *   include_rank0 = 0: drop sorted rank 0 (the reference's "self" slot) and
+ *   return ranks 1..k; 1: return ranks 0..k-1.
+ *   Distances are ranked in fp64 exactly like the reference; ties broken by
+ *   the smaller index.
+ * ---------------------------------------------------------------------- */
+size_t b2_knn_workspace_bytes(int32_t n, int32_t d, int32_t k, int32_t n_queries);
+int b2_knn_l2_f32(const float* X, int64_t ldx, int32_t n, int32_t d, int32_t k,
+                  int32_t q_begin, int32_t q_end, int include_rank0,
+                  int32_t* idx_out, double* dist_out,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Dense pairwise euclidean distance matrix, fp32 (small N only)
+ * replaces: dance.utils.matrix.pairwise_distance (utils/matrix.py:164-180) */
+int b2_pairwise_l2_dense_f32(const float* X, int64_t ldx, int32_t n, int32_t d,
+                             float* D, int64_t ldd, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Graph assembly for scGNN: feature2adj (scgnn2.py:650-672, union-symmetrise,
+ * drop diagonal) + preprocess_graph (scgnn2.py:1191-1198,  Â = D^-1/2 (A+I) D^-1/2)
+ *   knn_idx [n,k] → CSR of (A ∪ Aᵀ) + I with sorted columns.
+ *   Two-phase: `count` returns nnz (host int64), then `fill` writes arrays.
+ *   vals_norm : Â values;  the same rowptr/colidx serve as the label matrix
+ *   L = A + I for b2_gae_loss_grad_f32.  Σ A (no diagonal) = nnz - n.
+ * ---------------------------------------------------------------------- */
+size_t b2_knn_graph_workspace_bytes(int32_t n, int32_t k);
+int b2_knn_graph_build(const int32_t* knn_idx, int32_t n, int32_t k,
+                       int32_t* rowptr /* n+1 */, int32_t* colidx /* cap */, float* vals_norm /* cap */,
+                       int64_t capacity, int64_t* nnz_out_host,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * K9  normalize_total (+ optional log1p), in place on dense X [n,g]
+ * replaces: scanpy.pp.normalize_total / log1p via AnnDataTransform
+ *           (transforms/interface.py:67-68), NormalizeTotal (normalize.py:569-628),
+ *           Log1P (normalize.py:531-564), NormalizeTotalLog1P (:664-679)
+ *   target_sum <= 0 → median of the (included-gene) totals over cells with
+ *   total > 0 (computed on device; this call then synchronises the stream).
+ *   max_fraction < 1 → genes that exceed that fraction of ANY cell's total are
+ *   excluded from the totals (scanpy exclude_highly_expressed).
+ *   Rows with total == 0 are left unchanged (scanpy ≥1.10.1).
+ *   do_log1p: 0 none, 1 natural log1p; base > 0 divides by ln(base).
+ * ---------------------------------------------------------------------- */
+size_t b2_normalize_total_workspace_bytes(int32_t n, int32_t g);
+int b2_normalize_total_log1p_f32(float* X, int64_t ldx, int32_t n, int32_t g,
+                                 float target_sum, float max_fraction,
+                                 int do_normalize, int do_log1p, float base,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DANCE_B200_H_ */

@@ -1,0 +1,157 @@
+"""Generate the golden fixtures in ``tests/golden/`` by running the REFERENCE's own code
+(through ``oracle.ref_loader``) on small seeded inputs.  TEST INFRASTRUCTURE.
+
+Run in the build container (needs ``/root/reference``):  ``python -m oracle.make_golden``
+The fixtures are committed; the GPU box never runs this script.
+"""
+from __future__ import annotations
+
+import warnings
+from pathlib import Path
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from . import port, ref_loader
+
+OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
+
+
+def _knn_graph_fixture(ref):
+    """feature2adj + preprocess_graph + gae constants (scgnn2.py:650-689,1191-1209,567-569)."""
+    X = port.synthetic_embedding(300, d=16, n_clusters=4, seed=11)
+    k = 10
+    adj, adj_train, edge_list = ref.feature2adj(X, k, False)
+    adj_train = sp.csr_matrix(adj_train)
+    adj_train.sort_indices()
+    knn_idx = np.array([e[1] for e in edge_list], dtype=np.int64).reshape(X.shape[0], k)
+    knn_w = np.array([e[2] for e in edge_list], dtype=np.float64).reshape(X.shape[0], k)
+    adj_norm = ref.preprocess_graph(adj_train).coalesce()
+    an = sp.csr_matrix((adj_norm.values().numpy(), adj_norm.indices().numpy()), shape=tuple(adj_norm.shape))
+    an.sort_indices()
+    n = X.shape[0]
+    pos_weight = float(n * n - adj_train.sum()) / adj_train.sum()
+    norm = n * n / float((n * n - adj_train.sum()) * 2)
+    np.savez_compressed(OUT / "knn_graph.npz", X=X, k=k, knn_idx=knn_idx, knn_w=knn_w,
+                        adj_indptr=adj_train.indptr, adj_indices=adj_train.indices,
+                        norm_indptr=an.indptr, norm_indices=an.indices, norm_data=an.data.astype(np.float32),
+                        pos_weight=pos_weight, norm=norm)
+    return X, adj_train, an, pos_weight, norm
+
+
+def _graph_ae_fixture(ref, X, adj_train, an, pos_weight, norm):
+    """Graph_AE GCN branch: forward, loss, gradients, one Adam step (scgnn2.py:373-412,479-502,555-595,603-615)."""
+    torch.manual_seed(3)
+    n = X.shape[0]
+    model = ref.Graph_AE(X.shape[1], 16, 0, 2, 64)
+    x = torch.from_numpy(X)
+    adj_t = ref.sparse_mx_to_torch_sparse_tensor(an)
+    labels = torch.from_numpy((adj_train + sp.eye(n)).toarray()).float()
+    w = {k: v.detach().clone().numpy() for k, v in model.state_dict().items() if k.startswith("gc")}
+    out = dict(w1=w["gc1.weight"], w2=w["gc2.weight"], w3=w["gc3.weight"])
+
+    # eval mode: z = mu
+    model.eval()
+    z, info, recon = model(x, adj_t, use_GAT=False)
+    out.update(eval_z=z.detach().numpy(), eval_mu=info[0].detach().numpy(), eval_logvar=info[1].detach().numpy())
+
+    # training mode with recorded noise
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    torch.manual_seed(5)
+    eps = torch.randn(n, 16)
+    torch.manual_seed(5)  # reparameterize draws randn_like(std) first thing → identical eps
+    opt.zero_grad()
+    z, info, recon = model(x, adj_t, use_GAT=False)
+    assert torch.allclose(z, eps * torch.exp(info[1]) + info[0])
+    loss = ref.gae_loss_function(preds=recon, labels=labels, mu=info[0], logvar=info[1], n_nodes=n, norm=norm,
+                                 pos_weight=pos_weight)
+    loss.backward()
+    out.update(eps=eps.numpy(), train_z=z.detach().numpy(), loss=np.float64(loss.item()),
+               g_w1=model.gc1.weight.grad.numpy().copy(), g_w2=model.gc2.weight.grad.numpy().copy(),
+               g_w3=model.gc3.weight.grad.numpy().copy())
+    opt.step()
+    out.update(w1_after=model.gc1.weight.detach().numpy().copy(), w2_after=model.gc2.weight.detach().numpy().copy(),
+               w3_after=model.gc3.weight.detach().numpy().copy())
+    # hidden1 for the layer-level check
+    hidden1 = ref.GraphConvolution(X.shape[1], 32, 0.)
+    with torch.no_grad():
+        hidden1.weight.copy_(torch.from_numpy(out["w1"]))
+        out["hidden1"] = hidden1(x, adj_t).numpy()
+    np.savez_compressed(OUT / "graph_ae_gcn.npz", **out)
+
+
+def sample_index(size: int) -> np.ndarray:
+    """Fixed pseudo-random sample of flat indices used to spot-check large tensors."""
+    return np.sort(np.random.default_rng(size).choice(size, size=min(2000, size), replace=False))
+
+
+def _sample(a: np.ndarray) -> np.ndarray:
+    return a.reshape(-1)[sample_index(a.size)].copy()
+
+
+def _feature_ae_fixture(ref):
+    """Feature_AE + train_handler/loss_function_graph: two optimiser steps on two batches
+    (scgnn2.py:338-370,1217-1315).  dim kept small (32) and post-step weights / gradients stored as
+    a fixed 2000-element sample + Frobenius norm per tensor so the fixture stays small."""
+    torch.manual_seed(7)
+    n, g, bs = 160, 32, 80
+    X = port.synthetic_expression(n, g, density=0.3, seed=2)
+    model = ref.Feature_AE(dim=g)
+    init = {k: v.detach().clone().numpy() for k, v in model.state_dict().items()}
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    loader = torch.utils.data.DataLoader(ref.ExpressionDataset(X), batch_size=bs)
+    trs = torch.zeros(n, g)
+    param = {"device": "cpu", "epoch_num": 0, "total_epoch": 1, "n_feature_orig": g}
+    import logging
+    logging.getLogger("dance-ref-stub").setLevel(logging.WARNING)
+    _, z_all, recon_all = ref.train_handler(model=model, train_loader=loader, optimizer=opt, TRS=trs, total_epoch=1,
+                                            impute_regu=None, regu_type=["LTMG", "noregu"], regu_strength=0.9,
+                                            masked_prob=0, param=param)
+    after = {k: v.detach().clone().numpy() for k, v in model.state_dict().items()}
+    out = {"X": X, "batch_size": bs, "regu_strength": 0.9, "z_all": z_all.detach().numpy(),
+           "recon_all": recon_all.detach().numpy()}
+    out.update({f"init.{k}": v for k, v in init.items()})
+    for k, v in after.items():
+        out[f"after.{k}.sample"], out[f"after.{k}.norm"] = _sample(v), np.float64(np.linalg.norm(v.astype(np.float64)))
+    # single-batch forward/loss/grad snapshot ("noregu" and "LTMG") from the initial weights
+    m2 = ref.Feature_AE(dim=g)
+    m2.load_state_dict({k: torch.from_numpy(v) for k, v in init.items()})
+    xb = torch.from_numpy(X[:bs])
+    z, recon = m2(xb)
+    loss = ref.loss_function_graph(recon, xb.clone(), regulationMatrix={"LTMG_regu": trs[:bs]}, regu_strength=0.9,
+                                   regularizer_type="LTMG", param=param)
+    loss.backward()
+    out.update(b0_z=z.detach().numpy(), b0_recon=recon.detach().numpy(), b0_loss_ltmg=np.float64(loss.item()))
+    for k, p in m2.named_parameters():
+        gnp = p.grad.numpy()
+        out[f"b0_grad.{k}.sample"], out[f"b0_grad.{k}.norm"] = _sample(gnp), np.float64(np.linalg.norm(gnp.astype(np.float64)))
+    np.savez_compressed(OUT / "feature_ae.npz", **out)
+
+
+def _matrix_fixture():
+    """utils/matrix.py pairwise_distance (numba) on a seeded 40×7 matrix."""
+    mx = ref_loader.matrix()
+    X = np.random.default_rng(4).normal(size=(40, 7)).astype(np.float32)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        D = mx.pairwise_distance(X, 0)
+    np.savez_compressed(OUT / "pairwise.npz", X=X, D=D)
+
+
+def main():
+    OUT.mkdir(parents=True, exist_ok=True)
+    ref = ref_loader.scgnn2()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        X, adj_train, an, pw, norm = _knn_graph_fixture(ref)
+        _graph_ae_fixture(ref, X, adj_train, an, pw, norm)
+        _feature_ae_fixture(ref)
+        _matrix_fixture()
+    for f in sorted(OUT.glob("*.npz")):
+        print(f.name, f.stat().st_size)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,296 @@
+"""CPU restatement ("port") of the reference's algorithm for the scGNN message-passing
+hot path.  TEST INFRASTRUCTURE: imported only by ``tests/``, ``__graft_entry__.smoke()``
+and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py``.
+
+Each function cites the reference file:line it follows (paths relative to the
+reference repository root).  Parity status: PINNED — every function here is checked
+against the reference's own code executed through ``oracle.ref_loader`` (in the build
+container, ``tests/test_oracle_vs_reference.py``) and against the committed fixtures in
+``tests/golden/`` generated from that reference (``oracle/make_golden.py``); the
+normalize / distance functions are additionally pinned by the reference's own
+known-answer tests (tests/utils/test_matrix.py, tests/transforms/test_normalize.py).
+
+Implementation language: numpy / scipy / torch-CPU, i.e. the same libraries the
+reference's CPU path runs on, so timing it is timing the reference's CPU arithmetic.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+import torch.nn.functional as F
+from scipy.spatial import distance
+
+
+# --------------------------------------------------------------------------- kNN graph
+def knn_indices(X: np.ndarray, k: int, block: int = 1024, return_dist: bool = False):
+    """Sorted ranks 1..k of every row under fp64 euclidean distance.
+
+    Follows calculateKNNgraphDistanceMatrixStatsSingleThread (scgnn2.py:675-689): per row
+    ``distance.cdist(row, X, "euclidean")`` (fp64 on the fp32 features), ``argsort``, take
+    ``res[0][1..k]``.  Rows are processed in blocks (identical per-pair arithmetic) and the
+    argsort is made tie-stable (``kind="stable"`` → ties by smaller index; the reference's
+    quicksort leaves tie order unspecified).
+    """
+    n = X.shape[0]
+    idx = np.empty((n, k), dtype=np.int64)
+    dist = np.empty((n, k), dtype=np.float64) if return_dist else None
+    for i0 in range(0, n, block):
+        d = distance.cdist(X[i0:i0 + block], X, "euclidean")
+        order = np.argsort(d, axis=1, kind="stable")[:, 1:k + 1]
+        idx[i0:i0 + block] = order
+        if return_dist:
+            dist[i0:i0 + block] = np.take_along_axis(d, order, axis=1)
+    return (idx, dist) if return_dist else idx
+
+
+def feature2adj(X_embed: np.ndarray, neighborhood_factor, block: int = 1024):
+    """feature2adj with retain_weights=False (scgnn2.py:650-672).
+
+    Returns (adj_train CSR 0/1 symmetric without diagonal, knn index array).  The reference
+    goes through networkx ``from_dict_of_lists`` (undirected ⇒ union-symmetrised, rows in
+    natural order, App. B) and then clears the diagonal; the same matrix is built here with
+    scipy.
+    """
+    n = X_embed.shape[0]
+    k_tmp = neighborhood_factor if neighborhood_factor > 1 else round(n * neighborhood_factor)
+    k = int(k_tmp - 1 if k_tmp == n else k_tmp)
+    idx = knn_indices(X_embed, k, block=block)
+    rows = np.repeat(np.arange(n, dtype=np.int64), k)
+    cols = idx.reshape(-1)
+    a = sp.csr_matrix((np.ones(rows.size, dtype=np.float64), (rows, cols)), shape=(n, n))
+    a = a + a.T
+    a.data[:] = 1.0
+    a.setdiag(0)
+    a.eliminate_zeros()
+    a.sort_indices()
+    return a.tocsr(), idx
+
+
+def preprocess_graph(adj_train: sp.spmatrix) -> sp.csr_matrix:
+    """Â = D^-1/2 (A + I) D^-1/2 as fp32 CSR with sorted columns (scgnn2.py:1191-1198,1205)."""
+    adj = sp.coo_matrix(adj_train)
+    adj_ = adj + sp.eye(adj.shape[0])
+    rowsum = np.array(adj_.sum(1))
+    d_inv_sqrt = sp.diags(np.power(rowsum, -0.5).flatten())
+    out = adj_.dot(d_inv_sqrt).transpose().dot(d_inv_sqrt).tocsr().astype(np.float32)
+    out.sort_indices()
+    return out
+
+
+def gae_norm_constants(adj_train: sp.spmatrix) -> Tuple[float, float]:
+    """pos_weight and norm of graph_AE_handler (scgnn2.py:567-569)."""
+    n = adj_train.shape[0]
+    s = adj_train.sum()
+    pos_weight = float(n * n - s) / s
+    norm = n * n / float((n * n - s) * 2)
+    return pos_weight, norm
+
+
+def to_torch_sparse(m: sp.spmatrix) -> torch.Tensor:
+    """sparse_mx_to_torch_sparse_tensor (scgnn2.py:1201-1209)."""
+    m = m.tocoo().astype(np.float32)
+    idx = torch.from_numpy(np.vstack((m.row, m.col)).astype(np.int64))
+    return torch.sparse_coo_tensor(idx, torch.from_numpy(m.data), torch.Size(m.shape)).coalesce()
+
+
+# --------------------------------------------------------------------------- Graph AE (GCN branch)
+def graph_conv(x: torch.Tensor, weight: torch.Tensor, adj: torch.Tensor, act=None) -> torch.Tensor:
+    """GraphConvolution.forward with dropout 0 (scgnn2.py:497-502)."""
+    support = torch.mm(x, weight)
+    out = torch.spmm(adj, support)
+    return act(out) if act is not None else out
+
+
+def gae_loss(preds, labels, mu, logvar, n_nodes, norm, pos_weight):
+    """gae_loss_function (scgnn2.py:603-615)."""
+    cost = norm * F.binary_cross_entropy_with_logits(preds, labels, pos_weight=labels * pos_weight)
+    if logvar is None:
+        return cost
+    kld = -0.5 / n_nodes * torch.mean(torch.sum(1 + 2 * logvar - mu.pow(2) - logvar.exp().pow(2), 1))
+    return cost + kld
+
+
+def graph_ae_gcn_forward(x, w1, w2, w3, adj, eps: Optional[torch.Tensor]):
+    """Graph_AE.forward with use_GAT=False (scgnn2.py:389-412): returns (z, mu, logvar, hidden1).
+
+    ``eps`` is the reparameterisation noise (``torch.randn_like(std)``, scgnn2.py:397); pass
+    None for eval mode (z = mu).
+    """
+    hidden1 = graph_conv(x, w1, adj, F.relu)
+    mu = graph_conv(hidden1, w2, adj)
+    logvar = graph_conv(hidden1, w3, adj)
+    z = mu if eps is None else eps.mul(torch.exp(logvar)).add(mu)
+    return z, mu, logvar, hidden1
+
+
+def graph_ae_gcn_loss(x, w1, w2, w3, adj_norm_sp: sp.spmatrix, adj_train: sp.spmatrix, eps=None, dense_labels=True):
+    """One forward of the GCN branch of graph_AE_handler (scgnn2.py:555-590): loss + tensors.
+
+    The label matrix is the dense (A + I) of scgnn2.py:557 — only feasible for small n.
+    """
+    n = x.shape[0]
+    adj = to_torch_sparse(adj_norm_sp)
+    pos_weight, norm = gae_norm_constants(adj_train)
+    z, mu, logvar, hidden1 = graph_ae_gcn_forward(x, w1, w2, w3, adj, eps)
+    labels = torch.from_numpy((adj_train + sp.eye(n)).toarray()).float()
+    preds = torch.mm(z, z.t())  # InnerProductDecoder, identity activation (scgnn2.py:423-426)
+    loss = gae_loss(preds, labels, mu, logvar, n, norm, pos_weight)
+    return loss, z, mu, logvar, hidden1
+
+
+# --------------------------------------------------------------------------- Feature AE
+class FeatureAE(torch.nn.Module):
+    """Feature_AE (scgnn2.py:338-370): dim→512→128→512→dim, ReLU after every layer."""
+
+    def __init__(self, dim: int):
+        super().__init__()
+        self.dim = dim
+        self.fc1 = torch.nn.Linear(dim, 512)
+        self.fc2 = torch.nn.Linear(512, 128)
+        self.fc3 = torch.nn.Linear(128, 512)
+        self.fc4 = torch.nn.Linear(512, dim)
+
+    def forward(self, x):
+        z = F.relu(self.fc2(F.relu(self.fc1(x.view(-1, self.dim)))))
+        return z, F.relu(self.fc4(F.relu(self.fc3(z))))
+
+
+def feature_ae_loss(recon, x, regularizer_type="noregu", regu_strength=0.9, ltmg=None):
+    """loss_function_graph, branches 'noregu' and 'LTMG' (scgnn2.py:1298-1315)."""
+    bce = F.mse_loss(recon, x, reduction="sum")
+    if regularizer_type == "noregu":
+        return bce
+    if regularizer_type == "LTMG":
+        return (1 - regu_strength) * bce + regu_strength * (F.mse_loss(recon, x, reduction="none") * ltmg).sum()
+    raise ValueError(regularizer_type)
+
+
+def feature_ae_epoch(model: FeatureAE, optimizer, X: torch.Tensor, batch_size: int, regularizer_type="LTMG",
+                     regu_strength=0.9, ltmg: Optional[torch.Tensor] = None):
+    """One epoch of train_handler with masked_prob = 0 (scgnn2.py:1254-1293); returns
+    (sum of batch losses, z_all, recon_all)."""
+    model.train()
+    total = 0.0
+    zs, rs = [], []
+    n = X.shape[0]
+    for b0 in range(0, n, batch_size):
+        data = X[b0:b0 + batch_size]
+        t = ltmg[b0:b0 + batch_size] if ltmg is not None else torch.zeros_like(data)
+        optimizer.zero_grad()
+        z, recon = model(data)
+        loss = feature_ae_loss(recon, data, regularizer_type, regu_strength, t)
+        loss.backward()
+        total += loss.item()
+        optimizer.step()
+        zs.append(z.detach())
+        rs.append(recon.detach())
+    return total, torch.cat(zs, 0), torch.cat(rs, 0)
+
+
+# --------------------------------------------------------------------------- preprocessing
+def normalize_total(X: np.ndarray, target_sum: Optional[float] = None, exclude_highly_expressed: bool = False,
+                    max_fraction: float = 0.05) -> np.ndarray:
+    """scanpy.pp.normalize_total 1.10.1 on a dense matrix (called at
+    transforms/normalize.py:618-620 and through AnnDataTransform, interface.py:67-68).
+    Pinned by the reference's tests/transforms/test_normalize.py:8-30."""
+    X = np.array(X, dtype=np.float32, copy=True)
+    counts = X.sum(1)
+    if exclude_highly_expressed:
+        hi = (X > counts[:, None] * max_fraction).sum(0) > 0
+        counts = X[:, ~hi].sum(1)
+    if target_sum is None:
+        target_sum = np.median(counts[counts > 0], axis=0)
+    scale = counts / target_sum
+    scale = scale + (scale == 0)  # zero-count cells are left unchanged (scanpy >= 1.10.1)
+    return (X / scale[:, None]).astype(np.float32)
+
+
+def log1p(X: np.ndarray, base: Optional[float] = None) -> np.ndarray:
+    """scanpy.pp.log1p (called at transforms/normalize.py:563); pinned by test_normalize.py:33-43."""
+    out = np.log1p(np.asarray(X, dtype=np.float32))
+    if base is not None:
+        out = out / np.float32(np.log(base))
+    return out
+
+
+def pairwise_euclidean(X: np.ndarray) -> np.ndarray:
+    """dance.utils.matrix.pairwise_distance(x, 0) (utils/matrix.py:100-105,164-180): per pair
+    (a-b)² in fp32, accumulated in fp64 (numba unifies ``sum = 0`` with the fp32 terms to
+    float64), sqrt, cast to fp32."""
+    X = np.asarray(X, dtype=np.float32)
+    diff = X[:, None, :] - X[None, :, :]
+    sq = (diff * diff).astype(np.float32)
+    s = np.zeros(sq.shape[:2], dtype=np.float64)
+    for c in range(X.shape[1]):  # sequential accumulation order of the numba loop
+        s += sq[:, :, c].astype(np.float64)
+    return np.sqrt(s).astype(np.float32)
+
+
+def matrix_normalize(mat: np.ndarray, mode: str = "normalize", axis: int = 0, eps: float = -1.0) -> np.ndarray:
+    """dance.utils.matrix.normalize (utils/matrix.py:8-67); pinned by tests/utils/test_matrix.py:9-29."""
+    opts = {"axis": axis, "keepdims": True}
+    shift = 0
+    if mode == "standardize":
+        shift = -mat.mean(**opts)
+    elif mode == "minmax":
+        min_vals = mat.min(**opts)
+        shift = -min_vals
+    if mode == "normalize":
+        denom = mat.sum(**opts)
+    elif mode == "standardize":
+        denom = mat.std(**opts)
+    elif mode == "minmax":
+        denom = mat.max(**opts) - min_vals
+    elif mode == "l2":
+        denom = (mat**2).sum(**opts)**0.5
+    else:
+        denom = None
+    if denom is None:
+        denom = 1
+    elif eps == -1:
+        denom = np.where(denom == 0, 1, denom)
+    elif eps > 0:
+        denom = denom + eps
+    else:
+        raise ValueError(f"Invalid {eps=!r}. Must be positive or -1, the later set zero entries to one.")
+    return (mat + shift) / denom
+
+
+# --------------------------------------------------------------------------- synthetic data
+def synthetic_embedding(n: int, d: int = 128, n_clusters: int = 10, seed: int = 0) -> np.ndarray:
+    """Z[N,d]: mixture of `n_clusters` unit-variance Gaussians, centres ~ N(0, 3²)."""
+    rng = np.random.default_rng(seed)
+    centres = rng.normal(0.0, 3.0, size=(n_clusters, d))
+    lab = rng.integers(0, n_clusters, size=n)
+    return (centres[lab] + rng.normal(0.0, 1.0, size=(n, d))).astype(np.float32)
+
+
+def synthetic_expression(n: int, g: int, density: float = 0.10, n_types: int = 10, seed: int = 0,
+                         log_normalize: bool = True) -> np.ndarray:
+    """Cell×gene matrix: NB counts (dispersion 0.5), log-normal gene means / size factors,
+    `n_types` latent types shifting 5 % of the genes ×4, Bernoulli dropout to `density`."""
+    rng = np.random.default_rng(seed)
+    mu_g = rng.lognormal(0.0, 1.0, size=g)
+    s_c = rng.lognormal(0.0, 0.5, size=n)
+    types = rng.integers(0, n_types, size=n)
+    shift = np.ones((n_types, g))
+    for t in range(n_types):
+        shift[t, rng.choice(g, size=max(1, g // 20), replace=False)] = 4.0
+    out = np.empty((n, g), dtype=np.float32)
+    r = 2.0  # NB "size" = 1/dispersion
+    for i0 in range(0, n, 16384):
+        i1 = min(n, i0 + 16384)
+        mean = s_c[i0:i1, None] * mu_g[None, :] * shift[types[i0:i1]]
+        lam = rng.gamma(shape=r, scale=mean / r)
+        cnt = rng.poisson(lam).astype(np.float32)
+        nz = (cnt > 0).mean()
+        keep = min(1.0, density / max(nz, 1e-9))
+        cnt *= rng.random(cnt.shape) < keep
+        out[i0:i1] = cnt
+    if log_normalize:
+        out = log1p(normalize_total(out, target_sum=1e4))
+    return out

@@ -1,0 +1,160 @@
+"""Pin the oracle (oracle/port.py): against the reference's own known-answer tests, against the
+committed fixtures generated from the reference (tests/golden, oracle/make_golden.py) and — when
+/root/reference is present (build container) — against the reference code executed live."""
+import itertools
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.spatial
+import torch
+
+from oracle import port, ref_loader
+
+from conftest import rel_err
+
+
+# ---- the reference's own golden vectors ------------------------------------------------------
+def test_matrix_normalize_known_answers():
+    # reference tests/utils/test_matrix.py:9-29
+    mat = np.array([[1, 1], [4, 4]])
+    assert port.matrix_normalize(mat, mode="normalize", axis=0).tolist() == [[0.2, 0.2], [0.8, 0.8]]
+    assert port.matrix_normalize(mat, mode="normalize", axis=1).tolist() == [[0.5, 0.5], [0.5, 0.5]]
+    assert port.matrix_normalize(mat, mode="standardize", axis=0).tolist() == [[-1, -1], [1, 1]]
+    assert port.matrix_normalize(mat, mode="standardize", axis=1).tolist() == [[0, 0], [0, 0]]
+    assert port.matrix_normalize(mat, mode="minmax", axis=0).tolist() == [[0, 0], [1, 1]]
+    assert port.matrix_normalize(mat, mode="minmax", axis=1).tolist() == [[0, 0], [0, 0]]
+    assert port.matrix_normalize(mat, mode="l2", axis=0).tolist() == (mat / np.sqrt((mat**2).sum(0))).tolist()
+    assert port.matrix_normalize(mat, mode="l2", axis=1).tolist() == (mat / np.sqrt((mat**2).sum(1, keepdims=True))).tolist()
+
+
+REF_DIST_MAT = np.array([[0, 1, 2], [2, 2, 4], [5, 3, 5], [3, 2, 1], [5, 6, 3]], dtype=np.float32)
+
+
+def test_pairwise_euclidean_known_answers():
+    # reference tests/utils/test_matrix.py:32-52
+    n = REF_DIST_MAT.shape[0]
+    ans = np.zeros((n, n), dtype=np.float32)
+    for i, j in itertools.product(range(n), range(n)):
+        ans[i, j] = scipy.spatial.distance.euclidean(REF_DIST_MAT[i], REF_DIST_MAT[j])
+    assert np.allclose(ans, port.pairwise_euclidean(REF_DIST_MAT))
+
+
+def test_normalize_total_known_answers(assert_ary_isclose):
+    # reference tests/transforms/test_normalize.py:8-30 (NormalizeTotal → exclude_highly_expressed=True)
+    x = np.array([[1, 1, 1], [1, 1, 1], [3, 0, 0]], dtype=np.float32)
+    out = port.normalize_total(x, target_sum=30, exclude_highly_expressed=True, max_fraction=0.99)
+    assert_ary_isclose(out, np.array([[15.0, 15.0, 15.0], [15.0, 15.0, 15.0], [3.0, 0.0, 0.0]]))
+    out = port.normalize_total(out, target_sum=30, exclude_highly_expressed=True, max_fraction=1.0)
+    assert_ary_isclose(out, np.array([[10.0, 10.0, 10.0], [10.0, 10.0, 10.0], [30.0, 0.0, 0.0]]))
+
+
+def test_log1p_known_answers(assert_ary_isclose):
+    # reference tests/transforms/test_normalize.py:33-43
+    x = np.array([[1, 1, 1], [1, 1, 1], [3, 0, 0]])
+    assert_ary_isclose(port.log1p(x), np.log1p(x))
+
+
+# ---- committed fixtures generated from the reference --------------------------------------------
+def test_pairwise_golden(golden):
+    g = golden("pairwise")
+    assert np.array_equal(port.pairwise_euclidean(g["X"]), g["D"])  # bit-exact vs the numba kernel
+
+
+def test_knn_graph_golden(golden):
+    g = golden("knn_graph")
+    X, k = g["X"], int(g["k"])
+    idx, dist = port.knn_indices(X, k, return_dist=True)
+    assert np.array_equal(idx, g["knn_idx"])                      # neighbour indices: bit-exact
+    assert np.array_equal(1 / (dist + 1e-16), g["knn_w"])         # fp64 weights 1/(d+1e-16): bit-exact
+    adj, _ = port.feature2adj(X, k)
+    assert np.array_equal(adj.indptr, g["adj_indptr"]) and np.array_equal(adj.indices, g["adj_indices"])
+    an = port.preprocess_graph(adj)
+    assert np.array_equal(an.indptr, g["norm_indptr"]) and np.array_equal(an.indices, g["norm_indices"])
+    assert np.array_equal(an.data, g["norm_data"])
+    pw, norm = port.gae_norm_constants(adj)
+    assert pw == float(g["pos_weight"]) and norm == float(g["norm"])
+
+
+def _graph_inputs(golden):
+    g = golden("knn_graph")
+    adj = sp.csr_matrix((np.ones(len(g["adj_indices"])), g["adj_indices"], g["adj_indptr"]), shape=(len(g["X"]),) * 2)
+    an = sp.csr_matrix((g["norm_data"], g["norm_indices"], g["norm_indptr"]), shape=adj.shape)
+    return g["X"], adj, an
+
+
+def test_graph_ae_golden(golden):
+    X, adj, an = _graph_inputs(golden)
+    g = golden("graph_ae_gcn")
+    x = torch.from_numpy(X)
+    w = [torch.from_numpy(g[k]).requires_grad_() for k in ("w1", "w2", "w3")]
+    loss, z, mu, logvar, hidden1 = port.graph_ae_gcn_loss(x, *w, an, adj, eps=torch.from_numpy(g["eps"]))
+    loss.backward()
+    assert rel_err(hidden1.detach().numpy(), g["hidden1"]) < 1e-6
+    assert rel_err(z.detach().numpy(), g["train_z"]) < 1e-6
+    assert abs(loss.item() - float(g["loss"])) < 1e-6 * abs(float(g["loss"]))
+    for wi, key in zip(w, ("g_w1", "g_w2", "g_w3")):
+        assert rel_err(wi.grad.numpy(), g[key]) < 1e-5
+    _, z_eval, mu_eval, lv_eval, _ = port.graph_ae_gcn_loss(x, *[wi.detach() for wi in w], an, adj, eps=None)
+    assert rel_err(z_eval.numpy(), g["eval_z"]) < 1e-6 and rel_err(lv_eval.numpy(), g["eval_logvar"]) < 1e-6
+
+
+def _load_feature_ae(g):
+    dim = g["X"].shape[1]
+    model = port.FeatureAE(dim)
+    model.load_state_dict({k[len("init."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("init.")})
+    return model
+
+
+def test_feature_ae_golden(golden):
+    from oracle.make_golden import sample_index
+    g = golden("feature_ae")
+    X = torch.from_numpy(g["X"])
+    bs = int(g["batch_size"])
+    model = _load_feature_ae(g)
+    z, recon = model(X[:bs])
+    loss = port.feature_ae_loss(recon, X[:bs], "LTMG", float(g["regu_strength"]), torch.zeros(bs, X.shape[1]))
+    loss.backward()
+    assert rel_err(z.detach().numpy(), g["b0_z"]) < 1e-6 and rel_err(recon.detach().numpy(), g["b0_recon"]) < 1e-6
+    assert abs(loss.item() - float(g["b0_loss_ltmg"])) <= 1e-6 * abs(float(g["b0_loss_ltmg"]))
+    for k, p in model.named_parameters():
+        gnp = p.grad.numpy()
+        assert np.allclose(gnp.reshape(-1)[sample_index(gnp.size)], g[f"b0_grad.{k}.sample"], rtol=1e-4, atol=1e-6)
+        assert abs(np.linalg.norm(gnp.astype(np.float64)) - float(g[f"b0_grad.{k}.norm"])) < 1e-5 * float(g[f"b0_grad.{k}.norm"])
+    # one full epoch (two optimiser steps) of train_handler
+    model = _load_feature_ae(g)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    _, z_all, recon_all = port.feature_ae_epoch(model, opt, X, bs, "LTMG", float(g["regu_strength"]))
+    assert rel_err(z_all.numpy(), g["z_all"]) < 1e-5 and rel_err(recon_all.numpy(), g["recon_all"]) < 1e-5
+    for k, v in model.state_dict().items():
+        v = v.numpy()
+        assert np.allclose(v.reshape(-1)[sample_index(v.size)], g[f"after.{k}.sample"], rtol=1e-4, atol=1e-6)
+
+
+# ---- live against the reference (build container only) -----------------------------------------
+needs_ref = pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
+
+
+@needs_ref
+def test_port_vs_live_reference_knn_graph():
+    ref = ref_loader.scgnn2()
+    X = port.synthetic_embedding(257, d=24, n_clusters=5, seed=3)
+    for k in (3, 15):
+        _, adj_train_ref, edges = ref.feature2adj(X, k, False)
+        adj, idx = port.feature2adj(X, k)
+        assert np.array_equal(idx.reshape(-1), np.array([e[1] for e in edges]))
+        assert (sp.csr_matrix(adj_train_ref) != adj).nnz == 0
+        an_ref = ref.preprocess_graph(adj_train_ref).coalesce()
+        an = port.preprocess_graph(adj).tocoo()
+        assert np.array_equal(an_ref.values().numpy(), an.data)
+        assert np.array_equal(an_ref.indices().numpy(), np.vstack((an.row, an.col)))
+
+
+@needs_ref
+def test_port_vs_live_reference_fractional_neighbourhood():
+    # neighborhood_factor <= 1 means a fraction of N (scgnn2.py:651-654); default 0.05
+    ref = ref_loader.scgnn2()
+    X = port.synthetic_embedding(120, d=8, n_clusters=3, seed=9)
+    _, adj_train_ref, _ = ref.feature2adj(X, 0.05, False)
+    adj, idx = port.feature2adj(X, 0.05)
+    assert idx.shape[1] == 6 and (sp.csr_matrix(adj_train_ref) != adj).nnz == 0
