@@ -14,6 +14,7 @@ void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 int sm_count();
 const char* last_error();
+extern long long g_launch_count;   // kernels launched by this library (process-wide; see b2_launch_count)
 
 #define B2_CHECK_CUDA(expr)                                   \
   do {                                                        \
@@ -23,6 +24,7 @@ const char* last_error();
 
 #define B2_CHECK_LAUNCH(name)                                 \
   do {                                                        \
+    ++b2::g_launch_count;                                     \
     cudaError_t _e = cudaGetLastError();                      \
     if (_e != cudaSuccess) return b2::cuda_fail(_e, name);    \
   } while (0)

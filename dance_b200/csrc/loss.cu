@@ -61,15 +61,15 @@ constexpr int GL_JT = 128;     // j-tile staged in shared memory
 
 template <int D>
 __global__ void __launch_bounds__(GL_ROWS)
-gae_allpairs_kernel(const float* __restrict__ z, int64_t ldz, int32_t n, int32_t j_chunk, float coef,
-                    float* __restrict__ dz, double* __restrict__ loss_acc) {
+gae_allpairs_kernel(const float* __restrict__ z, int64_t ldz, int32_t n, int32_t row_begin, int32_t n_rows,
+                    int32_t j_chunk, float coef, float* __restrict__ dz, double* __restrict__ loss_acc) {
   __shared__ __align__(16) float zj[GL_JT][D];
-  const int i = blockIdx.x * GL_ROWS + threadIdx.x;
-  const bool live = i < n;
+  const int i = blockIdx.x * GL_ROWS + threadIdx.x;   // local row
+  const bool live = i < n_rows;
   float zi[D], acc[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) {
-    zi[d] = live ? z[(int64_t)i * ldz + d] : 0.f;
+    zi[d] = live ? z[(int64_t)(row_begin + i) * ldz + d] : 0.f;
     acc[d] = 0.f;
   }
   const int j_begin = blockIdx.y * j_chunk;
@@ -122,16 +122,16 @@ gae_allpairs_kernel(const float* __restrict__ z, int64_t ldz, int32_t n, int32_t
 template <int D>
 __global__ void __launch_bounds__(256)
 gae_edges_kernel(const float* __restrict__ z, int64_t ldz, const int32_t* __restrict__ rowptr,
-                 const int32_t* __restrict__ colidx, int32_t n, float coef, float pw, int use_pw,
+                 const int32_t* __restrict__ colidx, int32_t row_begin, int32_t n_rows, float coef, float pw, int use_pw,
                  float* __restrict__ dz, double* __restrict__ loss_acc) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   double loss = 0.0;
-  for (int64_t i = warp; i < n; i += nwarps) {
+  for (int64_t i = warp; i < n_rows; i += nwarps) {
     float zi[D], acc[D];
 #pragma unroll
-    for (int d = 0; d < D; ++d) { zi[d] = __ldg(z + i * ldz + d); acc[d] = 0.f; }
+    for (int d = 0; d < D; ++d) { zi[d] = __ldg(z + (row_begin + i) * ldz + d); acc[d] = 0.f; }
     const int32_t s = rowptr[i], e = rowptr[i + 1];
     for (int32_t p = s + lane; p < e; p += 32) {
       const int32_t j = colidx[p];
@@ -166,12 +166,12 @@ gae_edges_kernel(const float* __restrict__ z, int64_t ldz, const int32_t* __rest
 
 // KLD = -0.5/n · mean_i Σ_d (1 + 2·lv - mu² - exp(lv)²)        (scgnn2.py:614)
 __global__ void __launch_bounds__(256)
-gae_kld_kernel(const float* __restrict__ mu, const float* __restrict__ logvar, int64_t ldm, int32_t n, int32_t d,
-               float* __restrict__ dmu, float* __restrict__ dlogvar, int64_t ldd, double* __restrict__ loss_acc) {
+gae_kld_kernel(const float* __restrict__ mu, const float* __restrict__ logvar, int64_t ldm, int32_t n, int32_t n_rows,
+               int32_t d, float* __restrict__ dmu, float* __restrict__ dlogvar, int64_t ldd, double* __restrict__ loss_acc) {
   const double c = -0.5 / ((double)n * (double)n);
   const float cf = (float)c;
   double local = 0.0;
-  const int64_t total = (int64_t)n * d;
+  const int64_t total = (int64_t)n_rows * d;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = t / d;
     const int dd = (int)(t % d);
@@ -188,9 +188,9 @@ gae_kld_kernel(const float* __restrict__ mu, const float* __restrict__ logvar, i
 __global__ void gae_finish_kernel(const double* acc, float* loss_out) { loss_out[0] = (float)acc[0]; }
 
 template <int D>
-static int launch_gae(const float* z, int64_t ldz, const int32_t* rp, const int32_t* ci, int32_t n, float coef,
-                      float pw, int use_pw, float* dz, double* acc, cudaStream_t st) {
-  const int row_blocks = ceil_div(n, GL_ROWS);
+static int launch_gae(const float* z, int64_t ldz, const int32_t* rp, const int32_t* ci, int32_t n, int32_t row_begin,
+                      int32_t n_rows, float coef, float pw, int use_pw, float* dz, double* acc, cudaStream_t st) {
+  const int row_blocks = ceil_div(n_rows, GL_ROWS);
   // split the j range so that small graphs still fill the machine
   int j_splits = 1;
   const int target = sm_count() * 4;
@@ -200,12 +200,12 @@ static int launch_gae(const float* z, int64_t ldz, const int32_t* rp, const int3
   int j_chunk = ceil_div(ceil_div(n, j_splits), GL_JT) * GL_JT;
   j_splits = ceil_div(n, j_chunk);
   dim3 grid(row_blocks, j_splits);
-  gae_allpairs_kernel<D><<<grid, GL_ROWS, 0, st>>>(z, ldz, n, j_chunk, coef, dz, acc);
+  gae_allpairs_kernel<D><<<grid, GL_ROWS, 0, st>>>(z, ldz, n, row_begin, n_rows, j_chunk, coef, dz, acc);
   B2_CHECK_LAUNCH("gae_allpairs_kernel");
-  int64_t blocks = ceil_div<int64_t>(n, 8);
+  int64_t blocks = ceil_div<int64_t>(n_rows, 8);
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  gae_edges_kernel<D><<<(unsigned)blocks, 256, 0, st>>>(z, ldz, rp, ci, n, coef, pw, use_pw, dz, acc);
+  gae_edges_kernel<D><<<(unsigned)blocks, 256, 0, st>>>(z, ldz, rp, ci, row_begin, n_rows, coef, pw, use_pw, dz, acc);
   B2_CHECK_LAUNCH("gae_edges_kernel");
   return B2_OK;
 }
@@ -234,35 +234,37 @@ extern "C" size_t b2_gae_loss_workspace_bytes(int32_t n, int32_t d) { return 256
 
 extern "C" int b2_gae_loss_grad_f32(const float* z, int64_t ldz, const float* mu, const float* logvar, int64_t ldm,
                                     const int32_t* lab_rowptr, const int32_t* lab_colidx, int32_t n, int32_t d,
-                                    float norm, float pos_weight, int use_pos_weight, float* dz, float* dmu,
+                                    int32_t row_begin, int32_t n_rows, float norm, float pos_weight, int use_pos_weight, float* dz, float* dmu,
                                     float* dlogvar, int64_t ldd, float* loss_out, void* workspace,
                                     size_t workspace_bytes, void* stream) {
   B2_REQUIRE(z && lab_rowptr && lab_colidx && dz && loss_out, "b2_gae_loss_grad_f32: null pointer");
   B2_REQUIRE(n > 0 && d > 0 && ldz >= d, "b2_gae_loss_grad_f32: bad shape");
+  B2_REQUIRE(row_begin >= 0 && n_rows >= 0 && row_begin + n_rows <= n, "b2_gae_loss_grad_f32: bad row range");
   B2_REQUIRE(workspace && workspace_bytes >= 256, "b2_gae_loss_grad_f32: workspace too small");
   B2_REQUIRE((mu == nullptr) == (logvar == nullptr), "b2_gae_loss_grad_f32: mu/logvar must both be given or both NULL");
   if (mu) B2_REQUIRE(dmu && dlogvar && ldm >= d && ldd >= d, "b2_gae_loss_grad_f32: dmu/dlogvar required with mu/logvar");
   cudaStream_t st = as_stream(stream);
   double* acc = reinterpret_cast<double*>(workspace);
   B2_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), st));
-  B2_CHECK_CUDA(cudaMemsetAsync(dz, 0, sizeof(float) * (size_t)n * d, st));
+  B2_CHECK_CUDA(cudaMemsetAsync(dz, 0, sizeof(float) * (size_t)n_rows * d, st));
   const float coef = (use_pos_weight ? norm : 1.f) / ((float)n * (float)n);
   int rc;
   switch (d) {
-    case 8: rc = launch_gae<8>(z, ldz, lab_rowptr, lab_colidx, n, coef, pos_weight, use_pos_weight, dz, acc, st); break;
-    case 16: rc = launch_gae<16>(z, ldz, lab_rowptr, lab_colidx, n, coef, pos_weight, use_pos_weight, dz, acc, st); break;
-    case 32: rc = launch_gae<32>(z, ldz, lab_rowptr, lab_colidx, n, coef, pos_weight, use_pos_weight, dz, acc, st); break;
-    case 64: rc = launch_gae<64>(z, ldz, lab_rowptr, lab_colidx, n, coef, pos_weight, use_pos_weight, dz, acc, st); break;
+    case 8: rc = launch_gae<8>(z, ldz, lab_rowptr, lab_colidx, n, row_begin, n_rows, coef, pos_weight, use_pos_weight, dz, acc, st); break;
+    case 16: rc = launch_gae<16>(z, ldz, lab_rowptr, lab_colidx, n, row_begin, n_rows, coef, pos_weight, use_pos_weight, dz, acc, st); break;
+    case 32: rc = launch_gae<32>(z, ldz, lab_rowptr, lab_colidx, n, row_begin, n_rows, coef, pos_weight, use_pos_weight, dz, acc, st); break;
+    case 64: rc = launch_gae<64>(z, ldz, lab_rowptr, lab_colidx, n, row_begin, n_rows, coef, pos_weight, use_pos_weight, dz, acc, st); break;
     default:
       set_error("b2_gae_loss_grad_f32: embedding size %d unsupported (8, 16, 32, 64)", d);
       return B2_ERR_UNSUPPORTED;
   }
   if (rc != B2_OK) return rc;
   if (mu) {
-    int64_t blocks = ceil_div<int64_t>((int64_t)n * d, 256);
+    int64_t blocks = ceil_div<int64_t>((int64_t)n_rows * d, 256);
+    if (blocks < 1) blocks = 1;
     const int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    gae_kld_kernel<<<(unsigned)blocks, 256, 0, st>>>(mu, logvar, ldm, n, d, dmu, dlogvar, ldd, acc);
+    gae_kld_kernel<<<(unsigned)blocks, 256, 0, st>>>(mu, logvar, ldm, n, n_rows, d, dmu, dlogvar, ldd, acc);
     B2_CHECK_LAUNCH("gae_kld_kernel");
   }
   gae_finish_kernel<<<1, 1, 0, st>>>(acc, loss_out);

@@ -6,6 +6,7 @@
 namespace b2 {
 
 static thread_local char g_err[512] = "";
+long long g_launch_count = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -41,6 +42,8 @@ extern "C" {
 const char* b2_last_error(void) { return b2::last_error(); }
 
 int b2_version(void) { return 100; }
+
+int64_t b2_launch_count(void) { return (int64_t)b2::g_launch_count; }
 
 int b2_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;

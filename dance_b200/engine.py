@@ -226,14 +226,29 @@ class GraphAEEngine:
             self._bufs[n] = b
         return b
 
+    # -- cell-sharded execution ---------------------------------------------------
+    def set_sharding(self, comm, bounds):
+        """Row-shard the graph across ranks: this rank owns rows bounds[comm.rank] of Â (``adj`` passed
+        to forward/train_step is then the local row block, column ids global)."""
+        self.comm, self.bounds = comm, bounds
+
+    def _gather(self, local: torch.Tensor, key: str) -> torch.Tensor:
+        comm = getattr(self, "comm", None)
+        if comm is None or not comm.enabled:
+            return local
+        full = self._bufs.setdefault(("full", key, local.shape[1]),
+                                     torch.empty(self.bounds[-1][1], local.shape[1], dtype=torch.float32, device=self.device))
+        return comm.all_gather_rows(local, self.bounds, out=full)
+
     def forward(self, x: torch.Tensor, adj: CSR, eps: Optional[torch.Tensor] = None):
-        """Graph_AE.forward(use_GAT=False) (scgnn2.py:402-412): returns (z, mu, logvar); z = mu when eps is None."""
+        """Graph_AE.forward(use_GAT=False) (scgnn2.py:402-412): returns (z, mu, logvar); z = mu when eps is None.
+        Under sharding x / eps / outputs are the local rows."""
         P, pr, e = self.params.p, self.precision, self.emb
         b = self._buffers(x.shape[0])
         ops.gemm(x, P["gc1.weight"], out=b["s1"], precision=pr)          # support = input @ W      (scgnn2.py:499)
-        ops.spmm(adj, b["s1"], act="relu", out=b["h1"])                  # act(spmm(adj, support))  (scgnn2.py:500-501)
+        ops.spmm(adj, self._gather(b["s1"], "s1"), act="relu", out=b["h1"])   # act(spmm(adj, support)) (scgnn2.py:500-501)
         ops.gemm(b["h1"], P["gc23.weight"], out=b["s2"], precision=pr)
-        ops.spmm(adj, b["s2"], out=b["ml"])
+        ops.spmm(adj, self._gather(b["s2"], "s2"), out=b["ml"])
         mu, logvar = b["ml"][:, :e], b["ml"][:, e:]
         if eps is None:
             return mu, mu, logvar
@@ -244,19 +259,29 @@ class GraphAEEngine:
                    adj_t: Optional[CSR] = None):
         """One epoch of the graph_AE_handler loop (scgnn2.py:575-593): forward, gae_loss_function,
         backward, Adam.  ``adj_t`` = Âᵀ for the backward SpMMs; defaults to Â itself (the
-        preprocess_graph output is symmetric, scgnn2.py:1196).  Loss is left in ``self.loss``."""
+        preprocess_graph output is symmetric, scgnn2.py:1196).  Loss is left in ``self.loss``
+        (under sharding: all-reduced, so every rank holds the global value)."""
         P, G, pr, e = self.params.p, self.params.g, self.precision, self.emb
         adj_t = adj_t or adj
-        b = self._buffers(x.shape[0])
+        comm = getattr(self, "comm", None)
+        sharded = comm is not None and comm.enabled
+        n_loc = x.shape[0]
+        row_begin = self.bounds[comm.rank][0] if sharded else 0
+        b = self._buffers(n_loc)
         z, mu, logvar = self.forward(x, adj, eps)
         dmu, dlv = b["dml"][:, :e], b["dml"][:, e:]
-        ops.gae_loss_grad(z, labels, norm, pos_weight, mu, logvar, True, dz=b["dz"], dmu=dmu, dlogvar=dlv, loss=self.loss)
+        z_all = self._gather(z, "z")
+        ops.gae_loss_grad(z_all, labels, norm, pos_weight, mu, logvar, True, dz=b["dz"], dmu=dmu, dlogvar=dlv, loss=self.loss,
+                          row_begin=row_begin, n_rows=n_loc)
         ops.reparam_bwd(b["dz"], logvar, eps, dmu, dlv)                  # chain through z = mu + eps·exp(logvar)
-        ops.spmm(adj_t, b["dml"], out=b["ds2"])                          # d support2 = Âᵀ · d[mu|logvar]
+        ops.spmm(adj_t, self._gather(b["dml"], "dml"), out=b["ds2"])     # d support2 = Âᵀ · d[mu|logvar]
         ops.gemm(b["h1"], b["ds2"], transA=True, out=G["gc23.weight"], precision=pr)
         ops.gemm(b["ds2"], P["gc23.weight"], transB=True, mask=b["h1"], out=b["dh1"], precision=pr)  # ⊙ relu'(hidden1)
-        ops.spmm(adj_t, b["dh1"], out=b["ds1"])
+        ops.spmm(adj_t, self._gather(b["dh1"], "dh1"), out=b["ds1"])
         ops.gemm(x, b["ds1"], transA=True, out=G["gc1.weight"], precision=pr)
+        if sharded:
+            comm.allreduce_sum_(self.params.grad)
+            comm.allreduce_sum_(self.loss)
         if self.grad_hook is not None:
             self.grad_hook(self.params.grad)
         self.params.adam_step(self.lr)

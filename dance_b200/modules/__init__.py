@@ -1,0 +1,1 @@
+from .scgnn2 import ScGNN2, feature_AE_handler, graph_AE_handler  # noqa: F401

@@ -11,12 +11,69 @@ from typing import Optional, Tuple
 
 import torch
 
-from ._lib import B2Error, check, lib
+from ._lib import B2Error, check
+from ._lib import lib as _raw_lib
 
 ACT = {"none": 0, None: 0, "relu": 1, "elu": 2, "tanh": 3}
 PREC = {"fp32": 0, "simt": 0, "tf32x3": 1, "tf32": 2}
 
 _DEFAULT_PRECISION = "tf32x3"
+
+# ---- instrumentation (bench.py): launch counter + optional per-entry-point CUDA-event timing -------------
+_timing = {"on": False, "events": []}
+_launch_base = [0]
+
+
+class _TimedLib:
+    """Proxy over the ctypes library: when timing is enabled every compute entry point is bracketed by
+    CUDA events on the launching (current) stream."""
+
+    def __getattr__(self, name):
+        fn = getattr(_raw_lib(), name)
+        if not _timing["on"] or name.endswith("_bytes") or name in ("b2_last_error", "b2_version", "b2_launch_count",
+                                                                     "b2_device_info"):
+            return fn
+
+        def timed(*a):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            rc = fn(*a)
+            e.record()
+            _timing["events"].append((name[3:], s, e))
+            return rc
+        return timed
+
+
+_proxy = _TimedLib()
+
+
+def lib():
+    return _proxy
+
+
+def reset_counters():
+    _launch_base[0] = _raw_lib().b2_launch_count()
+
+
+def counters():
+    return {"launches": _raw_lib().b2_launch_count() - _launch_base[0]}
+
+
+def enable_kernel_timing(on: bool):
+    _timing["on"] = bool(on)
+    if on:
+        _timing["events"] = []
+
+
+def kernel_times():
+    """{entry point: {"ms": total, "n": calls}} for the calls recorded since timing was enabled (synchronises)."""
+    torch.cuda.synchronize()
+    out = {}
+    for name, s, e in _timing["events"]:
+        d = out.setdefault(name, {"ms": 0.0, "n": 0})
+        d["ms"] += s.elapsed_time(e)
+        d["n"] += 1
+    return out
 
 
 def set_default_precision(p: str):
@@ -125,7 +182,8 @@ def spmm(A: CSR, X: torch.Tensor, reduce: str = "sum", act: Optional[str] = None
     if out is None:
         out = torch.empty((n_rows, F), dtype=torch.float32, device=X.device)
     _chk(out, torch.float32, "out", 2)
-    check(lib().b2_spmm_csr_f32(_p(A.rowptr), _p(A.colidx), _p(A.vals), _p(X), ldx, _p(out), _rowmajor(out, "out"),
+    colidx_ptr = _p(A.colidx) if A.nnz else _p(A.rowptr)  # an empty matrix has no colidx storage; never dereferenced
+    check(lib().b2_spmm_csr_f32(_p(A.rowptr), colidx_ptr, _p(A.vals) if A.nnz else None, _p(X), ldx, _p(out), _rowmajor(out, "out"),
                                 n_rows, n_cols, F, {"sum": 0, "mean": 1}[reduce], ACT[act], _stream()), "b2_spmm_csr_f32")
     return out
 
@@ -203,15 +261,16 @@ def mse_sum_loss_grad(recon, target, ltmg_regu=None, regu_strength=0.0, relu_mas
 
 
 def gae_loss_grad(z, labels: CSR, norm: float, pos_weight: float, mu=None, logvar=None, use_pos_weight=True,
-                  dz=None, dmu=None, dlogvar=None, loss=None):
+                  dz=None, dmu=None, dlogvar=None, loss=None, row_begin: int = 0, n_rows: Optional[int] = None):
     """Matrix-free Graph-AE loss: returns (loss[1], dz, dmu, dlogvar).
 
     ``dmu``/``dlogvar`` may be column slices of one packed [n, 2d] buffer (shared leading dimension).
     """
     _chk(z, torch.float32, "z", 2)
     n, d = z.shape
+    n_rows = n if n_rows is None else n_rows
     if dz is None:
-        dz = torch.empty((n, d), dtype=torch.float32, device=z.device)
+        dz = torch.empty((n_rows, d), dtype=torch.float32, device=z.device)
     ldm = ldd = 0
     if mu is not None:
         _chk(mu, torch.float32, "mu", 2)
@@ -220,8 +279,8 @@ def gae_loss_grad(z, labels: CSR, norm: float, pos_weight: float, mu=None, logva
         if _rowmajor(logvar, "logvar") != ldm:
             raise B2Error("gae_loss_grad: mu and logvar must share a leading dimension")
         if dmu is None:
-            dmu = torch.empty((n, d), dtype=torch.float32, device=z.device)
-            dlogvar = torch.empty((n, d), dtype=torch.float32, device=z.device)
+            dmu = torch.empty((n_rows, d), dtype=torch.float32, device=z.device)
+            dlogvar = torch.empty((n_rows, d), dtype=torch.float32, device=z.device)
         ldd = _rowmajor(dmu, "dmu")
         if _rowmajor(dlogvar, "dlogvar") != ldd:
             raise B2Error("gae_loss_grad: dmu and dlogvar must share a leading dimension")
@@ -229,7 +288,8 @@ def gae_loss_grad(z, labels: CSR, norm: float, pos_weight: float, mu=None, logva
         loss = torch.empty(1, dtype=torch.float32, device=z.device)
     ws = _workspace(256, z.device)
     check(lib().b2_gae_loss_grad_f32(_p(z), _rowmajor(z, "z"), _p(mu), _p(logvar), ldm, _p(labels.rowptr),
-                                     _p(labels.colidx), n, d, float(norm), float(pos_weight), int(use_pos_weight),
+                                     _p(labels.colidx), n, d, row_begin, n_rows, float(norm), float(pos_weight),
+                                     int(use_pos_weight),
                                      _p(dz), _p(dmu), _p(dlogvar), ldd, _p(loss), _p(ws), ws.numel(), _stream()),
           "b2_gae_loss_grad_f32")
     return loss, dz, dmu, dlogvar

@@ -1,0 +1,90 @@
+"""Cell-sharded data parallelism over the GPUs of one box: one process per GPU,
+``torch.distributed`` (NCCL over NVLink/NVSwitch on GPUs, gloo in the CPU tests) for the
+plumbing.  The reference has no distributed path at all — this is new.
+
+Decomposition:
+  * cells (graph rows) are split into contiguous shards, one per rank;
+  * Feature-AE: pure sample parallelism; ONE all-reduce(sum) of the flat gradient bucket per
+    optimiser step (``FlatParams.grad`` is a single contiguous buffer);
+  * Graph-AE (GCN): each rank owns its rows of Â (CSR rows local, column ids global); the narrow
+    dense operand (N×32) is all-gathered before every SpMM, the decoder all-gathers z (N×16);
+    weight gradients are all-reduced.  Â is symmetric, so the backward SpMM Âᵀ·dY restricted to
+    the local rows is again ``Â_local · all_gather(dY)``.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous, balanced row ranges (first ``n % world`` shards get one extra row)."""
+    base, rem = divmod(n, world)
+    out, start = [], 0
+    for r in range(world):
+        size = base + (1 if r < rem else 0)
+        out.append((start, start + size))
+        start += size
+    return out
+
+
+class Comm:
+    """Thin wrapper over a torch.distributed process group (or a no-op for world size 1)."""
+
+    def __init__(self, group=None):
+        self.enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.group = group
+        self.rank = dist.get_rank(group) if self.enabled else 0
+        self.world = dist.get_world_size(group) if self.enabled else 1
+
+    @classmethod
+    def from_env(cls, backend: Optional[str] = None) -> "Comm":
+        """Initialise from the torchrun environment (RANK / WORLD_SIZE / MASTER_*)."""
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if world > 1 and not dist.is_initialized():
+            if backend is None:
+                backend = "nccl" if torch.cuda.is_available() else "gloo"
+            if backend == "nccl":
+                torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+            dist.init_process_group(backend=backend)
+        return cls()
+
+    def allreduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
+        if self.enabled:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def allreduce_max_(self, t: torch.Tensor) -> torch.Tensor:
+        if self.enabled:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return t
+
+    def all_gather_rows(self, local: torch.Tensor, bounds: List[Tuple[int, int]], out: Optional[torch.Tensor] = None):
+        """Concatenate the ranks' row blocks [n_r, F] → [N, F] (row counts may differ by one)."""
+        if not self.enabled:
+            return local
+        n_total = bounds[-1][1]
+        F = local.shape[1]
+        if out is None:
+            out = torch.empty((n_total, F), dtype=local.dtype, device=local.device)
+        local = local.contiguous()
+        sizes = [b - a for a, b in bounds]
+        if len(set(sizes)) == 1:
+            dist.all_gather_into_tensor(out, local, group=self.group)
+        else:
+            # collectives need equal-sized contributions: pad every shard to the largest one, then compact
+            mx = max(sizes)
+            pad = torch.zeros((mx, F), dtype=local.dtype, device=local.device)
+            pad[:local.shape[0]] = local
+            buf = torch.empty((self.world * mx, F), dtype=local.dtype, device=local.device)
+            dist.all_gather_into_tensor(buf, pad, group=self.group)
+            for r, (a, b) in enumerate(bounds):
+                out[a:b] = buf[r * mx:r * mx + (b - a)]
+        return out
+
+    def barrier(self):
+        if self.enabled:
+            dist.barrier(group=self.group)

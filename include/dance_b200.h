@@ -47,6 +47,8 @@ extern "C" {
 
 const char* b2_last_error(void);
 int b2_version(void);
+/* Number of CUDA kernels this library has launched in the calling process (bench.py's `gpu_launches`). */
+int64_t b2_launch_count(void);
 /* Fills SM count and compute capability of the current device. */
 int b2_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -124,13 +126,18 @@ int b2_mse_sum_loss_grad_f32(const float* recon, const float* target, const floa
  *   loss_out[0] = cost + KLD ; dz [n,d] dense, dmu/dlogvar [n,d] with leading
  *   dimension ldd are OVERWRITTEN with d loss / d z (decoder part) and the KLD
  *   parts respectively.  L must be symmetric (it always is: scgnn2.py:658-664).
+ *   Row sharding (cell-sharded multi-GPU): z holds all n rows; this call handles rows
+ *   [row_begin, row_begin+n_rows): lab_rowptr has n_rows+1 entries (global column ids),
+ *   mu/logvar/dz/dmu/dlogvar are the n_rows local rows, and loss_out receives this
+ *   shard's additive share of the loss (constants use the global n).
  *   mu/logvar may be NULL (plain GAE: cost only).
  *   When use_pos_weight == 0 computes loss_function (scgnn2.py:618-619):
  *   plain mean BCE (GAT branch), norm ignored. */
 size_t b2_gae_loss_workspace_bytes(int32_t n, int32_t d);
 int b2_gae_loss_grad_f32(const float* z, int64_t ldz, const float* mu, const float* logvar, int64_t ldm,
                          const int32_t* lab_rowptr, const int32_t* lab_colidx,
-                         int32_t n, int32_t d, float norm, float pos_weight, int use_pos_weight,
+                         int32_t n, int32_t d, int32_t row_begin, int32_t n_rows,
+                         float norm, float pos_weight, int use_pos_weight,
                          float* dz, float* dmu, float* dlogvar, int64_t ldd, float* loss_out,
                          void* workspace, size_t workspace_bytes, void* stream);
 

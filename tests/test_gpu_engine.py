@@ -1,0 +1,104 @@
+"""Layer- and step-level parity of the engines against the fixtures generated from the reference."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+PRECISIONS = ["fp32", "tf32x3"]
+
+
+def _graph(golden, cuda):
+    from dance_b200 import ops
+    g = golden("knn_graph")
+    n = len(g["X"])
+    an = sp.csr_matrix((g["norm_data"], g["norm_indices"], g["norm_indptr"]), shape=(n, n))
+    A = ops.CSR.from_scipy(an, cuda)
+    L = ops.CSR(A.rowptr, A.colidx, None, A.shape)   # labels A + I share the sparsity pattern of Â
+    return g, A, L
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_graph_ae_engine_matches_reference(cuda, golden, precision):
+    """Graph_AE GCN branch: hidden1, z, loss, weight gradients, weights after one Adam step — ≤1e-4 rel."""
+    from dance_b200.engine import GraphAEEngine
+    g, A, L = _graph(golden, cuda)
+    gg = golden("graph_ae_gcn")
+    x = torch.from_numpy(g["X"]).to(cuda)
+    eng = GraphAEEngine(x.shape[1], 16, device=cuda, lr=1e-2, precision=precision)
+    eng.load_state_dict({"gc1.weight": gg["w1"], "gc2.weight": gg["w2"], "gc3.weight": gg["w3"]})
+    z, mu, lv = eng.forward(x, A, None)
+    assert rel_err(z.cpu().numpy(), gg["eval_z"]) < 1e-4 and rel_err(lv.cpu().numpy(), gg["eval_logvar"]) < 1e-4
+    assert rel_err(eng._buffers(x.shape[0])["h1"].cpu().numpy(), gg["hidden1"]) < 1e-4
+    z, mu, lv = eng.train_step(x, A, L, float(g["norm"]), float(g["pos_weight"]), torch.from_numpy(gg["eps"]).to(cuda))
+    assert rel_err(z.cpu().numpy(), gg["train_z"]) < 1e-4
+    assert abs(eng.loss.item() - float(gg["loss"])) < 1e-4 * abs(float(gg["loss"]))
+    grads = eng.grads()
+    for name, key in (("gc1.weight", "g_w1"), ("gc2.weight", "g_w2"), ("gc3.weight", "g_w3")):
+        assert rel_err(grads[name].cpu().numpy(), gg[key]) < 1e-4, name
+    sd = eng.state_dict()
+    for name, key in (("gc1.weight", "w1_after"), ("gc2.weight", "w2_after"), ("gc3.weight", "w3_after")):
+        assert rel_err(sd[name].cpu().numpy(), gg[key]) < 1e-4, name
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_feature_ae_engine_matches_reference(cuda, golden, precision):
+    """Feature_AE: forward, LTMG loss, gradients of batch 0, and a full epoch of train_handler — ≤1e-4 rel."""
+    from dance_b200.engine import FeatureAEEngine
+    from oracle.make_golden import sample_index
+    g = golden("feature_ae")
+    X = torch.from_numpy(g["X"]).to(cuda)
+    bs, rs = int(g["batch_size"]), float(g["regu_strength"])
+    init = {k[len("init."):]: g[k] for k in g.files if k.startswith("init.")}
+
+    eng = FeatureAEEngine(X.shape[1], device=cuda, lr=1e-3, precision=precision)
+    eng.load_state_dict(init)
+    z, r = eng.forward(X[:bs])
+    assert rel_err(z.cpu().numpy(), g["b0_z"]) < 1e-4 and rel_err(r.cpu().numpy(), g["b0_recon"]) < 1e-4
+    eng.lr = 0.0  # inspect gradients without moving the weights
+    eng.loss_acc.zero_()
+    eng.train_step(X[:bs], None, rs, "LTMG")
+    assert abs(eng.loss_acc.item() - float(g["b0_loss_ltmg"])) < 1e-4 * float(g["b0_loss_ltmg"])
+    for k, gt in eng.params.g.items():
+        gnp = gt.cpu().numpy()
+        got = gnp.reshape(-1)[sample_index(gnp.size)]
+        want = g[f"b0_grad.{k}.sample"]
+        assert np.linalg.norm(got - want) <= 1e-4 * max(np.linalg.norm(want), 1e-12), k
+        assert abs(np.linalg.norm(gnp.astype(np.float64)) - float(g[f"b0_grad.{k}.norm"])) <= 1e-4 * float(g[f"b0_grad.{k}.norm"]), k
+
+    eng = FeatureAEEngine(X.shape[1], device=cuda, lr=1e-3, precision=precision)
+    eng.load_state_dict(init)
+    z_all = torch.empty(X.shape[0], 128, device=cuda)
+    r_all = torch.empty_like(X)
+    eng.train_epoch(X, bs, "LTMG", rs, None, z_all, r_all)
+    assert rel_err(z_all.cpu().numpy(), g["z_all"]) < 1e-4 and rel_err(r_all.cpu().numpy(), g["recon_all"]) < 1e-4
+    for k, v in eng.state_dict().items():
+        v = v.cpu().numpy()
+        got, want = v.reshape(-1)[sample_index(v.size)], g[f"after.{k}.sample"]
+        assert np.linalg.norm(got - want) <= 1e-4 * np.linalg.norm(want), k
+
+
+def test_full_size_properties_spmm_linearity_and_symmetry(cuda):
+    """Size-independent properties at a size the oracle cannot reach quickly: linearity of the
+    aggregate, Â symmetric ⇒ ⟨Âx, y⟩ = ⟨x, Ây⟩, and row sums of the kNN-graph normalisation."""
+    from dance_b200 import ops
+    from oracle import port
+    n, d, k = 200_000, 32, 15
+    X = torch.from_numpy(port.synthetic_embedding(n, d=d, seed=0)).to(cuda)
+    idx, _ = ops.knn(X, k)
+    A = ops.knn_graph_build(idx)
+    assert int(A.rowptr[-1].item()) == A.nnz and A.nnz >= n * (k + 1)
+    rows = torch.repeat_interleave(torch.arange(n, device=cuda), (A.rowptr[1:] - A.rowptr[:-1]).long())
+    assert torch.all(idx.min() >= 0) and torch.all(A.colidx[1:][rows[1:] == rows[:-1]] > A.colidx[:-1][rows[1:] == rows[:-1]])  # sorted, unique
+    x, y = torch.randn(n, 32, device=cuda), torch.randn(n, 32, device=cuda)
+    Ax, Ay = ops.spmm(A, x), ops.spmm(A, y)
+    lin = ops.spmm(A, 2 * x + y)
+    assert rel_err(lin.cpu().numpy(), (2 * Ax + Ay).cpu().numpy()) < 1e-5
+    lhs, rhs = (Ax.double() * y.double()).sum().item(), (x.double() * Ay.double()).sum().item()
+    assert abs(lhs - rhs) < 1e-6 * max(abs(lhs), 1.0)
+    # D^-1/2 (A+I) D^-1/2 applied to sqrt(deg) returns sqrt(deg)
+    deg = (A.rowptr[1:] - A.rowptr[:-1]).float().sqrt().unsqueeze(1).repeat(1, 4).contiguous()
+    assert rel_err(ops.spmm(A, deg).cpu().numpy(), deg.cpu().numpy()) < 1e-5

@@ -1,0 +1,266 @@
+"""Parity of every CUDA kernel (called through the C-ABI) against the oracle / golden fixtures."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_csr(n_rows, n_cols, density, seed, empty_rows=True):
+    rng = np.random.default_rng(seed)
+    m = sp.random(n_rows, n_cols, density=density, random_state=rng, format="csr", dtype=np.float32)
+    m.data = rng.normal(size=m.data.shape).astype(np.float32)
+    if empty_rows and n_rows > 4:
+        m = m.tolil()
+        m[1, :] = 0
+        m[n_rows - 1, :] = 0
+        m = m.tocsr()
+        m.eliminate_zeros()
+    m.sort_indices()
+    return m
+
+
+@pytest.mark.parametrize("F", [4, 8, 16, 32, 48, 64, 128, 200, 400, 512])
+@pytest.mark.parametrize("reduce", ["sum", "mean"])
+def test_spmm_matches_cpu_csr(cuda, F, reduce):
+    from dance_b200 import ops
+    m = _rand_csr(257, 301, 0.05, seed=F)
+    X = np.random.default_rng(1).normal(size=(301, F)).astype(np.float32)
+    ref = (m.astype(np.float64) @ X.astype(np.float64))
+    if reduce == "mean":
+        deg = np.diff(m.indptr)
+        ref = ref / np.maximum(deg, 1)[:, None]
+    A = ops.CSR.from_scipy(m, cuda)
+    Y = ops.spmm(A, torch.from_numpy(X).to(cuda), reduce=reduce).cpu().numpy()
+    assert rel_err(Y, ref) < 1e-6
+    assert np.all(Y[1] == 0) and np.all(Y[-1] == 0)  # empty rows
+
+
+def test_spmm_unweighted_relu_and_padded_ld(cuda):
+    from dance_b200 import ops
+    m = _rand_csr(500, 500, 0.03, seed=5, empty_rows=False)
+    X = torch.randn(500, 64, device=cuda)
+    Xv = X[:, :32]  # leading dimension 64, F = 32
+    A = ops.CSR.from_scipy(m, cuda, with_values=False)
+    ones = m.copy()
+    ones.data[:] = 1
+    ref = np.maximum(ones.astype(np.float64) @ Xv.cpu().numpy().astype(np.float64), 0)
+    Y = ops.spmm(A, Xv, act="relu").cpu().numpy()
+    assert rel_err(Y, ref) < 1e-6
+
+
+def test_spmm_skewed_degrees(cuda):
+    """A few very long rows among short ones (gene-side rows of the cell×gene graph)."""
+    from dance_b200 import ops
+    rng = np.random.default_rng(0)
+    n, c = 2000, 3000
+    rows = np.concatenate([np.zeros(2500, int), np.full(2900, 7), rng.integers(0, n, 20000)])
+    cols = np.concatenate([rng.choice(c, 2500, replace=False), rng.choice(c, 2900, replace=False), rng.integers(0, c, 20000)])
+    m = sp.csr_matrix((rng.normal(size=rows.size).astype(np.float32), (rows, cols)), shape=(n, c))
+    m.sum_duplicates()
+    m.sort_indices()
+    X = rng.normal(size=(c, 32)).astype(np.float32)
+    Y = ops.spmm(ops.CSR.from_scipy(m, cuda), torch.from_numpy(X).to(cuda)).cpu().numpy()
+    assert rel_err(Y, m.astype(np.float64) @ X.astype(np.float64)) < 1e-6
+
+
+def test_spmm_empty_matrix(cuda):
+    from dance_b200 import ops
+    m = sp.csr_matrix((10, 10), dtype=np.float32)
+    Y = ops.spmm(ops.CSR.from_scipy(m, cuda), torch.ones(10, 8, device=cuda))
+    assert torch.all(Y == 0)
+
+
+def test_csr_transpose_is_exact_and_deterministic(cuda):
+    from dance_b200 import ops
+    m = _rand_csr(300, 211, 0.04, seed=2)
+    A = ops.CSR.from_scipy(m, cuda)
+    At, perm = ops.csr_transpose(A)
+    mt = m.T.tocsr()
+    mt.sort_indices()
+    assert np.array_equal(At.rowptr.cpu().numpy(), mt.indptr)
+    assert np.array_equal(At.colidx.cpu().numpy(), mt.indices)
+    assert np.array_equal(At.vals.cpu().numpy(), mt.data)
+    assert np.array_equal(m.data[perm.cpu().numpy()], mt.data)
+
+
+@pytest.mark.parametrize("transA,transB", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("shape", [(130, 70, 50), (257, 129, 33), (64, 512, 128), (1, 5, 3)])
+def test_gemm_simt_all_layouts(cuda, transA, transB, shape):
+    from dance_b200 import ops
+    M, N, K = shape
+    rng = np.random.default_rng(M + N + K)
+    A = rng.normal(size=(K, M) if transA else (M, K)).astype(np.float32)
+    B = rng.normal(size=(N, K) if transB else (K, N)).astype(np.float32)
+    bias = rng.normal(size=N).astype(np.float32)
+    ref = (A.T if transA else A).astype(np.float64) @ (B.T if transB else B).astype(np.float64) + bias
+    C = ops.gemm(torch.from_numpy(A).to(cuda), torch.from_numpy(B).to(cuda), transA=bool(transA), transB=bool(transB),
+                 bias=torch.from_numpy(bias).to(cuda), precision="fp32").cpu().numpy()
+    assert rel_err(C, ref) < 1e-6
+
+
+def test_gemm_epilogue_act_mask_accumulate(cuda):
+    from dance_b200 import ops
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(100, 40)).astype(np.float32)
+    B = rng.normal(size=(40, 60)).astype(np.float32)
+    mask = rng.normal(size=(100, 60)).astype(np.float32)
+    C0 = rng.normal(size=(100, 60)).astype(np.float32)
+    ref = np.maximum(A.astype(np.float64) @ B, 0) * (mask > 0) + C0
+    out = torch.from_numpy(C0.copy()).to(cuda)
+    ops.gemm(torch.from_numpy(A).to(cuda), torch.from_numpy(B).to(cuda), act="relu", mask=torch.from_numpy(mask).to(cuda),
+             out=out, accumulate=True, precision="fp32")
+    assert rel_err(out.cpu().numpy(), ref) < 1e-6
+
+
+def test_colsum(cuda):
+    from dance_b200 import ops
+    X = torch.randn(1237, 77, device=cuda)
+    assert rel_err(ops.colsum(X).cpu().numpy(), X.double().sum(0).cpu().numpy()) < 1e-6
+
+
+def test_mse_loss_grad(cuda):
+    from dance_b200 import ops
+    rng = np.random.default_rng(3)
+    r = np.maximum(rng.normal(size=(50, 30)), 0).astype(np.float32)
+    x = rng.normal(size=(50, 30)).astype(np.float32)
+    T = rng.random(size=(50, 30)).astype(np.float32)
+    for ltmg, s in ((None, 0.0), (None, 0.9), (T, 0.9)):
+        w = (1 - s) + (s * T if ltmg is not None else 0)
+        ref_loss = (w * (r - x)**2).sum()
+        ref_grad = 2 * w * (r - x) * (r > 0)
+        loss, grad = ops.mse_sum_loss_grad(torch.from_numpy(r).to(cuda), torch.from_numpy(x).to(cuda),
+                                           None if ltmg is None else torch.from_numpy(T).to(cuda), s, relu_mask=True)
+        assert abs(loss.item() - ref_loss) < 1e-5 * ref_loss
+        assert rel_err(grad.cpu().numpy(), ref_grad) < 1e-6
+
+
+def test_adam_matches_torch(cuda):
+    from dance_b200 import ops
+    torch.manual_seed(0)
+    p_ref = torch.nn.Parameter(torch.randn(1000, dtype=torch.float32))
+    opt = torch.optim.Adam([p_ref], lr=1e-2, weight_decay=0.0)
+    p = p_ref.detach().clone().to(cuda)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 6):
+        g = torch.randn(1000)
+        p_ref.grad = g.clone()
+        opt.step()
+        ops.adam_step(p, g.to(cuda), m, v, step, lr=1e-2)
+        assert torch.allclose(p.cpu(), p_ref.detach(), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("n,d,k", [(300, 16, 10), (257, 24, 15), (1000, 128, 15), (130, 3, 6), (90, 50, 40)])
+def test_knn_bit_exact_vs_oracle(cuda, n, d, k):
+    from dance_b200 import ops
+    from oracle import port
+    X = port.synthetic_embedding(n, d=d, n_clusters=4, seed=n + d)
+    idx_ref, dist_ref = port.knn_indices(X, k, return_dist=True)
+    idx, dist = ops.knn(torch.from_numpy(X).to(cuda), k)
+    assert np.array_equal(idx.cpu().numpy().astype(np.int64), idx_ref)          # neighbour indices: bit-exact
+    assert np.array_equal(dist.cpu().numpy(), dist_ref)                         # fp64 distances: bit-exact
+
+
+def test_knn_golden_and_graph_build(cuda, golden):
+    from dance_b200 import ops
+    g = golden("knn_graph")
+    X, k = torch.from_numpy(g["X"]).to(cuda), int(g["k"])
+    idx, dist = ops.knn(X, k)
+    assert np.array_equal(idx.cpu().numpy(), g["knn_idx"])
+    assert np.array_equal(1 / (dist.cpu().numpy() + 1e-16), g["knn_w"])
+    A = ops.knn_graph_build(idx)
+    assert np.array_equal(A.rowptr.cpu().numpy(), g["norm_indptr"])
+    assert np.array_equal(A.colidx.cpu().numpy(), g["norm_indices"])
+    assert np.array_equal(A.vals.cpu().numpy(), g["norm_data"])                 # D^-1/2 (A+I) D^-1/2 values: bit-exact
+    # Σ A (no diagonal) = nnz - n is what pos_weight / norm are computed from (scgnn2.py:567-569)
+    n = X.shape[0]
+    s = A.nnz - n
+    assert float(n * n - s) / s == float(g["pos_weight"])
+
+
+def test_knn_with_duplicates_and_rank0(cuda):
+    """Ties are broken by the smaller index; include_rank0 keeps the self slot."""
+    from dance_b200 import ops
+    X = np.random.default_rng(0).normal(size=(64, 5)).astype(np.float32)
+    X[10] = X[3]
+    idx, dist = ops.knn(torch.from_numpy(X).to(cuda), 4, include_rank0=True)
+    idx = idx.cpu().numpy()
+    assert idx[3, 0] == 3 and idx[3, 1] == 10 and idx[10, 0] == 3 and idx[10, 1] == 10
+    assert dist[3, 1].item() == 0.0
+
+
+def test_knn_query_range(cuda):
+    """Row-sharded queries (the multi-GPU decomposition) reproduce the full result."""
+    from dance_b200 import ops
+    from oracle import port
+    X = torch.from_numpy(port.synthetic_embedding(500, d=32, seed=1)).to(cuda)
+    full, _ = ops.knn(X, 15)
+    a, _ = ops.knn(X, 15, q_begin=0, q_end=200)
+    b, _ = ops.knn(X, 15, q_begin=200, q_end=500)
+    assert torch.equal(full, torch.cat([a, b]))
+
+
+def test_pairwise_dense_golden(cuda, golden):
+    from dance_b200 import ops
+    g = golden("pairwise")
+    D = ops.pairwise_l2_dense(torch.from_numpy(g["X"]).to(cuda)).cpu().numpy()
+    assert np.array_equal(D, g["D"])   # bit-exact vs the reference's numba kernel
+
+
+def test_normalize_total_reference_known_answers(cuda, assert_ary_isclose):
+    # reference tests/transforms/test_normalize.py:8-43
+    from dance_b200 import ops
+    x = torch.tensor([[1, 1, 1], [1, 1, 1], [3, 0, 0]], dtype=torch.float32, device=cuda)
+    a = ops.normalize_total_log1p_(x.clone(), target_sum=30, max_fraction=0.99, log1p=False)
+    assert_ary_isclose(a.cpu().numpy(), np.array([[15.0, 15.0, 15.0], [15.0, 15.0, 15.0], [3.0, 0.0, 0.0]]))
+    b = ops.normalize_total_log1p_(a.clone(), target_sum=30, max_fraction=1.0, log1p=False)
+    assert_ary_isclose(b.cpu().numpy(), np.array([[10.0, 10.0, 10.0], [10.0, 10.0, 10.0], [30.0, 0.0, 0.0]]))
+    c = ops.normalize_total_log1p_(x.clone(), normalize=False, log1p=True)
+    assert_ary_isclose(c.cpu().numpy(), np.log1p(x.cpu().numpy()))
+
+
+@pytest.mark.parametrize("target,maxfrac", [(1e4, 1.0), (None, 1.0), (None, 0.05), (50.0, 0.2)])
+def test_normalize_total_log1p_vs_oracle(cuda, target, maxfrac):
+    from dance_b200 import ops
+    from oracle import port
+    X = port.synthetic_expression(333, 203, density=0.2, seed=4, log_normalize=False)
+    X[7] = 0  # an all-zero cell stays untouched
+    ref = port.log1p(port.normalize_total(X, target_sum=target, exclude_highly_expressed=maxfrac < 1, max_fraction=maxfrac), base=2)
+    out = ops.normalize_total_log1p_(torch.from_numpy(X).to(cuda), target_sum=target, max_fraction=maxfrac, base=2)
+    assert np.allclose(out.cpu().numpy(), ref, rtol=2e-6, atol=1e-7)
+    assert np.all(out[7].cpu().numpy() == 0)
+
+
+def test_gae_loss_matches_dense_reference_formula(cuda, golden):
+    """Matrix-free decoder loss == dense BCE-with-logits on z zᵀ (scgnn2.py:423-426,603-619)."""
+    import torch.nn.functional as F
+    from dance_b200 import ops
+    from oracle import port
+    g = golden("knn_graph")
+    gg = golden("graph_ae_gcn")
+    n = len(g["X"])
+    adj = sp.csr_matrix((np.ones(len(g["adj_indices"])), g["adj_indices"], g["adj_indptr"]), shape=(n, n))
+    labels_sp = (adj + sp.eye(n)).tocsr()
+    labels_sp.sort_indices()
+    z = torch.from_numpy(gg["train_z"]).requires_grad_()
+    mu = torch.from_numpy(gg["eval_mu"]).requires_grad_()
+    lv = torch.from_numpy(gg["eval_logvar"]).requires_grad_()
+    pw, norm = float(g["pos_weight"]), float(g["norm"])
+    ref = port.gae_loss(z @ z.t(), torch.from_numpy(labels_sp.toarray()).float(), mu, lv, n, norm, pw)
+    ref.backward()
+    L = ops.CSR.from_scipy(labels_sp, cuda, with_values=False)
+    loss, dz, dmu, dlv = ops.gae_loss_grad(z.detach().to(cuda), L, norm, pw, mu.detach().to(cuda), lv.detach().to(cuda))
+    assert abs(loss.item() - ref.item()) < 2e-6 * abs(ref.item())
+    assert rel_err(dz.cpu().numpy(), z.grad.numpy()) < 1e-5
+    assert rel_err(dmu.cpu().numpy(), mu.grad.numpy()) < 1e-5
+    assert rel_err(dlv.cpu().numpy(), lv.grad.numpy()) < 1e-5
+    # plain BCE (GAT branch, scgnn2.py:618-619)
+    z2 = z.detach().clone().requires_grad_()
+    ref2 = F.binary_cross_entropy_with_logits(z2 @ z2.t(), torch.from_numpy(labels_sp.toarray()).float())
+    ref2.backward()
+    loss2, dz2, _, _ = ops.gae_loss_grad(z2.detach().to(cuda), L, 1.0, 1.0, use_pos_weight=False)
+    assert abs(loss2.item() - ref2.item()) < 2e-6 * abs(ref2.item())
+    assert rel_err(dz2.cpu().numpy(), z2.grad.numpy()) < 1e-5

@@ -1,0 +1,164 @@
+"""world_size-2 gloo tests (CPU) of the cell-sharded decomposition used on N GPUs (dance_b200/parallel.py,
+GraphAEEngine.set_sharding): shard bounds, uneven all-gather, and — with the oracle's torch-CPU arithmetic in
+place of the CUDA kernels — that the row-sharded GCN forward/backward + all-reduce reproduces the unsharded
+loss and weight gradients, and that data-parallel Feature-AE gradients sum to the global-batch gradient."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, fn_name, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, str(ROOT))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        q.put((rank, globals()[fn_name](rank, world)))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(fn_name, world=2):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, fn_name, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return out
+
+
+def test_shard_bounds():
+    from dance_b200.parallel import shard_bounds
+    for n, w in ((10, 3), (7, 8), (1_000_000, 8), (5, 1)):
+        b = shard_bounds(n, w)
+        assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        sizes = [e - s for s, e in b]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _gather_case(rank, world):
+    from dance_b200.parallel import Comm, shard_bounds
+    comm = Comm()
+    bounds = shard_bounds(11, world)   # uneven: 6 + 5
+    full = torch.arange(11 * 3, dtype=torch.float32).view(11, 3)
+    a, b = bounds[rank]
+    out = comm.all_gather_rows(full[a:b].clone(), bounds)
+    t = torch.tensor([float(rank + 1)])
+    comm.allreduce_sum_(t)
+    return bool(torch.equal(out, full)) and t.item() == 3.0 and comm.world == 2
+
+
+def test_all_gather_rows_uneven_gloo():
+    assert all(_run("_gather_case").values())
+
+
+def _sharded_gcn_case(rank, world):
+    """Row-sharded Graph-AE step with the communication pattern of GraphAEEngine.train_step."""
+    from dance_b200.parallel import Comm, shard_bounds
+    from oracle import port
+    comm = Comm()
+    n, d, e = 203, 16, 16
+    X = torch.from_numpy(port.synthetic_embedding(n, d=d, n_clusters=3, seed=2))
+    adj, _ = port.feature2adj(X.numpy(), 8)
+    an = port.preprocess_graph(adj)
+    pw, norm = port.gae_norm_constants(adj)
+    torch.manual_seed(0)
+    w1, w2, w3 = (torch.nn.init.xavier_uniform_(torch.empty(d, 32)), torch.nn.init.xavier_uniform_(torch.empty(32, e)),
+                  torch.nn.init.xavier_uniform_(torch.empty(32, e)))
+    eps = torch.randn(n, e)
+    # unsharded reference (autograd)
+    W = [w.clone().requires_grad_() for w in (w1, w2, w3)]
+    loss_ref, *_ = port.graph_ae_gcn_loss(X, *W, an, adj, eps=eps)
+    loss_ref.backward()
+
+    bounds = shard_bounds(n, world)
+    a, b = bounds[rank]
+    A_loc = torch.from_numpy(an[a:b].toarray())                      # local row block of Â, global columns
+    L_loc = torch.from_numpy((adj + sp.eye(n)).tocsr()[a:b].toarray()).float()
+    x, ep = X[a:b], eps[a:b]
+    gather = lambda t: comm.all_gather_rows(t.contiguous(), bounds)
+    # forward
+    s1 = x @ w1
+    h1 = torch.relu(A_loc @ gather(s1))
+    w23 = torch.cat([w2, w3], 1)
+    ml = A_loc @ gather(h1 @ w23)
+    mu, lv = ml[:, :e], ml[:, e:]
+    z = mu + ep * torch.exp(lv)
+    z_all = gather(z)
+    # loss share of this shard: rows local × all columns (constants use the global n)
+    logits = z @ z_all.t()
+    bce = torch.nn.functional.binary_cross_entropy_with_logits(logits, L_loc, pos_weight=L_loc * pw, reduction="sum")
+    kld = -0.5 / n * torch.sum(1 + 2 * lv - mu.pow(2) - lv.exp().pow(2)) / n
+    loss = norm * bce / (n * n) + kld
+    # gradients wrt the local rows (L symmetric ⇒ factor 2 on the decoder part)
+    sig = torch.sigmoid(logits)
+    g = norm / (n * n) * (sig * (1 - L_loc) - pw * L_loc * (1 - sig))
+    dz = 2 * g @ z_all
+    cf = -0.5 / (n * n)
+    dmu = cf * (-2 * mu) + dz
+    dlv = cf * (2 - 2 * lv.exp().pow(2)) + dz * ep * torch.exp(lv)
+    dml = torch.cat([dmu, dlv], 1)
+    ds2 = A_loc @ gather(dml)                                        # Âᵀ·dY on local rows = Â_loc·gather(dY) (Â symmetric)
+    g23 = h1.t() @ ds2
+    dh1 = (ds2 @ w23.t()) * (h1 > 0)
+    ds1 = A_loc @ gather(dh1)
+    g1 = x.t() @ ds1
+    flat = torch.cat([g1.reshape(-1), g23.reshape(-1), loss.reshape(1)])
+    comm.allreduce_sum_(flat)
+    g1r, g23r, lossr = flat[:d * 32].view(d, 32), flat[d * 32:-1].view(32, 2 * e), flat[-1]
+    rel = lambda p, q: (torch.norm(p - q) / torch.norm(q)).item()
+    return (abs(lossr.item() - loss_ref.item()) / abs(loss_ref.item()), rel(g1r, W[0].grad), rel(g23r[:, :e], W[1].grad),
+            rel(g23r[:, e:], W[2].grad))
+
+
+def test_sharded_gcn_matches_unsharded_gloo():
+    for rank, errs in _run("_sharded_gcn_case").items():
+        assert max(errs) < 1e-5, (rank, errs)
+
+
+def _dp_feature_ae_case(rank, world):
+    """Sum-reduced per-shard gradients == gradient of the loss over the union batch (loss uses reduction='sum')."""
+    from dance_b200.parallel import Comm, shard_bounds
+    from oracle import port
+    comm = Comm()
+    X = torch.from_numpy(port.synthetic_expression(64, 24, density=0.3, seed=1))
+    torch.manual_seed(0)
+    model = port.FeatureAE(24)
+    ref = port.FeatureAE(24)
+    ref.load_state_dict(model.state_dict())
+    _, r = ref(X)
+    port.feature_ae_loss(r, X, "LTMG", 0.9, torch.zeros_like(X)).backward()
+    a, b = shard_bounds(64, world)[rank]
+    _, r = model(X[a:b])
+    port.feature_ae_loss(r, X[a:b], "LTMG", 0.9, torch.zeros_like(X[a:b])).backward()
+    flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    comm.allreduce_sum_(flat)
+    flat_ref = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
+    return (torch.norm(flat - flat_ref) / torch.norm(flat_ref)).item()
+
+
+def test_data_parallel_feature_ae_gradients_gloo():
+    assert max(_run("_dp_feature_ae_case").values()) < 1e-5
