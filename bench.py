@@ -78,13 +78,19 @@ def synth_expression_gpu(n, g, device, seed=0, density=0.10, chunk=65536):
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    Q_OLD = Q.replace("clocks_event_reasons", "clocks_throttle_reasons")
 
     def __init__(self, gpu_index=0):
         self.rows, self.proc, self.gpu_index = [], None, gpu_index
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            q = self.Q
+            probe = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu_index)],
+                                   capture_output=True, text=True, timeout=20)
+            if probe.returncode != 0 or "not a valid" in (probe.stdout + probe.stderr).lower():
+                q = self.Q_OLD
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -209,6 +215,7 @@ def main():
     ap.add_argument("--cpu-cells", type=int, default=16384, help="bounded CPU sample (cells) for cpu_baseline / --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cuda-profiler", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
@@ -298,7 +305,11 @@ def main():
     if rank == 0:
         sampler.start()
     launches_before = ops.counters()["launches"]
+    if args.cuda_profiler:
+        torch.cuda.profiler.start()
     total_ms = timed(lambda: step(X), args.steps)
+    if args.cuda_profiler:
+        torch.cuda.profiler.stop()
     launches = ops.counters()["launches"] - launches_before
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps

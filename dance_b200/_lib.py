@@ -26,7 +26,8 @@ _SIGNATURES = {
     "b2_gemm_workspace_bytes": (c_sz, [C.c_int] * 6),
     "b2_gemm_f32": (C.c_int, [c_vp, c_i64, C.c_int, c_vp, c_i64, C.c_int, c_vp, c_i64, C.c_int, C.c_int, C.c_int,
                               c_vp, C.c_int, c_vp, c_i64, c_f32, C.c_int, c_vp, c_sz, c_vp]),
-    "b2_colsum_f32": (C.c_int, [c_vp, c_i64, C.c_int, C.c_int, c_vp, c_f32, c_vp]),
+    "b2_colsum_workspace_bytes": (c_sz, [C.c_int, C.c_int]),
+    "b2_colsum_f32": (C.c_int, [c_vp, c_i64, C.c_int, C.c_int, c_vp, c_f32, c_vp, c_sz, c_vp]),
     "b2_mse_sum_loss_grad_f32": (C.c_int, [c_vp, c_vp, c_vp, c_f32, C.c_int, c_vp, c_vp, c_i64, c_vp]),
     "b2_gae_loss_workspace_bytes": (c_sz, [c_i32, c_i32]),
     "b2_gae_loss_grad_f32": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_f32, C.c_int,

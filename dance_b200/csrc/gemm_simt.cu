@@ -162,13 +162,40 @@ __global__ void colsum_finish_kernel(const float* __restrict__ partial, int N, i
 
 }  // namespace b2
 
-extern "C" int b2_colsum_f32(const float* X, int64_t ldx, int M, int N, float* out, float beta, void* stream) {
+static int colsum_splits(int M, int N) {
+  // enough blocks to fill the machine: (N/32 column blocks) x splits; each split covers >= 256 rows
+  const int col_blocks = b2::ceil_div(N, 32);
+  int splits = b2::ceil_div(b2::sm_count() * 4, col_blocks);
+  const int max_splits = M / 256 > 0 ? M / 256 : 1;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  return splits;
+}
+
+extern "C" size_t b2_colsum_workspace_bytes(int M, int N) {
+  const int splits = colsum_splits(M, N);
+  return splits > 1 ? (size_t)splits * N * sizeof(float) : 0;
+}
+
+extern "C" int b2_colsum_f32(const float* X, int64_t ldx, int M, int N, float* out, float beta, void* workspace,
+                             size_t workspace_bytes, void* stream) {
   using namespace b2;
   B2_REQUIRE(X && out && M >= 0 && N > 0 && ldx >= N, "b2_colsum_f32: bad arguments");
   cudaStream_t st = as_stream(stream);
-  // single pass per column block; deterministic (fixed row striding order)
-  dim3 grid(ceil_div(N, 32), 1);
-  colsum_kernel<<<grid, 256, 0, st>>>(X, ldx, M, N, out, beta, nullptr, 1);
+  const int splits = colsum_splits(M, N);
+  if (splits == 1) {
+    dim3 grid(ceil_div(N, 32), 1);
+    colsum_kernel<<<grid, 256, 0, st>>>(X, ldx, M, N, out, beta, nullptr, 1);
+    B2_CHECK_LAUNCH("colsum_kernel");
+    return B2_OK;
+  }
+  B2_REQUIRE(workspace && workspace_bytes >= (size_t)splits * N * sizeof(float), "b2_colsum_f32: workspace too small");
+  float* partial = reinterpret_cast<float*>(workspace);
+  // deterministic two-stage reduction: fixed row ranges per split, fixed summation order in the finish kernel
+  dim3 grid(ceil_div(N, 32), splits);
+  colsum_kernel<<<grid, 256, 0, st>>>(X, ldx, M, N, out, beta, partial, splits);
   B2_CHECK_LAUNCH("colsum_kernel");
+  colsum_finish_kernel<<<ceil_div(N, 256), 256, 0, st>>>(partial, N, splits, out, beta);
+  B2_CHECK_LAUNCH("colsum_finish_kernel");
   return B2_OK;
 }

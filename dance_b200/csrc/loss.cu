@@ -56,64 +56,103 @@ __device__ __forceinline__ float sigmoid_f(float x) {
   return x >= 0.f ? s : e * s;
 }
 
-constexpr int GL_ROWS = 128;   // rows of z owned by one CTA (one per thread)
-constexpr int GL_JT = 128;     // j-tile staged in shared memory
+constexpr int GL_THREADS = 128;            // threads per CTA
+// rows of z per thread (amortises the shared-memory operand reads); 1 for wide embeddings (register budget)
+template <int D> struct GaeCfg { static constexpr int RPT = D <= 16 ? 2 : 1; static constexpr int ROWS = GL_THREADS * RPT; };
+constexpr int GL_JT = 128;                 // j-tile staged in shared memory
 
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// All-pairs part: thread t owns rows i0+t and i0+t+GL_THREADS, loops over every column j (tiles in smem,
+// broadcast reads).  Per logit: 2·D FMA (dot + gradient accumulate) and three SFU ops
+// (e = 2^(-|x|·log2e), r = 1/(1+e), log2(1+e)); softplus(x) = max(x,0) + ln2·log2(1+e), σ(x) = x≥0 ? r : e·r.
 template <int D>
-__global__ void __launch_bounds__(GL_ROWS)
+__global__ void __launch_bounds__(GL_THREADS)
 gae_allpairs_kernel(const float* __restrict__ z, int64_t ldz, int32_t n, int32_t row_begin, int32_t n_rows,
                     int32_t j_chunk, float coef, float* __restrict__ dz, double* __restrict__ loss_acc) {
+  constexpr int GL_RPT = GaeCfg<D>::RPT, GL_ROWS = GaeCfg<D>::ROWS;
   __shared__ __align__(16) float zj[GL_JT][D];
-  const int i = blockIdx.x * GL_ROWS + threadIdx.x;   // local row
-  const bool live = i < n_rows;
-  float zi[D], acc[D];
+  float zi[GL_RPT][D], acc[GL_RPT][D];
+  bool live[GL_RPT];
 #pragma unroll
-  for (int d = 0; d < D; ++d) {
-    zi[d] = live ? z[(int64_t)(row_begin + i) * ldz + d] : 0.f;
-    acc[d] = 0.f;
+  for (int r = 0; r < GL_RPT; ++r) {
+    const int i = blockIdx.x * GL_ROWS + r * GL_THREADS + threadIdx.x;   // local row
+    live[r] = i < n_rows;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      zi[r][d] = live[r] ? z[(int64_t)(row_begin + i) * ldz + d] : 0.f;
+      acc[r][d] = 0.f;
+    }
   }
   const int j_begin = blockIdx.y * j_chunk;
   const int j_end = min(n, j_begin + j_chunk);
   double loss = 0.0;
+  constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
   for (int j0 = j_begin; j0 < j_end; j0 += GL_JT) {
     const int cnt = min(GL_JT, j_end - j0);
     __syncthreads();
-    for (int t = threadIdx.x; t < GL_JT * D; t += GL_ROWS) {
-      const int jj = t / D, d = t % D;
-      zj[jj][d] = (jj < cnt) ? z[(int64_t)(j0 + jj) * ldz + d] : 0.f;
+    for (int t = threadIdx.x; t < GL_JT * D / 4; t += GL_THREADS) {
+      const int jj = t / (D / 4), q = t % (D / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (jj < cnt) {
+        const float* src = z + (int64_t)(j0 + jj) * ldz + 4 * q;
+        v = make_float4(src[0], src[1], src[2], src[3]);
+      }
+      *reinterpret_cast<float4*>(&zj[jj][4 * q]) = v;
     }
     __syncthreads();
-    float tile_loss = 0.f;
+    float relu_sum[GL_RPT], lg_sum[GL_RPT];
+#pragma unroll
+    for (int r = 0; r < GL_RPT; ++r) { relu_sum[r] = 0.f; lg_sum[r] = 0.f; }
+#pragma unroll 2
     for (int jj = 0; jj < cnt; ++jj) {
-      float x = 0.f;
+      float zv[D];
 #pragma unroll
-      for (int d = 0; d < D; ++d) x = fmaf(zi[d], zj[jj][d], x);
-      const float e = __expf(-fabsf(x));
-      const float inv = 1.f / (1.f + e);
-      const float s = x >= 0.f ? inv : e * inv;         // sigmoid(x)
-      tile_loss += fmaxf(x, 0.f) + __logf(1.f + e);     // softplus(x); e in (0,1]
+      for (int d = 0; d < D; d += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(&zj[jj][d]);
+        zv[d] = v.x; zv[d + 1] = v.y; zv[d + 2] = v.z; zv[d + 3] = v.w;
+      }
 #pragma unroll
-      for (int d = 0; d < D; ++d) acc[d] = fmaf(s, zj[jj][d], acc[d]);
+      for (int r = 0; r < GL_RPT; ++r) {
+        float x0 = 0.f, x1 = 0.f;   // two chains halve the dependent-FMA latency
+#pragma unroll
+        for (int d = 0; d < D; d += 2) { x0 = fmaf(zi[r][d], zv[d], x0); x1 = fmaf(zi[r][d + 1], zv[d + 1], x1); }
+        const float x = x0 + x1;
+        const float e = ex2_approx(-fabsf(x) * LOG2E);
+        const float inv = rcp_approx(1.f + e);
+        const float sgm = x >= 0.f ? inv : e * inv;          // sigmoid(x)
+        relu_sum[r] += fmaxf(x, 0.f);
+        lg_sum[r] += lg2_approx(1.f + e);                    // softplus(x) = max(x,0) + ln2·log2(1+e)
+#pragma unroll
+        for (int d = 0; d < D; ++d) acc[r][d] = fmaf(sgm, zv[d], acc[r][d]);
+      }
     }
-    if (live) loss += (double)tile_loss;
+#pragma unroll
+    for (int r = 0; r < GL_RPT; ++r)
+      if (live[r]) loss += (double)(relu_sum[r] + LN2 * lg_sum[r]);
   }
-  if (live) {
-    const float c2 = 2.f * coef;
+  const float c2 = 2.f * coef;
+#pragma unroll
+  for (int r = 0; r < GL_RPT; ++r) {
+    if (!live[r]) continue;
+    const int64_t i = (int64_t)blockIdx.x * GL_ROWS + r * GL_THREADS + threadIdx.x;
     if (gridDim.y == 1) {
 #pragma unroll
-      for (int d = 0; d < D; ++d) dz[(int64_t)i * D + d] += c2 * acc[d];
+      for (int d = 0; d < D; ++d) dz[i * D + d] += c2 * acc[r][d];
     } else {
 #pragma unroll
-      for (int d = 0; d < D; ++d) atomicAdd(dz + (int64_t)i * D + d, c2 * acc[d]);
+      for (int d = 0; d < D; ++d) atomicAdd(dz + i * D + d, c2 * acc[r][d]);
     }
   }
   loss = warp_sum(loss);
-  __shared__ double sred[GL_ROWS / 32];
+  __shared__ double sred[GL_THREADS / 32];
   if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = loss;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
-    for (int w = 0; w < GL_ROWS / 32; ++w) t += sred[w];
+    for (int w = 0; w < GL_THREADS / 32; ++w) t += sred[w];
     atomicAdd(loss_acc, t * (double)coef);
   }
 }
@@ -190,7 +229,7 @@ __global__ void gae_finish_kernel(const double* acc, float* loss_out) { loss_out
 template <int D>
 static int launch_gae(const float* z, int64_t ldz, const int32_t* rp, const int32_t* ci, int32_t n, int32_t row_begin,
                       int32_t n_rows, float coef, float pw, int use_pw, float* dz, double* acc, cudaStream_t st) {
-  const int row_blocks = ceil_div(n_rows, GL_ROWS);
+  const int row_blocks = ceil_div(n_rows, GaeCfg<D>::ROWS);
   // split the j range so that small graphs still fill the machine
   int j_splits = 1;
   const int target = sm_count() * 4;
@@ -200,7 +239,7 @@ static int launch_gae(const float* z, int64_t ldz, const int32_t* rp, const int3
   int j_chunk = ceil_div(ceil_div(n, j_splits), GL_JT) * GL_JT;
   j_splits = ceil_div(n, j_chunk);
   dim3 grid(row_blocks, j_splits);
-  gae_allpairs_kernel<D><<<grid, GL_ROWS, 0, st>>>(z, ldz, n, row_begin, n_rows, j_chunk, coef, dz, acc);
+  gae_allpairs_kernel<D><<<grid, GL_THREADS, 0, st>>>(z, ldz, n, row_begin, n_rows, j_chunk, coef, dz, acc);
   B2_CHECK_LAUNCH("gae_allpairs_kernel");
   int64_t blocks = ceil_div<int64_t>(n_rows, 8);
   const int64_t cap = (int64_t)sm_count() * 16;

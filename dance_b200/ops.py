@@ -240,8 +240,10 @@ def colsum(X: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool
     _chk(X, torch.float32, "X", 2)
     if out is None:
         out = torch.empty(X.shape[1], dtype=torch.float32, device=X.device)
+    nbytes = lib().b2_colsum_workspace_bytes(X.shape[0], X.shape[1])
+    ws = _workspace(nbytes, X.device) if nbytes else None
     check(lib().b2_colsum_f32(_p(X), _rowmajor(X, "X"), X.shape[0], X.shape[1], _p(out), 1.0 if accumulate else 0.0,
-                              _stream()), "b2_colsum_f32")
+                              _p(ws), ws.numel() if ws is not None else 0, _stream()), "b2_colsum_f32")
     return out
 
 

@@ -103,7 +103,9 @@ int b2_gemm_f32(const float* A, int64_t lda, int transA,
                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* column sums: out[N] = (beta ? out : 0) + Σ_rows X[M,N]   (bias gradients) */
-int b2_colsum_f32(const float* X, int64_t ldx, int M, int N, float* out, float beta, void* stream);
+size_t b2_colsum_workspace_bytes(int M, int N);
+int b2_colsum_f32(const float* X, int64_t ldx, int M, int N, float* out, float beta,
+                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
  * Losses (forward value + gradient w.r.t. the prediction, one pass)
