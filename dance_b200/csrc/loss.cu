@@ -64,6 +64,17 @@ constexpr int GL_JT = 128;                 // j-tile staged in shared memory
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// packed fp32 FMA (Blackwell FFMA2): two independent fused multiply-adds per issue slot
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1,%2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1,%2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
 
 // All-pairs part: thread t owns rows i0+t and i0+t+GL_THREADS, loops over every column j (tiles in smem,
 // broadcast reads).  Per logit: 2·D FMA (dot + gradient accumulate) and three SFU ops
@@ -74,16 +85,17 @@ gae_allpairs_kernel(const float* __restrict__ z, int64_t ldz, int32_t n, int32_t
                     int32_t j_chunk, float coef, float* __restrict__ dz, double* __restrict__ loss_acc) {
   constexpr int GL_RPT = GaeCfg<D>::RPT, GL_ROWS = GaeCfg<D>::ROWS;
   __shared__ __align__(16) float zj[GL_JT][D];
-  float zi[GL_RPT][D], acc[GL_RPT][D];
+  float2 zi[GL_RPT][D / 2], acc[GL_RPT][D / 2];   // feature pairs (d, d+1) packed for FFMA2
   bool live[GL_RPT];
 #pragma unroll
   for (int r = 0; r < GL_RPT; ++r) {
     const int i = blockIdx.x * GL_ROWS + r * GL_THREADS + threadIdx.x;   // local row
     live[r] = i < n_rows;
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      zi[r][d] = live[r] ? z[(int64_t)(row_begin + i) * ldz + d] : 0.f;
-      acc[r][d] = 0.f;
+    for (int d = 0; d < D / 2; ++d) {
+      zi[r][d] = live[r] ? make_float2(z[(int64_t)(row_begin + i) * ldz + 2 * d], z[(int64_t)(row_begin + i) * ldz + 2 * d + 1])
+                         : make_float2(0.f, 0.f);
+      acc[r][d] = make_float2(0.f, 0.f);
     }
   }
   const int j_begin = blockIdx.y * j_chunk;
@@ -103,35 +115,43 @@ gae_allpairs_kernel(const float* __restrict__ z, int64_t ldz, int32_t n, int32_t
       *reinterpret_cast<float4*>(&zj[jj][4 * q]) = v;
     }
     __syncthreads();
-    float relu_sum[GL_RPT], lg_sum[GL_RPT];
+    // Σ_j log2(1+e_j) = log2 Π_j (1+e_j): each factor is in (1,2], so 32 of them stay far below FLT_MAX —
+    // one MUFU.LG2 per 32 logits instead of one per logit.
+    float relu_sum[GL_RPT], lg_sum[GL_RPT], prod[GL_RPT];
 #pragma unroll
-    for (int r = 0; r < GL_RPT; ++r) { relu_sum[r] = 0.f; lg_sum[r] = 0.f; }
+    for (int r = 0; r < GL_RPT; ++r) { relu_sum[r] = 0.f; lg_sum[r] = 0.f; prod[r] = 1.f; }
 #pragma unroll 2
     for (int jj = 0; jj < cnt; ++jj) {
-      float zv[D];
+      if ((jj & 31) == 31) {
+#pragma unroll
+        for (int r = 0; r < GL_RPT; ++r) { lg_sum[r] += lg2_approx(prod[r]); prod[r] = 1.f; }
+      }
+      float2 zv[D / 2];
 #pragma unroll
       for (int d = 0; d < D; d += 4) {
         const float4 v = *reinterpret_cast<const float4*>(&zj[jj][d]);
-        zv[d] = v.x; zv[d + 1] = v.y; zv[d + 2] = v.z; zv[d + 3] = v.w;
+        zv[d / 2] = make_float2(v.x, v.y);
+        zv[d / 2 + 1] = make_float2(v.z, v.w);
       }
 #pragma unroll
       for (int r = 0; r < GL_RPT; ++r) {
-        float x0 = 0.f, x1 = 0.f;   // two chains halve the dependent-FMA latency
+        float2 xa = make_float2(0.f, 0.f), xb = make_float2(0.f, 0.f);   // two packed chains = 4 partial sums
 #pragma unroll
-        for (int d = 0; d < D; d += 2) { x0 = fmaf(zi[r][d], zv[d], x0); x1 = fmaf(zi[r][d + 1], zv[d + 1], x1); }
-        const float x = x0 + x1;
+        for (int d = 0; d < D / 2; d += 2) { xa = ffma2(zi[r][d], zv[d], xa); xb = ffma2(zi[r][d + 1], zv[d + 1], xb); }
+        const float x = (xa.x + xa.y) + (xb.x + xb.y);
         const float e = ex2_approx(-fabsf(x) * LOG2E);
         const float inv = rcp_approx(1.f + e);
         const float sgm = x >= 0.f ? inv : e * inv;          // sigmoid(x)
         relu_sum[r] += fmaxf(x, 0.f);
-        lg_sum[r] += lg2_approx(1.f + e);                    // softplus(x) = max(x,0) + ln2·log2(1+e)
+        prod[r] *= (1.f + e);                                // softplus(x) = max(x,0) + ln2·log2(1+e)
+        const float2 sg2 = make_float2(sgm, sgm);
 #pragma unroll
-        for (int d = 0; d < D; ++d) acc[r][d] = fmaf(sgm, zv[d], acc[r][d]);
+        for (int d = 0; d < D / 2; ++d) acc[r][d] = ffma2(sg2, zv[d], acc[r][d]);
       }
     }
 #pragma unroll
     for (int r = 0; r < GL_RPT; ++r)
-      if (live[r]) loss += (double)(relu_sum[r] + LN2 * lg_sum[r]);
+      if (live[r]) loss += (double)(relu_sum[r] + LN2 * (lg_sum[r] + lg2_approx(prod[r])));
   }
   const float c2 = 2.f * coef;
 #pragma unroll
@@ -140,10 +160,10 @@ gae_allpairs_kernel(const float* __restrict__ z, int64_t ldz, int32_t n, int32_t
     const int64_t i = (int64_t)blockIdx.x * GL_ROWS + r * GL_THREADS + threadIdx.x;
     if (gridDim.y == 1) {
 #pragma unroll
-      for (int d = 0; d < D; ++d) dz[i * D + d] += c2 * acc[r][d];
+      for (int d = 0; d < D / 2; ++d) { dz[i * D + 2 * d] += c2 * acc[r][d].x; dz[i * D + 2 * d + 1] += c2 * acc[r][d].y; }
     } else {
 #pragma unroll
-      for (int d = 0; d < D; ++d) atomicAdd(dz + i * D + d, c2 * acc[r][d]);
+      for (int d = 0; d < D / 2; ++d) { atomicAdd(dz + i * D + 2 * d, c2 * acc[r][d].x); atomicAdd(dz + i * D + 2 * d + 1, c2 * acc[r][d].y); }
     }
   }
   loss = warp_sum(loss);

@@ -286,3 +286,117 @@ class GraphAEEngine:
             self.grad_hook(self.params.grad)
         self.params.adam_step(self.lr)
         return z, mu, logvar
+
+
+class GATEngine:
+    """The 2-layer GAT of Graph_AE (scgnn2.py:376-378, 883-917): layer 1 concat + ELU, layer 2 head-mean,
+    skip projections and biases, global-max edge softmax — explicit forward / backward / Adam.
+
+    Per layer the attention projection and the skip projection read the same input, so they are stored
+    packed ``[linear_proj ; skip_proj]`` and evaluated by ONE GEMM; ``state_dict`` splits them back into the
+    reference's keys (``gat.gat_net.{l}.linear_proj.weight`` …).
+    """
+
+    def __init__(self, dim: int, hid: int = 64, embedding_size: int = 16, heads: int = 2, device="cuda", lr: float = 1e-2,
+                 precision: Optional[str] = None, seed: Optional[int] = None):
+        self.device, self.lr, self.precision, self.nh = torch.device(device), lr, precision, heads
+        self.layers = [dict(fin=dim, F=hid, concat=True, act="elu"), dict(fin=hid * heads, F=embedding_size, concat=False, act=None)]
+        shapes = []
+        for l, L in enumerate(self.layers):
+            W = heads * L["F"]
+            shapes += [(f"l{l}.projskip", (2 * W, L["fin"])), (f"l{l}.a_trg", (W, )), (f"l{l}.a_src", (W, )),
+                       (f"l{l}.bias", (W if L["concat"] else L["F"], ))]
+        self.params = FlatParams(shapes, self.device)
+        gen = torch.Generator().manual_seed(seed) if seed is not None else None
+        for l, L in enumerate(self.layers):
+            W, fin, F = heads * L["F"], L["fin"], L["F"]
+            proj = torch.empty(W, fin)
+            proj.copy_((torch.rand(W, fin, generator=gen) * 2 - 1) * (6.0 / (W + fin))**0.5)   # xavier_uniform_
+            skip = (torch.rand(W, fin, generator=gen) * 2 - 1) / fin**0.5          # nn.Linear default init
+            # xavier_uniform_ on a (1, NH, F) tensor: fan_in = NH·F, fan_out = F   (torch's fan computation for 3-D tensors)
+            ab = (6.0 / (heads * F + F))**0.5
+            self.params.p[f"l{l}.projskip"][:W].copy_(proj)
+            self.params.p[f"l{l}.projskip"][W:].copy_(skip)
+            self.params.p[f"l{l}.a_trg"].copy_((torch.rand(W, generator=gen) * 2 - 1) * ab)
+            self.params.p[f"l{l}.a_src"].copy_((torch.rand(W, generator=gen) * 2 - 1) * ab)
+            self.params.p[f"l{l}.bias"].zero_()
+        self.loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._cache = {}
+
+    # reference key layout: gat.gat_net.{l}.{linear_proj.weight, skip_proj.weight, scoring_fn_target, scoring_fn_source, bias}
+    def state_dict(self):
+        sd = {}
+        for l, L in enumerate(self.layers):
+            W, F = self.nh * L["F"], L["F"]
+            pre = f"gat.gat_net.{l}."
+            sd[pre + "linear_proj.weight"] = self.params.p[f"l{l}.projskip"][:W].detach().clone()
+            sd[pre + "skip_proj.weight"] = self.params.p[f"l{l}.projskip"][W:].detach().clone()
+            sd[pre + "scoring_fn_target"] = self.params.p[f"l{l}.a_trg"].detach().clone().view(1, self.nh, F)
+            sd[pre + "scoring_fn_source"] = self.params.p[f"l{l}.a_src"].detach().clone().view(1, self.nh, F)
+            sd[pre + "bias"] = self.params.p[f"l{l}.bias"].detach().clone()
+        return sd
+
+    def _split(self, store, l):
+        W, F = self.nh * self.layers[l]["F"], self.layers[l]["F"]
+        pre = f"gat.gat_net.{l}."
+        return {pre + "linear_proj.weight": store[f"l{l}.projskip"][:W], pre + "skip_proj.weight": store[f"l{l}.projskip"][W:],
+                pre + "scoring_fn_target": store[f"l{l}.a_trg"].view(1, self.nh, F),
+                pre + "scoring_fn_source": store[f"l{l}.a_src"].view(1, self.nh, F), pre + "bias": store[f"l{l}.bias"]}
+
+    def load_state_dict(self, sd):
+        for l in range(len(self.layers)):
+            for k, dst in self._split(self.params.p, l).items():
+                dst.copy_(torch.as_tensor(sd[k], dtype=torch.float32).reshape(dst.shape))
+
+    def grads(self):
+        out = {}
+        for l in range(len(self.layers)):
+            out.update(self._split(self.params.g, l))
+        return out
+
+    def forward(self, x: torch.Tensor, T: CSR, keep: bool = False):
+        """GAT.forward on the target-indexed CSR ``T`` (row v = sources of v's in-edges); returns the node embedding."""
+        P, pr, nh = self.params.p, self.precision, self.nh
+        h = x
+        for l, L in enumerate(self.layers):
+            W = nh * L["F"]
+            hs = ops.gemm(h, P[f"l{l}.projskip"], transB=True, precision=pr)         # [n, 2W]: projection | skip projection
+            H, skip = hs[:, :W], hs[:, W:]
+            s_src, s_trg = ops.gat_scores(H, P[f"l{l}.a_src"], P[f"l{l}.a_trg"], nh)
+            agg, alpha, _ = ops.gat_aggregate_fwd(T, H, s_src, s_trg, nh, "leakyrelu", 0.2, "global", keep_alpha=keep)
+            out = ops.gat_combine_fwd(agg, skip, P[f"l{l}.bias"], nh, L["concat"], L["act"])
+            if keep:
+                self._cache[l] = dict(x=h, hs=hs, s_src=s_src, s_trg=s_trg, alpha=alpha, out=out)
+            h = out
+        return h
+
+    def train_step(self, x: torch.Tensor, T: CSR, Tt: CSR, t_perm: torch.Tensor, labels: CSR):
+        """One epoch of graph_AE_handler with use_GAT=True (scgnn2.py:575-593): forward, loss_function
+        (plain mean BCE on z zᵀ, scgnn2.py:618-619), backward, Adam."""
+        P, G, pr, nh = self.params.p, self.params.g, self.precision, self.nh
+        z = self.forward(x, T, keep=True)
+        _, dz, _, _ = ops.gae_loss_grad(z, labels, 1.0, 1.0, use_pos_weight=False, loss=self.loss)
+        dout = dz
+        for l in reversed(range(len(self.layers))):
+            L, c = self.layers[l], self._cache[l]
+            W, F = nh * L["F"], L["F"]
+            dhs = torch.empty_like(c["hs"])                                           # [n, 2W]: d projection | d skip
+            dH, dskip = dhs[:, :W], dhs[:, W:]
+            n = dout.shape[0]
+            dact = torch.empty_like(c["out"])
+            ops.check(ops.lib().b2_gat_combine_bwd_f32(ops._p(dout), ops._rowmajor(dout, "dout"), ops._p(c["out"]),
+                                                       ops._rowmajor(c["out"], "out"), n, nh, F, int(L["concat"]), ops.ACT[L["act"]],
+                                                       ops._p(dskip), ops._rowmajor(dskip, "dskip"), ops._p(dact),
+                                                       ops._rowmajor(dact, "dact"), ops._stream()), "b2_gat_combine_bwd_f32")
+            ops.colsum(dact, out=G[f"l{l}.bias"])
+            H = c["hs"][:, :W]
+            dHm, da_src, da_trg = ops.gat_aggregate_bwd(T, Tt, t_perm, H, P[f"l{l}.a_src"], P[f"l{l}.a_trg"], c["s_src"], c["s_trg"],
+                                                        c["alpha"], dskip, nh)
+            dH.copy_(dHm)
+            G[f"l{l}.a_src"].copy_(da_src)
+            G[f"l{l}.a_trg"].copy_(da_trg)
+            ops.gemm(dhs, c["x"], transA=True, out=G[f"l{l}.projskip"], precision=pr)
+            if l > 0:
+                dout = ops.gemm(dhs, P[f"l{l}.projskip"], precision=pr)
+        self.params.adam_step(self.lr)
+        return z

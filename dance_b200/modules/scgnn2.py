@@ -26,7 +26,7 @@ import numpy as np
 import torch
 
 from .. import ops
-from ..engine import FeatureAEEngine, GraphAEEngine
+from ..engine import FeatureAEEngine, GATEngine, GraphAEEngine
 
 logger = logging.getLogger("dance_b200.scgnn2")
 
@@ -93,8 +93,8 @@ def build_knn_graph(x_embed: torch.Tensor, neighborhood_factor):
 def graph_AE_handler(X_embed, CCC_graph, args, param, dense_recon_max_cells: int = 4096):
     """Graph autoencoder stage, GCN branch (scgnn2.py:530-600): returns (embed, recon_graph, edgeList, adj)."""
     logger.info("Starting Graph AE")
-    if args.graph_AE_use_GAT:
-        raise NotImplementedError("graph_AE_use_GAT branch is not wired into graph_AE_handler yet")
+    if args.graph_AE_use_GAT and args.graph_AE_GAT_dropout:
+        raise NotImplementedError("graph_AE_GAT_dropout > 0 is not built (the example default is 0)")
     if args.graph_AE_concat_prev_embed and param["epoch_num"] > 0:
         raise NotImplementedError("graph_AE_concat_prev_embed is not built")
     if args.graph_AE_retain_weights:
@@ -115,6 +115,22 @@ def graph_AE_handler(X_embed, CCC_graph, args, param, dense_recon_max_cells: int
     norm = n * n / float((n * n - adj_sum) * 2)                                 # scgnn2.py:568-569
     labels = ops.CSR(A.rowptr, A.colidx, None, A.shape)                         # A + I: pattern of Â, unit entries
     xin = torch.from_numpy(np.ascontiguousarray(zD, dtype=np.float32)).to(dev)
+    if args.graph_AE_use_GAT:
+        # edge_index = edgeList (i → its k neighbours), directed, no self loops (scgnn2.py:560-563); the kernels
+        # index the graph by TARGET node, i.e. the transpose of the regular kNN-list CSR
+        k = knn_idx.shape[1]
+        src_csr = ops.CSR(torch.arange(0, n * k + 1, k, dtype=torch.int32, device=dev), knn_idx.reshape(-1).contiguous(), None, (n, n))
+        T, _ = ops.csr_transpose(src_csr)
+        Tt, t_perm = ops.csr_transpose(T)
+        geng = GATEngine(X.shape[1], args.gat_hid_embed, args.graph_AE_embedding_size, args.gat_multi_heads, device=dev,
+                         lr=args.graph_AE_learning_rate, precision=param.get("precision"), seed=param.get("seed"))
+        z = None
+        for epoch in range(args.graph_AE_epoch):
+            z = geng.train_step(xin, T, Tt, t_perm, labels)                         # loss_function: plain BCE (scgnn2.py:581)
+            if logger.isEnabledFor(logging.INFO):
+                logger.info(f"Epoch: {epoch+1}/{args.graph_AE_epoch}, Current loss: {geng.loss.item():.4f}")
+        param["_graph_AE_engine"] = geng
+        return _graph_ae_outputs(z, n, knn_idx, knn_dist, A, dense_recon_max_cells)
     eng = GraphAEEngine(X.shape[1], args.graph_AE_embedding_size, device=dev, lr=args.graph_AE_learning_rate,
                         precision=param.get("precision"), seed=param.get("seed"))
     gen = torch.Generator(device=dev)
@@ -126,12 +142,16 @@ def graph_AE_handler(X_embed, CCC_graph, args, param, dense_recon_max_cells: int
         z, _, _ = eng.train_step(xin, A, labels, norm, pos_weight, eps)
         if logger.isEnabledFor(logging.INFO):
             logger.info(f"Epoch: {epoch+1}/{args.graph_AE_epoch}, Current loss: {eng.loss.item():.4f}")
+    param["_graph_AE_engine"] = eng
+    return _graph_ae_outputs(z, n, knn_idx, knn_dist, A, dense_recon_max_cells)
+
+
+def _graph_ae_outputs(z, n, knn_idx, knn_dist, A, dense_recon_max_cells):
     embed_out = z.cpu().numpy()
     recon = (z @ z.t()).cpu().numpy() if n <= dense_recon_max_cells else None   # InnerProductDecoder output, small N only
     k = knn_idx.shape[1]
     edge_index = np.stack([np.repeat(np.arange(n), k), knn_idx.cpu().numpy().reshape(-1).astype(np.int64)], 1)
     edge_w = 1.0 / (knn_dist.cpu().numpy().reshape(-1) + 1e-16)                 # scgnn2.py:686
-    param["_graph_AE_engine"] = eng
     adj = A.to_scipy()
     adj.data[:] = 1.0
     adj.setdiag(0)

@@ -389,3 +389,80 @@ def normalize_total_log1p_(X: torch.Tensor, target_sum: Optional[float] = None, 
                                              int(normalize), int(log1p), float(base or 0.0), _p(ws), ws.numel(),
                                              _stream()), "b2_normalize_total_log1p_f32")
     return X
+
+
+# ----------------------------------------------------------------------------- GAT
+SCORE_ACT = {"leakyrelu": 0, "sigmoid": 1}
+SHIFT = {"global": 0, "segment": 1}
+
+
+def gat_scores(H, a_src, a_trg, nheads: int):
+    """s_src[n,h] = <H[n,h,:], a_src[h,:]> (scgnn2.py:1016-1017)."""
+    _chk(H, torch.float32, "H", 2)
+    n, W = H.shape
+    F = W // nheads
+    s_src = torch.empty((n, nheads), dtype=torch.float32, device=H.device)
+    s_trg = torch.empty((n, nheads), dtype=torch.float32, device=H.device)
+    check(lib().b2_gat_scores_f32(_p(H), _rowmajor(H, "H"), _p(a_src), _p(a_trg), n, nheads, F, _p(s_src), _p(s_trg), _stream()),
+          "b2_gat_scores_f32")
+    return s_src, s_trg
+
+
+def gat_aggregate_fwd(T: CSR, H, s_src, s_trg, nheads: int, score_act="leakyrelu", slope=0.2, shift="global",
+                      out=None, keep_alpha=True):
+    """Fused edge softmax + aggregate on the target-indexed CSR ``T``; returns (out, alpha, gmax)."""
+    n, W = H.shape
+    F = W // nheads
+    if out is None:
+        out = torch.empty((n, W), dtype=torch.float32, device=H.device)
+    gmax = torch.empty(1, dtype=torch.float32, device=H.device)
+    act, sm = SCORE_ACT[score_act], SHIFT[shift]
+    if sm == 0:
+        check(lib().b2_gat_edge_max_f32(_p(T.rowptr), _p(T.colidx), _p(s_src), _p(s_trg), n, nheads, act, slope, _p(gmax),
+                                        _stream()), "b2_gat_edge_max_f32")
+    alpha = torch.empty((T.nnz, nheads), dtype=torch.float32, device=H.device) if keep_alpha else None
+    check(lib().b2_gat_aggregate_fwd_f32(_p(T.rowptr), _p(T.colidx), _p(H), _rowmajor(H, "H"), _p(s_src), _p(s_trg), n, nheads,
+                                         F, act, slope, sm, _p(gmax), _p(out), _rowmajor(out, "out"), _p(alpha), _stream()),
+          "b2_gat_aggregate_fwd_f32")
+    return out, alpha, gmax
+
+
+def gat_aggregate_bwd(T: CSR, Tt: CSR, t_perm, H, a_src, a_trg, s_src, s_trg, alpha, dOut, nheads: int,
+                      score_act="leakyrelu", slope=0.2):
+    """Returns (dH, da_src, da_trg)."""
+    n, W = H.shape
+    F = W // nheads
+    dev = H.device
+    dH = torch.empty((n, W), dtype=torch.float32, device=dev)
+    da_src = torch.empty(W, dtype=torch.float32, device=dev)
+    da_trg = torch.empty(W, dtype=torch.float32, device=dev)
+    ds_s = torch.empty(n * nheads, dtype=torch.float32, device=dev)
+    ds_t = torch.empty(n * nheads, dtype=torch.float32, device=dev)
+    dpre = torch.empty(max(T.nnz, 1) * nheads, dtype=torch.float32, device=dev)
+    check(lib().b2_gat_aggregate_bwd_f32(_p(T.rowptr), _p(T.colidx), _p(Tt.rowptr), _p(Tt.colidx), _p(t_perm), _p(H),
+                                         _rowmajor(H, "H"), _p(a_src), _p(a_trg), _p(s_src), _p(s_trg), _p(alpha), _p(dOut),
+                                         _rowmajor(dOut, "dOut"), n, nheads, F, SCORE_ACT[score_act], slope, _p(dH),
+                                         _rowmajor(dH, "dH"), _p(da_src), _p(da_trg), _p(ds_s), _p(ds_t), _p(dpre), _stream()),
+          "b2_gat_aggregate_bwd_f32")
+    return dH, da_src, da_trg
+
+
+def gat_combine_fwd(agg, skip, bias, nheads: int, concat: bool, act=None):
+    n, W = agg.shape
+    F = W // nheads
+    out = torch.empty((n, W if concat else F), dtype=torch.float32, device=agg.device)
+    check(lib().b2_gat_combine_fwd_f32(_p(agg), _rowmajor(agg, "agg"), _p(skip), _rowmajor(skip, "skip") if skip is not None else 0,
+                                       _p(bias), n, nheads, F, int(concat), ACT[act], _p(out), _rowmajor(out, "out"), _stream()),
+          "b2_gat_combine_fwd_f32")
+    return out
+
+
+def gat_combine_bwd(dout, out, nheads: int, F: int, concat: bool, act=None):
+    """Returns (dpre [n, nheads*F], dact [n, out width])."""
+    n = dout.shape[0]
+    dpre = torch.empty((n, nheads * F), dtype=torch.float32, device=dout.device)
+    dact = torch.empty_like(out)
+    check(lib().b2_gat_combine_bwd_f32(_p(dout), _rowmajor(dout, "dout"), _p(out), _rowmajor(out, "out"), n, nheads, F,
+                                       int(concat), ACT[act], _p(dpre), _rowmajor(dpre, "dpre"), _p(dact), _rowmajor(dact, "dact"),
+                                       _stream()), "b2_gat_combine_bwd_f32")
+    return dpre, dact

@@ -1,0 +1,5 @@
+from .base import BaseTransform  # noqa: F401
+from .interface import AnnDataTransform  # noqa: F401
+from .misc import Compose, SetConfig  # noqa: F401
+from .normalize import Log1P, NormalizeTotal, NormalizeTotalLog1P  # noqa: F401
+from . import pp  # noqa: F401

@@ -220,6 +220,49 @@ int b2_normalize_total_log1p_f32(float* X, int64_t ldx, int32_t n, int32_t g,
                                  int do_normalize, int do_log1p, float base,
                                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------
+ * K4  GAT layer (scGNN GATLayer scgnn2.py:989-1215; STAGATE GATConv stagate.py:61-125)
+ *   Graph = CSR indexed by TARGET node: row v lists the sources u of its in-edges.
+ *   H [n, nheads*F] projected features; s_src/s_trg [n, nheads] dense.
+ *   e = score_act(s_src[u] + s_trg[v]); α = softmax over the in-edges of v; out[v] = Σ α·H[u]
+ *   score_act : 0 LeakyReLU(slope) (scgnn2.py:1023), 1 sigmoid (stagate.py:119)
+ *   shift_mode: 0 subtract the GLOBAL max over all edges/heads (scgnn2.py:1076; value in
+ *               gmax_dev[0], produced by b2_gat_edge_max_f32), 1 per-target max (PyG softmax)
+ *   alpha_out [nnz, nheads] or NULL (needed by the backward pass).  nheads*F <= 512.
+ * ---------------------------------------------------------------------- */
+int b2_gat_scores_f32(const float* H, int64_t ldh, const float* a_src, const float* a_trg,
+                      int32_t n, int32_t nheads, int32_t F, float* s_src, float* s_trg, void* stream);
+int b2_gat_edge_max_f32(const int32_t* rowptr, const int32_t* colidx,
+                        const float* s_src, const float* s_trg, int32_t n, int32_t nheads,
+                        int score_act, float slope, float* gmax_dev, void* stream);
+int b2_gat_aggregate_fwd_f32(const int32_t* rowptr, const int32_t* colidx,
+                             const float* H, int64_t ldh, const float* s_src, const float* s_trg,
+                             int32_t n, int32_t nheads, int32_t F,
+                             int score_act, float slope, int shift_mode, const float* gmax_dev,
+                             float* out, int64_t ldo, float* alpha_out, void* stream);
+/* Backward of scores + aggregate.  (t_rowptr, t_colidx, t_perm) = b2_csr_transpose of the target
+ * CSR.  Outputs: dH [n, nheads*F] (overwritten: message path + score path), da_src/da_trg
+ * [nheads*F] (overwritten).  ds_src_ws/ds_trg_ws [n*nheads] and dpre_edge_ws [nnz*nheads] are
+ * caller-provided scratch. */
+int b2_gat_aggregate_bwd_f32(const int32_t* rowptr, const int32_t* colidx,
+                             const int32_t* t_rowptr, const int32_t* t_colidx, const int32_t* t_perm,
+                             const float* H, int64_t ldh, const float* a_src, const float* a_trg,
+                             const float* s_src, const float* s_trg, const float* alpha,
+                             const float* dOut, int64_t lddo, int32_t n, int32_t nheads, int32_t F,
+                             int score_act, float slope,
+                             float* dH, int64_t lddh, float* da_src, float* da_trg,
+                             float* ds_src_ws, float* ds_trg_ws, float* dpre_edge_ws, void* stream);
+/* skip connection + concat | head-mean + bias + activation (scgnn2.py:1189-1215):
+ *   concat: out[n, nheads*F] = act(agg + skip + bias) ; else out[n,F] = act(mean_h(agg + skip) + bias)
+ *   skip may be NULL.  Backward: dpre [n, nheads*F] = d(agg) = d(skip); dact [n, OW] (optional) is the
+ *   gradient before the bias add (its column sums are the bias gradient). */
+int b2_gat_combine_fwd_f32(const float* agg, int64_t ldagg, const float* skip, int64_t ldskip, const float* bias,
+                           int32_t n, int32_t nheads, int32_t F, int concat, int act,
+                           float* out, int64_t ldo, void* stream);
+int b2_gat_combine_bwd_f32(const float* dout, int64_t lddo, const float* out, int64_t ldo,
+                           int32_t n, int32_t nheads, int32_t F, int concat, int act,
+                           float* dpre, int64_t ldp, float* dact, int64_t ldact, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,8 @@ def _knn_graph_fixture(ref):
     n = X.shape[0]
     pos_weight = float(n * n - adj_train.sum()) / adj_train.sum()
     norm = n * n / float((n * n - adj_train.sum()) * 2)
+    global _KNN_IDX
+    _KNN_IDX = knn_idx
     np.savez_compressed(OUT / "knn_graph.npz", X=X, k=k, knn_idx=knn_idx, knn_w=knn_w,
                         adj_indptr=adj_train.indptr, adj_indices=adj_train.indices,
                         norm_indptr=an.indptr, norm_indices=an.indices, norm_data=an.data.astype(np.float32),
@@ -80,6 +82,39 @@ def _graph_ae_fixture(ref, X, adj_train, an, pos_weight, norm):
         hidden1.weight.copy_(torch.from_numpy(out["w1"]))
         out["hidden1"] = hidden1(x, adj_t).numpy()
     np.savez_compressed(OUT / "graph_ae_gcn.npz", **out)
+
+
+def _gat_fixture(ref, X, knn_idx, adj_train):
+    """Graph_AE with use_GAT=True (scgnn2.py:376-378, 883-1215, 560-563, 618-619): forward, plain-BCE loss,
+    gradients of every GAT parameter, one Adam step."""
+    torch.manual_seed(13)
+    n, k = knn_idx.shape
+    model = ref.Graph_AE(X.shape[1], 16, 0, 2, 64)
+    # non-zero biases so that the bias path is exercised (the reference initialises them to zero)
+    with torch.no_grad():
+        for layer in model.gat.gat_net:
+            layer.bias.normal_(0, 0.1)
+    sd = {k_: v.detach().clone().numpy() for k_, v in model.state_dict().items() if k_.startswith("gat.")}
+    edge_index = torch.from_numpy(np.stack([np.repeat(np.arange(n), k), knn_idx.reshape(-1)]).astype(np.int64))
+    labels = torch.from_numpy((adj_train + sp.eye(n)).toarray()).float()
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    opt.zero_grad()
+    x = torch.from_numpy(X)
+    embed, _, recon = model(x, edge_index, use_GAT=True)
+    loss = ref.loss_function(preds=recon, labels=labels)
+    loss.backward()
+    out = {"init." + k_: v for k_, v in sd.items()}
+    out.update(z=embed.detach().numpy(), loss=np.float64(loss.item()))
+    for k_, p in model.named_parameters():
+        if k_.startswith("gat."):
+            out["grad." + k_] = p.grad.numpy().copy()
+    # layer-1 output for a layer-level check
+    with torch.no_grad():
+        out["layer0_out"] = model.gat.gat_net[0]((x, edge_index))[0].numpy()
+    opt.step()
+    out.update({"after." + k_: v.detach().numpy().copy() for k_, v in model.state_dict().items() if k_.startswith("gat.")})
+    np.savez_compressed(OUT / "graph_ae_gat.npz", **out)
 
 
 def sample_index(size: int) -> np.ndarray:
@@ -147,6 +182,7 @@ def main():
         warnings.simplefilter("ignore")
         X, adj_train, an, pw, norm = _knn_graph_fixture(ref)
         _graph_ae_fixture(ref, X, adj_train, an, pw, norm)
+        _gat_fixture(ref, X, _KNN_IDX, adj_train)
         _feature_ae_fixture(ref)
         _matrix_fixture()
     for f in sorted(OUT.glob("*.npz")):

@@ -142,6 +142,45 @@ def graph_ae_gcn_loss(x, w1, w2, w3, adj_norm_sp: sp.spmatrix, adj_train: sp.spm
     return loss, z, mu, logvar, hidden1
 
 
+# --------------------------------------------------------------------------- Graph AE (GAT branch)
+def gat_layer(x, edge_index, proj_w, skip_w, a_src, a_trg, bias, concat: bool, act=None):
+    """GATLayer.forward with dropout 0 (scgnn2.py:989-1051 and helpers :1057-1215).
+
+    edge_index[0] = source nodes, edge_index[1] = target nodes; scores use LeakyReLU(0.2), the softmax shift is
+    the GLOBAL max over all edges and heads (:1076), the denominator gets +1e-16 (:1086), the skip connection is
+    the projected one (the reference adds the raw input only when FIN == FOUT, :1194-1197)."""
+    nh, F_ = a_src.shape[1], a_src.shape[2]
+    n = x.shape[0]
+    src, trg = edge_index[0], edge_index[1]
+    proj = (x @ proj_w.t()).view(-1, nh, F_)
+    s_src = (proj * a_src).sum(-1)
+    s_trg = (proj * a_trg).sum(-1)
+    scores = torch.nn.functional.leaky_relu(s_src.index_select(0, src) + s_trg.index_select(0, trg), 0.2)
+    ex = (scores - scores.max()).exp()
+    denom = torch.zeros(n, nh, dtype=ex.dtype).index_add_(0, trg, ex)
+    att = (ex / (denom.index_select(0, trg) + 1e-16)).unsqueeze(-1)
+    out = torch.zeros(n, nh, F_, dtype=x.dtype).index_add_(0, trg, proj.index_select(0, src) * att)
+    if out.shape[-1] == x.shape[-1]:
+        out = out + x.unsqueeze(1)
+    else:
+        out = out + (x @ skip_w.t()).view(-1, nh, F_)
+    out = out.view(-1, nh * F_) if concat else out.mean(dim=1)
+    if bias is not None:
+        out = out + bias
+    return act(out) if act is not None else out
+
+
+def graph_ae_gat_forward(x, edge_index, sd):
+    """Graph_AE.encode_gat (scgnn2.py:385-386): 2 GAT layers — concat+ELU, then head-mean — from a reference
+    state_dict (keys gat.gat_net.{l}.*)."""
+    h = x
+    for l, (concat, act) in enumerate(((True, torch.nn.functional.elu), (False, None))):
+        pre = f"gat.gat_net.{l}."
+        h = gat_layer(h, edge_index, sd[pre + "linear_proj.weight"], sd[pre + "skip_proj.weight"], sd[pre + "scoring_fn_source"],
+                      sd[pre + "scoring_fn_target"], sd[pre + "bias"], concat, act)
+    return h
+
+
 # --------------------------------------------------------------------------- Feature AE
 class FeatureAE(torch.nn.Module):
     """Feature_AE (scgnn2.py:338-370): dim→512→128→512→dim, ReLU after every layer."""

@@ -102,3 +102,41 @@ def test_full_size_properties_spmm_linearity_and_symmetry(cuda):
     # D^-1/2 (A+I) D^-1/2 applied to sqrt(deg) returns sqrt(deg)
     deg = (A.rowptr[1:] - A.rowptr[:-1]).float().sqrt().unsqueeze(1).repeat(1, 4).contiguous()
     assert rel_err(ops.spmm(A, deg).cpu().numpy(), deg.cpu().numpy()) < 1e-5
+
+
+def _gat_graph(golden, cuda):
+    """Target-indexed CSR of the directed kNN edges (i → its neighbours), its transpose and the edge permutation."""
+    from dance_b200 import ops
+    g = golden("knn_graph")
+    n, k = g["knn_idx"].shape
+    src_csr = ops.CSR(torch.arange(0, n * k + 1, k, dtype=torch.int32, device=cuda),
+                      torch.from_numpy(g["knn_idx"].reshape(-1).astype(np.int32)).to(cuda), None, (n, n))
+    T, _ = ops.csr_transpose(src_csr)      # rows = targets (the neighbour), cols = sources (the query cell)
+    Tt, t_perm = ops.csr_transpose(T)
+    adj = sp.csr_matrix((np.ones(len(g["adj_indices"])), g["adj_indices"], g["adj_indptr"]), shape=(n, n))
+    L = (adj + sp.eye(n)).tocsr()
+    L.sort_indices()
+    return g, T, Tt, t_perm, ops.CSR.from_scipy(L, cuda, with_values=False)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_gat_engine_matches_reference(cuda, golden, precision):
+    """Graph_AE GAT branch (2 GATLayers + plain-BCE decoder loss): embedding, layer-1 output, loss, every
+    parameter gradient and the weights after one Adam step — ≤1e-4 rel against the reference fixture."""
+    from dance_b200.engine import GATEngine
+    g, T, Tt, t_perm, L = _gat_graph(golden, cuda)
+    gg = golden("graph_ae_gat")
+    x = torch.from_numpy(g["X"]).to(cuda)
+    eng = GATEngine(x.shape[1], 64, 16, 2, device=cuda, lr=1e-2, precision=precision)
+    eng.load_state_dict({k[len("init."):]: gg[k] for k in gg.files if k.startswith("init.")})
+    z = eng.forward(x, T, keep=True)
+    assert rel_err(eng._cache[0]["out"].cpu().numpy(), gg["layer0_out"]) < 1e-4
+    assert rel_err(z.cpu().numpy(), gg["z"]) < 1e-4
+    z = eng.train_step(x, T, Tt, t_perm, L)
+    assert abs(eng.loss.item() - float(gg["loss"])) < 1e-4 * float(gg["loss"])
+    for k, gt in eng.grads().items():
+        want = gg["grad." + k]
+        assert rel_err(gt.cpu().numpy().reshape(want.shape), want) < 2e-4, k
+    for k, v in eng.state_dict().items():
+        want = gg["after." + k]
+        assert rel_err(v.cpu().numpy().reshape(want.shape), want) < 1e-4, k

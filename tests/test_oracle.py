@@ -158,3 +158,22 @@ def test_port_vs_live_reference_fractional_neighbourhood():
     _, adj_train_ref, _ = ref.feature2adj(X, 0.05, False)
     adj, idx = port.feature2adj(X, 0.05)
     assert idx.shape[1] == 6 and (sp.csr_matrix(adj_train_ref) != adj).nnz == 0
+
+
+def test_graph_ae_gat_golden(golden):
+    """oracle.port GAT restatement vs the fixture generated from the reference's Graph_AE(use_GAT=True)."""
+    g = golden("knn_graph")
+    gg = golden("graph_ae_gat")
+    n, k = g["knn_idx"].shape
+    X = torch.from_numpy(g["X"])
+    edge_index = torch.from_numpy(np.stack([np.repeat(np.arange(n), k), g["knn_idx"].reshape(-1)]).astype(np.int64))
+    sd = {k_[len("init."):]: torch.from_numpy(gg[k_]).requires_grad_() for k_ in gg.files if k_.startswith("init.")}
+    z = port.graph_ae_gat_forward(X, edge_index, sd)
+    assert rel_err(z.detach().numpy(), gg["z"]) < 1e-6
+    adj = sp.csr_matrix((np.ones(len(g["adj_indices"])), g["adj_indices"], g["adj_indptr"]), shape=(n, n))
+    labels = torch.from_numpy((adj + sp.eye(n)).toarray()).float()
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(z @ z.t(), labels)
+    loss.backward()
+    assert abs(loss.item() - float(gg["loss"])) < 1e-6 * float(gg["loss"])
+    for k_, v in sd.items():
+        assert rel_err(v.grad.numpy(), gg["grad." + k_]) < 1e-5, k_
