@@ -15,9 +15,8 @@
 //            issuing thread accumulates lo·hi + hi·lo + hi·hi  (error ~2^-21 relative).
 //
 // Replaces torch.mm / nn.Linear on the reference path (scgnn2.py:352-370, 499).
-#include "common.cuh"
+#include "tc_common.cuh"
 
-#include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -49,105 +48,6 @@ struct Params {
   int tiles_m, tiles_n, splits, kb_per_split, kb_total, stages;
   unsigned mn_lbo, mn_sbo, mn_layout;   // MN-major descriptor fields (bring-up overridable, see gemm_tc())
 };
-
-// ---- PTX wrappers ------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// arrives on the mbarrier once all previously issued tcgen05.mma of this thread have completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// UMMA shared-memory matrix descriptor, sm_100 descriptor version 1.
-//   K-major  (layout SWIZZLE_128B = 2): rows of 128 B (32 tf32 along K), 8-row groups SBO = 1024 B
-//             apart, LBO unused (1); TMA swizzle 128B (16-byte chunks XOR row%8)
-//   MN-major (layout SWIZZLE_128B_BASE32B = 1 — the only legal smem layout for MN-major 32-bit
-//             operands): column blocks of [BK k-rows x 128 B (32 elements along M/N)], blocks LBO =
-//             BK*128 B apart, 4-k-row swizzle atoms SBO = 512 B apart; TMA swizzle 128B_ATOM_32B
-//             (32-byte chunks XOR row%4)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
-  d |= (uint64_t)layout << 61;
-  return d;
-}
-
-// kind::tf32 instruction descriptor: D fp32, A/B tf32, M = 128, N = BN, operand major-ness bits
-__device__ __forceinline__ uint32_t umma_idesc(int BN, int a_mn, int b_mn) {
-  uint32_t d = 0;
-  d |= 1u << 4;                       // c_format = F32
-  d |= 2u << 7;                       // a_format = TF32
-  d |= 2u << 10;                      // b_format = TF32
-  d |= (uint32_t)(a_mn & 1) << 15;    // a_major
-  d |= (uint32_t)(b_mn & 1) << 16;    // b_major
-  d |= (uint32_t)(BN >> 3) << 17;     // n_dim
-  d |= (uint32_t)(BM >> 4) << 24;     // m_dim
-  return d;
-}
 
 struct StageLayout {
   uint32_t a_hi, a_lo, b_hi, b_lo;  // byte offsets inside one stage
@@ -264,7 +164,7 @@ gemm_tc_kernel(const __grid_constant__ Params p) {
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc(p.BN, p.a_mn, p.b_mn);
+      const uint32_t idesc = umma_idesc(BM, p.BN, p.a_mn, p.b_mn);
       const uint32_t a_lbo = p.a_mn ? p.mn_lbo : 16, b_lbo = p.b_mn ? p.mn_lbo : 16;
       const uint32_t a_kstep = p.a_mn ? 1024u : (uint32_t)(UK * 4), b_kstep = p.b_mn ? 1024u : (uint32_t)(UK * 4);
       const uint32_t a_sbo = p.a_mn ? p.mn_sbo : 1024u, b_sbo = p.b_mn ? p.mn_sbo : 1024u;
@@ -450,8 +350,8 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D fp32 tensor map: `inner` contiguous elements, `outer` rows `ld` elements apart; box = {32, box_outer}
-static bool make_map(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer,
-                     bool mn_major) {
+bool make_tensor_map_f32(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer,
+                         bool mn_major) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t dims[2] = {inner, outer};
@@ -521,11 +421,11 @@ int gemm_tc(const float* A, int64_t lda, int transA, const float* B, int64_t ldb
   Params p;
   memset(&p, 0, sizeof(p));
   // A operand: K-major when A is [M,K] row-major, MN-major when stored [K,M]
-  const bool okA = transA ? make_map(&p.tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BK, true)
-                          : make_map(&p.tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BM, false);
+  const bool okA = transA ? make_tensor_map_f32(&p.tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BK, true)
+                          : make_tensor_map_f32(&p.tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BM, false);
   // B operand (UMMA B is N x K): K-major when B is stored [N,K] (transB), MN-major when [K,N]
-  const bool okB = transB ? make_map(&p.tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, (uint32_t)pl.BN, false)
-                          : make_map(&p.tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK, true);
+  const bool okB = transB ? make_tensor_map_f32(&p.tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, (uint32_t)pl.BN, false)
+                          : make_tensor_map_f32(&p.tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK, true);
   if (!okA || !okB) return B2_ERR_UNSUPPORTED;
   p.C = C; p.bias = bias; p.mask = mask; p.ldc = ldc; p.ldmask = ldmask;
   p.M = M; p.N = N; p.K = K; p.BN = pl.BN;

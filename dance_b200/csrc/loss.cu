@@ -246,9 +246,30 @@ gae_kld_kernel(const float* __restrict__ mu, const float* __restrict__ logvar, i
 
 __global__ void gae_finish_kernel(const double* acc, float* loss_out) { loss_out[0] = (float)acc[0]; }
 
+namespace gtc {   // gae_tc.cu: tcgen05 version of the all-pairs part
+size_t workspace_bytes(int32_t n);
+bool eligible(int32_t n, int32_t d, int32_t n_rows);
+int launch(const float* z, int64_t ldz, int32_t n, int32_t d, int32_t row_begin, int32_t n_rows, float coef, float* dz,
+           double* loss_acc, void* ws, size_t ws_bytes, cudaStream_t st);
+}  // namespace gtc
+
+template <int D>
+static int launch_gae_edges(const float* z, int64_t ldz, const int32_t* rp, const int32_t* ci, int32_t row_begin, int32_t n_rows,
+                            float coef, float pw, int use_pw, float* dz, double* acc, cudaStream_t st) {
+  int64_t blocks = ceil_div<int64_t>(n_rows, 8);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  gae_edges_kernel<D><<<(unsigned)blocks, 256, 0, st>>>(z, ldz, rp, ci, row_begin, n_rows, coef, pw, use_pw, dz, acc);
+  B2_CHECK_LAUNCH("gae_edges_kernel");
+  return B2_OK;
+}
+
 template <int D>
 static int launch_gae(const float* z, int64_t ldz, const int32_t* rp, const int32_t* ci, int32_t n, int32_t row_begin,
-                      int32_t n_rows, float coef, float pw, int use_pw, float* dz, double* acc, cudaStream_t st) {
+                      int32_t n_rows, float coef, float pw, int use_pw, float* dz, double* acc, bool skip_allpairs,
+                      cudaStream_t st) {
+  if (skip_allpairs) return launch_gae_edges<D>(z, ldz, rp, ci, row_begin, n_rows, coef, pw, use_pw, dz, acc, st);
   const int row_blocks = ceil_div(n_rows, GaeCfg<D>::ROWS);
   // split the j range so that small graphs still fill the machine
   int j_splits = 1;
@@ -261,12 +282,7 @@ static int launch_gae(const float* z, int64_t ldz, const int32_t* rp, const int3
   dim3 grid(row_blocks, j_splits);
   gae_allpairs_kernel<D><<<grid, GL_THREADS, 0, st>>>(z, ldz, n, row_begin, n_rows, j_chunk, coef, dz, acc);
   B2_CHECK_LAUNCH("gae_allpairs_kernel");
-  int64_t blocks = ceil_div<int64_t>(n_rows, 8);
-  const int64_t cap = (int64_t)sm_count() * 16;
-  if (blocks > cap) blocks = cap;
-  gae_edges_kernel<D><<<(unsigned)blocks, 256, 0, st>>>(z, ldz, rp, ci, row_begin, n_rows, coef, pw, use_pw, dz, acc);
-  B2_CHECK_LAUNCH("gae_edges_kernel");
-  return B2_OK;
+  return launch_gae_edges<D>(z, ldz, rp, ci, row_begin, n_rows, coef, pw, use_pw, dz, acc, st);
 }
 
 }  // namespace b2
@@ -289,7 +305,10 @@ extern "C" int b2_mse_sum_loss_grad_f32(const float* recon, const float* target,
   return B2_OK;
 }
 
-extern "C" size_t b2_gae_loss_workspace_bytes(int32_t n, int32_t d) { return 256; }
+extern "C" size_t b2_gae_loss_workspace_bytes(int32_t n, int32_t d) {
+  // 256 B of accumulators + the hi/lo tf32 split of z (padded to 32 columns) for the tensor-core path
+  return 256 + (d <= 32 ? gtc::workspace_bytes(n) : 0);
+}
 
 extern "C" int b2_gae_loss_grad_f32(const float* z, int64_t ldz, const float* mu, const float* logvar, int64_t ldm,
                                     const int32_t* lab_rowptr, const int32_t* lab_colidx, int32_t n, int32_t d,
@@ -308,11 +327,18 @@ extern "C" int b2_gae_loss_grad_f32(const float* z, int64_t ldz, const float* mu
   B2_CHECK_CUDA(cudaMemsetAsync(dz, 0, sizeof(float) * (size_t)n_rows * d, st));
   const float coef = (use_pos_weight ? norm : 1.f) / ((float)n * (float)n);
   int rc;
+  // large problems: the all-pairs part runs on tcgen05 (gae_tc.cu); the CUDA-core kernel serves small graphs
+  bool tc_done = false;
+  if (gtc::eligible(n, d, n_rows) && workspace_bytes >= 256 + gtc::workspace_bytes(n)) {
+    rc = gtc::launch(z, ldz, n, d, row_begin, n_rows, coef, dz, acc, reinterpret_cast<char*>(workspace) + 256, workspace_bytes - 256, st);
+    if (rc == B2_OK) tc_done = true;
+    else if (rc != B2_ERR_UNSUPPORTED) return rc;
+  }
   switch (d) {
-    case 8: rc = launch_gae<8>(z, ldz, lab_rowptr, lab_colidx, n, row_begin, n_rows, coef, pos_weight, use_pos_weight, dz, acc, st); break;
-    case 16: rc = launch_gae<16>(z, ldz, lab_rowptr, lab_colidx, n, row_begin, n_rows, coef, pos_weight, use_pos_weight, dz, acc, st); break;
-    case 32: rc = launch_gae<32>(z, ldz, lab_rowptr, lab_colidx, n, row_begin, n_rows, coef, pos_weight, use_pos_weight, dz, acc, st); break;
-    case 64: rc = launch_gae<64>(z, ldz, lab_rowptr, lab_colidx, n, row_begin, n_rows, coef, pos_weight, use_pos_weight, dz, acc, st); break;
+    case 8: rc = launch_gae<8>(z, ldz, lab_rowptr, lab_colidx, n, row_begin, n_rows, coef, pos_weight, use_pos_weight, dz, acc, tc_done, st); break;
+    case 16: rc = launch_gae<16>(z, ldz, lab_rowptr, lab_colidx, n, row_begin, n_rows, coef, pos_weight, use_pos_weight, dz, acc, tc_done, st); break;
+    case 32: rc = launch_gae<32>(z, ldz, lab_rowptr, lab_colidx, n, row_begin, n_rows, coef, pos_weight, use_pos_weight, dz, acc, tc_done, st); break;
+    case 64: rc = launch_gae<64>(z, ldz, lab_rowptr, lab_colidx, n, row_begin, n_rows, coef, pos_weight, use_pos_weight, dz, acc, tc_done, st); break;
     default:
       set_error("b2_gae_loss_grad_f32: embedding size %d unsupported (8, 16, 32, 64)", d);
       return B2_ERR_UNSUPPORTED;

@@ -288,7 +288,7 @@ def gae_loss_grad(z, labels: CSR, norm: float, pos_weight: float, mu=None, logva
             raise B2Error("gae_loss_grad: dmu and dlogvar must share a leading dimension")
     if loss is None:
         loss = torch.empty(1, dtype=torch.float32, device=z.device)
-    ws = _workspace(256, z.device)
+    ws = _workspace(lib().b2_gae_loss_workspace_bytes(n, d), z.device)
     check(lib().b2_gae_loss_grad_f32(_p(z), _rowmajor(z, "z"), _p(mu), _p(logvar), ldm, _p(labels.rowptr),
                                      _p(labels.colidx), n, d, row_begin, n_rows, float(norm), float(pos_weight),
                                      int(use_pos_weight),

@@ -264,3 +264,47 @@ def test_gae_loss_matches_dense_reference_formula(cuda, golden):
     loss2, dz2, _, _ = ops.gae_loss_grad(z2.detach().to(cuda), L, 1.0, 1.0, use_pos_weight=False)
     assert abs(loss2.item() - ref2.item()) < 2e-6 * abs(ref2.item())
     assert rel_err(dz2.cpu().numpy(), z2.grad.numpy()) < 1e-5
+
+
+def _dense_gae_reference(z, L_dense, norm, pw, mu=None, lv=None):
+    """fp64 dense restatement of gae_loss_function on the GPU (same formula as oracle.port.gae_loss)."""
+    import torch.nn.functional as F
+    z = z.double().requires_grad_()
+    logits = z @ z.t()
+    n = z.shape[0]
+    cost = norm * F.binary_cross_entropy_with_logits(logits, L_dense, pos_weight=L_dense * pw)
+    cost.backward()
+    return cost.item(), z.grad
+
+
+@pytest.mark.parametrize("n,d", [(3000, 16), (2500, 16), (4133, 8), (2304, 32)])
+def test_gae_loss_tensor_core_path(cuda, n, d):
+    """tcgen05 decoder (S in TMEM → SFU → G in TMEM → dZ) vs the dense fp64 formula and vs the CUDA-core kernel."""
+    import os
+    from dance_b200 import ops
+    from oracle import port
+    rng = np.random.default_rng(n)
+    z = torch.from_numpy((rng.normal(size=(n, d)) * 0.4).astype(np.float32)).to(cuda)
+    adj, _ = port.feature2adj(port.synthetic_embedding(n, d=8, seed=1), 6)
+    Lsp = (adj + sp.eye(n)).tocsr()
+    Lsp.sort_indices()
+    L = ops.CSR.from_scipy(Lsp, cuda, with_values=False)
+    Ld = torch.from_numpy(Lsp.toarray()).to(cuda).double()
+    pw, norm = port.gae_norm_constants(adj)
+    ref_loss, ref_dz = _dense_gae_reference(z, Ld, norm, pw)
+    loss_tc, dz_tc, _, _ = ops.gae_loss_grad(z, L, norm, pw)
+    os.environ["B2_GAE_NO_TC"] = "1"
+    try:
+        loss_cc, dz_cc, _, _ = ops.gae_loss_grad(z, L, norm, pw)
+    finally:
+        del os.environ["B2_GAE_NO_TC"]
+    assert abs(loss_tc.item() - ref_loss) < 2e-6 * abs(ref_loss), (loss_tc.item(), ref_loss)
+    assert abs(loss_cc.item() - ref_loss) < 2e-6 * abs(ref_loss)
+    assert rel_err(dz_tc.cpu().numpy(), ref_dz.cpu().numpy()) < 2e-5
+    assert rel_err(dz_cc.cpu().numpy(), ref_dz.cpu().numpy()) < 2e-5
+    # row-sharded form: two shards reproduce the full gradient and the loss is additive
+    h = n // 2 + 7
+    la, dza, _, _ = ops.gae_loss_grad(z, ops.CSR.from_scipy(Lsp[:h], cuda, with_values=False), norm, pw, row_begin=0, n_rows=h)
+    lb, dzb, _, _ = ops.gae_loss_grad(z, ops.CSR.from_scipy(Lsp[h:], cuda, with_values=False), norm, pw, row_begin=h, n_rows=n - h)
+    assert abs(la.item() + lb.item() - ref_loss) < 2e-6 * abs(ref_loss)
+    assert rel_err(torch.cat([dza, dzb]).cpu().numpy(), ref_dz.cpu().numpy()) < 2e-5
