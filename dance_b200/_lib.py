@@ -50,6 +50,11 @@ _SIGNATURES = {
     "b2_gat_combine_fwd_f32": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i32, c_i32, c_i32, C.c_int, C.c_int, c_vp, c_i64, c_vp]),
     "b2_gat_combine_bwd_f32": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32, C.c_int, C.c_int, c_vp, c_i64, c_vp, c_i64,
                                          c_vp]),
+    "b2_cellgene_graph_workspace_bytes": (c_sz, [c_i32, c_i32]),
+    "b2_cellgene_graph_count": (C.c_int, [c_vp, c_i64, c_i32, c_i32, C.POINTER(c_i64), c_vp, c_sz, c_vp]),
+    "b2_cellgene_graph_fill": (C.c_int, [c_vp, c_i64, c_i32, c_i32, C.c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "b2_sage_edge_values_f32": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
+    "b2_softmax_ce_sum_f32": (C.c_int, [c_vp, c_i64, c_vp, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp]),
     "b2_normalize_total_workspace_bytes": (c_sz, [c_i32, c_i32]),
     "b2_normalize_total_log1p_f32": (C.c_int, [c_vp, c_i64, c_i32, c_i32, c_f32, c_f32, C.c_int, C.c_int, c_f32, c_vp,
                                                c_sz, c_vp]),

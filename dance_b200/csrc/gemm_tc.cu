@@ -350,20 +350,25 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D fp32 tensor map: `inner` contiguous elements, `outer` rows `ld` elements apart; box = {32, box_outer}
-bool make_tensor_map_f32(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer,
-                         bool mn_major) {
+// general 2-D fp32 tensor map: box = {box_inner, box_outer}; swizzle: 0 none, 1 32B, 2 64B, 3 128B, 4 128B_ATOM_32B
+bool make_tensor_map_f32_ex(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                            uint32_t box_outer, int swizzle) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {ld * sizeof(float)};
-  cuuint32_t box[2] = {32, box_outer};
+  cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUtensorMapSwizzle mn_swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-  if (const char* e = getenv("B2_TC_MN_SWZ")) mn_swz = (CUtensorMapSwizzle)atoi(e);   // bring-up probe only
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? mn_swz : CU_TENSOR_MAP_SWIZZLE_128B,
-             CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, (CUtensorMapSwizzle)swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool make_tensor_map_f32(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer,
+                         bool mn_major) {
+  int mn_swz = (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  if (const char* e = getenv("B2_TC_MN_SWZ")) mn_swz = atoi(e);   // bring-up probe only
+  return make_tensor_map_f32_ex(map, ptr, inner, outer, ld, 32, box_outer, mn_major ? mn_swz : (int)CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 struct Plan {

@@ -38,7 +38,74 @@ spmm_csr_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
 #pragma unroll
     for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    for (int32_t base = start; base < end; base += G) {
+    // (col,val) pairs of the first PRE*G entries are fetched in ONE batch of independent loads (most kNN-graph rows
+    // are shorter than that), so the dependent chain per row is rowptr → pairs → gathers instead of one round trip
+    // per G-entry chunk.
+    constexpr int PRE = (G <= 8) ? 4 : ((G == 16) ? 2 : 1);
+    int32_t pc[PRE];
+    float pw[PRE];
+#pragma unroll
+    for (int q = 0; q < PRE; ++q) {
+      const int32_t e = start + q * G + gl;
+      pc[q] = 0;
+      pw[q] = 0.f;
+      if (e < end) {
+        pc[q] = __ldg(colidx + e);
+        pw[q] = vals ? __ldg(vals + e) : 1.f;
+      }
+    }
+    int32_t base = start;
+#pragma unroll
+    for (int q = 0; q < PRE; ++q) {
+      if (base >= end) break;
+      const int32_t c = pc[q];
+      const float w = pw[q];
+      const int cnt = min(G, end - base);
+      if (cnt == G) {
+        float4 x[TCH][VPL];
+#pragma unroll
+        for (int t0 = 0; t0 < G; t0 += TCH) {
+#pragma unroll
+          for (int t = 0; t < TCH; ++t) {
+            const int32_t cc = __shfl_sync(gmask, c, t0 + t, G);
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+              const int j = gl + v * G;
+              x[t][v] = (j < F4) ? __ldg(X4 + (int64_t)cc * ldx4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < TCH; ++t) {
+            const float ww = __shfl_sync(gmask, w, t0 + t, G);
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+              acc[v].x = fmaf(ww, x[t][v].x, acc[v].x);
+              acc[v].y = fmaf(ww, x[t][v].y, acc[v].y);
+              acc[v].z = fmaf(ww, x[t][v].z, acc[v].z);
+              acc[v].w = fmaf(ww, x[t][v].w, acc[v].w);
+            }
+          }
+        }
+      } else {
+        for (int t = 0; t < cnt; ++t) {
+          const int32_t cc = __shfl_sync(gmask, c, t, G);
+          const float ww = __shfl_sync(gmask, w, t, G);
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            const int j = gl + v * G;
+            if (j < F4) {
+              const float4 xv = __ldg(X4 + (int64_t)cc * ldx4 + j);
+              acc[v].x = fmaf(ww, xv.x, acc[v].x);
+              acc[v].y = fmaf(ww, xv.y, acc[v].y);
+              acc[v].z = fmaf(ww, xv.z, acc[v].z);
+              acc[v].w = fmaf(ww, xv.w, acc[v].w);
+            }
+          }
+        }
+      }
+      base += G;
+    }
+    for (; base < end; base += G) {
       const int32_t e = base + gl;
       int32_t c = 0;
       float w = 0.f;

@@ -466,3 +466,45 @@ def gat_combine_bwd(dout, out, nheads: int, F: int, concat: bool, act=None):
                                        int(concat), ACT[act], _p(dpre), _rowmajor(dpre, "dpre"), _p(dact), _rowmajor(dact, "dact"),
                                        _stream()), "b2_gat_combine_bwd_f32")
     return dpre, dact
+
+
+# ----------------------------------------------------------------------------- scDeepSort path
+def cellgene_graph(X: torch.Tensor, normalize_edges: bool = True):
+    """CellFeatureGraph edge list (cell_feature_graph.py:34-79): returns (src int64, dst int64, w fp32 [E,1], nnz)."""
+    _chk(X, torch.float32, "X", 2)
+    n, g = X.shape
+    nbytes = lib().b2_cellgene_graph_workspace_bytes(n, g)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=X.device)      # private: must survive between count and fill
+    nnz = C.c_int64(0)
+    check(lib().b2_cellgene_graph_count(_p(X), _rowmajor(X, "X"), n, g, C.byref(nnz), _p(ws), ws.numel(), _stream()),
+          "b2_cellgene_graph_count")
+    E = 2 * nnz.value + n + g
+    src = torch.empty(E, dtype=torch.int64, device=X.device)
+    dst = torch.empty(E, dtype=torch.int64, device=X.device)
+    w = torch.empty((E, 1), dtype=torch.float32, device=X.device)
+    check(lib().b2_cellgene_graph_fill(_p(X), _rowmajor(X, "X"), n, g, int(normalize_edges), nnz.value, _p(src), _p(dst), _p(w),
+                                       _p(ws), ws.numel(), _stream()), "b2_cellgene_graph_fill")
+    return src, dst, w, nnz.value
+
+
+def sage_edge_values(T: CSR, w: torch.Tensor, alpha: torch.Tensor, n_genes: int) -> torch.Tensor:
+    out = torch.empty(T.nnz, dtype=torch.float32, device=w.device)
+    check(lib().b2_sage_edge_values_f32(_p(T.rowptr), _p(T.colidx), _p(w), _p(alpha), T.shape[0], n_genes, _p(out), _stream()),
+          "b2_sage_edge_values_f32")
+    return out
+
+
+def softmax_ce_sum(logits: torch.Tensor, labels: torch.Tensor, dlogits: Optional[torch.Tensor] = None,
+                   loss_out: Optional[torch.Tensor] = None, need_grad: bool = True):
+    """CrossEntropyLoss(reduction='sum'): accumulates into loss_out[0]; returns (loss_out, dlogits)."""
+    _chk(logits, torch.float32, "logits", 2)
+    _chk(labels, torch.int64, "labels", 1)
+    n, c = logits.shape
+    if need_grad and dlogits is None:
+        dlogits = torch.empty_like(logits)
+    if loss_out is None:
+        loss_out = torch.zeros(1, dtype=torch.float32, device=logits.device)
+    check(lib().b2_softmax_ce_sum_f32(_p(logits), _rowmajor(logits, "logits"), _p(labels), n, c, _p(dlogits) if need_grad else None,
+                                      _rowmajor(dlogits, "dlogits") if need_grad else 0, _p(loss_out), _stream()),
+          "b2_softmax_ce_sum_f32")
+    return loss_out, dlogits

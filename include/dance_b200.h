@@ -263,6 +263,30 @@ int b2_gat_combine_bwd_f32(const float* dout, int64_t lddo, const float* out, in
                            int32_t n, int32_t nheads, int32_t F, int concat, int act,
                            float* dpre, int64_t ldp, float* dact, int64_t ldact, void* stream);
 
+/* ------------------------------------------------------------------------
+ * K10 CellFeatureGraph (transforms/graph/cell_feature_graph.py:34-79)
+ *   dense X [n_cells, n_genes] → COO edge list in the reference's order
+ *   [cell→gene ×nnz ; gene→cell ×nnz ; self ×(G+N)] (gene nodes first: ids 0..G-1, cell c = G+c),
+ *   int64 src/dst, fp32 w, with the per-destination renormalisation w ← indeg·w/Σ_in w (:62-68)
+ *   and unit self loops (:69).  `count` (synchronises) returns nnz; `fill` writes 2·nnz+G+N edges
+ *   and must be given the same workspace `count` filled.
+ * ---------------------------------------------------------------------- */
+size_t b2_cellgene_graph_workspace_bytes(int32_t n_cells, int32_t n_genes);
+int b2_cellgene_graph_count(const float* X, int64_t ldx, int32_t n_cells, int32_t n_genes,
+                            int64_t* nnz_out_host, void* workspace, size_t workspace_bytes, void* stream);
+int b2_cellgene_graph_fill(const float* X, int64_t ldx, int32_t n_cells, int32_t n_genes,
+                           int normalize_edges, int64_t nnz, int64_t* src, int64_t* dst, float* w,
+                           void* workspace, size_t workspace_bytes, void* stream);
+/* AdaptiveSAGE.message_func edge scalars (models/nn/gnn.py:62-82) on a destination-indexed CSR
+ * (node ids < n_genes are genes): out[p] = w[p] · alpha[idx(p)].  The mean aggregate (gnn.py:90) is
+ * b2_spmm_csr_f32(vals = out, reduce = 1). */
+int b2_sage_edge_values_f32(const int32_t* rowptr, const int32_t* colidx, const float* w, const float* alpha,
+                            int32_t n_nodes, int32_t n_genes, float* out, void* stream);
+/* nn.CrossEntropyLoss(reduction="sum") (scdeepsort.py:185): loss_out[0] += Σ_rows CE ; dlogits = softmax - onehot
+ * (dlogits may be NULL for evaluation). */
+int b2_softmax_ce_sum_f32(const float* logits, int64_t ld, const int64_t* labels, int32_t n, int32_t c,
+                          float* dlogits, int64_t ldd, float* loss_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

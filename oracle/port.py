@@ -230,6 +230,79 @@ def feature_ae_epoch(model: FeatureAE, optimizer, X: torch.Tensor, batch_size: i
     return total, torch.cat(zs, 0), torch.cat(rs, 0)
 
 
+# --------------------------------------------------------------------------- scDeepSort path (DGL-backed in the reference)
+# Parity status of this block: UNPINNED — the reference routes these through DGL 1.1.3 (absent here), so
+# they are restated from the reference text (cell_feature_graph.py:34-79, gnn.py:62-96, scdeepsort.py:142-250) and the
+# DGL semantics of SURVEY App. A; no reference execution or golden vector exists for them.
+def cell_feature_graph(feat: np.ndarray, normalize_edges: bool = True):
+    """CellFeatureGraph.__call__ edge list (cell_feature_graph.py:38-69): (src, dst, w[E,1]) with gene nodes first."""
+    feat = np.asarray(feat, dtype=np.float32)
+    n, g = feat.shape
+    row, col = np.nonzero(feat)
+    edata = feat[row, col].ravel()[:, None]
+    row = row + g
+    col, row = np.hstack((col, row)), np.hstack((row, col))
+    w = torch.from_numpy(np.vstack((edata, edata)).astype(np.float32))
+    src, dst = torch.from_numpy(row.astype(np.int64)), torch.from_numpy(col.astype(np.int64))
+    if normalize_edges:
+        in_deg = torch.bincount(dst, minlength=n + g)
+        order = torch.argsort(dst, stable=True)
+        bounds = torch.zeros(n + g + 1, dtype=torch.int64)
+        bounds[1:] = torch.cumsum(in_deg, 0)
+        for i in range(n + g):                      # the reference's per-node loop (:64-68), in fp32 like torch
+            eidx = order[bounds[i]:bounds[i + 1]]
+            if eidx.numel() > 0:
+                ew = w[eidx]
+                w[eidx] = in_deg[i] * ew / ew.sum()
+    nodes = torch.arange(n + g, dtype=torch.int64)
+    return torch.cat([src, nodes]), torch.cat([dst, nodes]), torch.cat([w, torch.ones(n + g, 1)])
+
+
+def adaptive_sage_neighbour_mean(src, dst, w, h, alpha, n_genes: int):
+    """update_all(message_func, fn.mean) of AdaptiveSAGE (gnn.py:62-90) on the full graph: the value the reference
+    stores in "neigh" (and never uses)."""
+    src_gene, dst_gene = src < n_genes, dst < n_genes
+    idx = torch.full_like(src, n_genes + 1)
+    idx = torch.where(src_gene & ~dst_gene, src, idx)
+    idx = torch.where(dst_gene & ~src_gene, dst, idx)
+    idx = torch.where(dst_gene & src_gene, torch.full_like(src, n_genes), idx)
+    m = h[src] * alpha[idx] * w
+    out = torch.zeros_like(h).index_add_(0, dst, m)
+    deg = torch.bincount(dst, minlength=h.shape[0]).clamp(min=1).unsqueeze(1)
+    return out / deg
+
+
+class ScDeepSortNet(torch.nn.Module):
+    """GNN (scdeepsort.py:26-88) with one AdaptiveSAGE layer as it actually computes (gnn.py:84-96): the output
+    depends on the destination features only."""
+
+    def __init__(self, dim_in, dim_hid, n_labels, gene_num):
+        super().__init__()
+        self.alpha = torch.nn.Parameter(torch.ones(gene_num + 2, 1))
+        self.sage_linear = torch.nn.Linear(dim_in, dim_hid)
+        torch.nn.init.xavier_uniform_(self.sage_linear.weight, gain=torch.nn.init.calculate_gain("relu"))
+        self.linear = torch.nn.Linear(dim_hid, n_labels)
+        torch.nn.init.xavier_uniform_(self.linear.weight, gain=torch.nn.init.calculate_gain("relu"))
+
+    def forward(self, h_dst):
+        return self.linear(torch.relu(self.sage_linear(h_dst)))
+
+
+def scdeepsort_epoch(net, optimizer, feats, labels, batch_index_lists):
+    """cal_loss (scdeepsort.py:213-250) for explicit batches: CrossEntropyLoss(reduction='sum'), Adam."""
+    loss_fn = torch.nn.CrossEntropyLoss(reduction="sum")
+    total_loss = total_size = 0.0
+    for idx in batch_index_lists:
+        idx = torch.as_tensor(idx, dtype=torch.int64)
+        loss = loss_fn(net(feats[idx]), labels[idx])
+        optimizer.zero_grad()
+        loss.backward()
+        optimizer.step()
+        total_size += idx.numel()
+        total_loss += loss.item() * idx.numel()
+    return total_loss / total_size
+
+
 # --------------------------------------------------------------------------- preprocessing
 def normalize_total(X: np.ndarray, target_sum: Optional[float] = None, exclude_highly_expressed: bool = False,
                     max_fraction: float = 0.05) -> np.ndarray:

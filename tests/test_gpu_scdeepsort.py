@@ -1,0 +1,120 @@
+"""scDeepSort path (BASELINE config 0): CellFeatureGraph construction, AdaptiveSAGE aggregate, and the
+ScDeepSort training loop against the oracle restatement (DGL-backed in the reference → restated)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _expr(n, g, seed):
+    from oracle import port
+    return port.synthetic_expression(n, g, density=0.15, seed=seed)
+
+
+def test_cellgene_graph_matches_oracle(cuda):
+    from dance_b200 import ops
+    from oracle import port
+    X = _expr(137, 61, 3)
+    X[5] = 0            # an empty cell: no in-edges to renormalise
+    X[:, 7] = 0         # an unexpressed gene
+    src_r, dst_r, w_r = port.cell_feature_graph(X, normalize_edges=True)
+    src, dst, w, nnz = ops.cellgene_graph(torch.from_numpy(X).to(cuda), True)
+    assert nnz == int((X != 0).sum())
+    assert torch.equal(src.cpu(), src_r) and torch.equal(dst.cpu(), dst_r)             # edge list and order: bit-exact
+    assert np.allclose(w.cpu().numpy(), w_r.numpy(), rtol=2e-6, atol=0)                 # fp32 renormalised weights
+    _, _, w_raw, _ = ops.cellgene_graph(torch.from_numpy(X).to(cuda), False)
+    _, _, w_raw_r = port.cell_feature_graph(X, normalize_edges=False)
+    assert torch.equal(w_raw.cpu(), w_raw_r)
+
+
+def test_cellfeaturegraph_transform_and_subgraph(cuda):
+    from dance_b200.data import AnnDataLite, Data
+    from dance_b200.transforms.graph import CellFeatureGraph
+    X = _expr(50, 20, 1)
+    rng = np.random.default_rng(0)
+    ad = AnnDataLite(X, obsm={"pca": rng.normal(size=(50, 8)).astype(np.float32)}, varm={"pca": rng.normal(size=(20, 8)).astype(np.float32)})
+    data = Data(ad, train_size=40)
+    CellFeatureGraph(cell_feature_channel="pca")(data)
+    g = data.data.uns["CellFeatureGraph"]
+    assert g.number_of_nodes() == 70 and g.ndata["features"].shape == (70, 8)
+    assert (g.ndata["cell_id"][:20] == torch.arange(20)).all() and (g.ndata["cell_id"][20:] == -1).all()
+    nnz = int((X != 0).sum())
+    assert g.num_edges() == 2 * nnz + 70
+    # node-induced subgraph of genes ∪ train cells, as examples/…/scdeepsort.py:60-66 does
+    sub = g.subgraph(torch.cat([torch.arange(20), torch.tensor(data.train_idx) + 20]))
+    assert sub.number_of_nodes() == 60
+    assert sub.num_edges() == 2 * int((X[:40] != 0).sum()) + 60
+    import pickle
+    g2 = pickle.loads(pickle.dumps(g))
+    assert torch.equal(g2.src, g.src) and torch.equal(g2.edata["weight"], g.edata["weight"])
+
+
+def test_adaptive_sage_neighbour_mean(cuda):
+    from dance_b200 import ops
+    from dance_b200.graph import GraphLite
+    from dance_b200.modules.scdeepsort import ScDeepSort
+    from oracle import port
+    n, g, F = 90, 40, 16
+    X = _expr(n, g, 5)
+    src, dst, w = port.cell_feature_graph(X)
+    h = torch.randn(n + g, F)
+    alpha = torch.rand(g + 2, 1) + 0.5
+    ref = port.adaptive_sage_neighbour_mean(src, dst, w, h, alpha, g)
+    gr = GraphLite(src, dst, n + g)
+    gr.edata["weight"] = w
+    gr.ndata["features"] = h
+    gr.ndata["cell_id"] = torch.cat([torch.arange(g, dtype=torch.int32), -torch.ones(n, dtype=torch.int32)])
+    m = ScDeepSort(F, 8, 1, device="cuda")
+    m._build(g, 3)
+    m.params.p["alpha"].copy_(alpha)
+    out = m.neighbour_mean(gr)
+    assert rel_err(out.cpu().numpy(), ref.numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_scdeepsort_training_matches_oracle(cuda, precision):
+    """Three epochs of explicit mini-batches: loss curve, logits and weights ≤1e-4 rel vs the torch-CPU restatement."""
+    from dance_b200.graph import GraphLite
+    from dance_b200.modules.scdeepsort import ScDeepSort
+    from oracle import port
+    n, g, F, C = 600, 50, 400, 7
+    rng = np.random.default_rng(1)
+    feats = torch.from_numpy(rng.normal(size=(n + g, F)).astype(np.float32))
+    labels = torch.from_numpy(rng.integers(0, C, size=n))
+    X = _expr(n, g, 2)
+    src, dst, w = port.cell_feature_graph(X)
+    gr = GraphLite(src, dst, n + g)
+    gr.edata["weight"] = w
+    gr.ndata["features"] = feats
+    gr.ndata["cell_id"] = torch.cat([torch.arange(g, dtype=torch.int32), -torch.ones(n, dtype=torch.int32)])
+    cells = np.arange(g, g + n)
+    batches = [[rng.permutation(cells)[i:i + 100] for i in range(0, n, 100)] for _ in range(3)]
+
+    model = ScDeepSort(F, 200, 1, device="cuda", batch_size=100, precision=precision, seed=0)
+    model._build(g, C)
+    init = model.state_dict()
+    net = port.ScDeepSortNet(F, 200, C, g)
+    with torch.no_grad():
+        net.sage_linear.weight.copy_(init["layers.0.layers.1.weight"].cpu()); net.sage_linear.bias.copy_(init["layers.0.layers.1.bias"].cpu())
+        net.linear.weight.copy_(init["linear.weight"].cpu()); net.linear.bias.copy_(init["linear.bias"].cpu())
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-4)
+    full_labels = torch.cat([-torch.ones(g, dtype=torch.long), labels])
+    ref_losses = [port.scdeepsort_epoch(net, opt, feats, full_labels, b) for b in batches]
+
+    model._feat, model._lab = feats.to(cuda), full_labels.to(cuda)
+    losses = [model.cal_loss(b, 1e-3, 1e-4) for b in batches]
+    assert np.allclose(losses, ref_losses, rtol=1e-4)
+    sd = model.state_dict()
+    assert rel_err(sd["layers.0.layers.1.weight"].cpu().numpy(), net.sage_linear.weight.detach().numpy()) < 1e-4
+    assert rel_err(sd["linear.weight"].cpu().numpy(), net.linear.weight.detach().numpy()) < 1e-4
+    assert torch.equal(sd["alpha"].cpu(), torch.ones(g + 2, 1))                       # alpha never moves (no gradient in the reference)
+    with torch.no_grad():
+        ref_prob = torch.softmax(net(feats[g:]), -1).numpy()
+    assert rel_err(model.predict_proba(gr), ref_prob) < 1e-4
+    # full fit() API runs and improves on the training set
+    model2 = ScDeepSort(F, 200, 1, device="cuda", batch_size=100, precision=precision, seed=0)
+    model2.fit(gr, labels, epochs=3, lr=1e-3, weight_decay=0, val_ratio=0.2)
+    assert model2.predict(gr).shape == (n, ) and model2.history[-1][0] < model2.history[0][0]
