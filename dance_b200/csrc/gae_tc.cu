@@ -105,8 +105,8 @@ gae_allpairs_tc_kernel(const __grid_constant__ Params p) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(stage_free + 8 * s, 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(s_full + 8 * b, 1);
-      mbar_init(s_empty + 8 * b, EW_THREADS);
-      mbar_init(g_full + 8 * b, EW_THREADS);
+      mbar_init(s_empty + 8 * b, EW_WARPS);   // one arrival per elementwise warp (512 per-thread arrivals on one
+      mbar_init(g_full + 8 * b, EW_WARPS);    // mbarrier cost ~2000 cycles per tile — measured)
       mbar_init(g_empty + 8 * b, 1);
     }
     mbar_init(d_full, 1);
@@ -214,7 +214,8 @@ gae_allpairs_tc_kernel(const __grid_constant__ Params p) {
       uint32_t v[EW_COLS];
       tmem_ld_32x32b_x16(tmem + lane_off + TM_S + (uint32_t)(b * BJ + part * EW_COLS), v);
       tc_fence_before();
-      mbar_arrive(s_empty + 8 * b);       // S[b] has been copied to registers
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty + 8 * b);       // S[b] has been copied to registers
       const int col0 = j_begin + t * BJ + part * EW_COLS;
       // staged so that the 16 independent SFU chains are issued back to back (ILP instead of one long dependent chain)
       float e[EW_COLS], sg[EW_COLS];
@@ -244,7 +245,8 @@ gae_allpairs_tc_kernel(const __grid_constant__ Params p) {
       tmem_st_32x32b_x16(tmem + lane_off + TM_GLO + (uint32_t)(b * BJ + part * EW_COLS), lo);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(g_full + 8 * b);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(g_full + 8 * b);
     }
     double loss = live ? (double)(relu_sum + LN2 * lg_sum) : 0.0;
     loss = warp_sum(loss);

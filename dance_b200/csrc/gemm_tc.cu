@@ -110,12 +110,12 @@ gemm_tc_kernel(const __grid_constant__ Params p) {
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar + 8 * s, 1);
-      mbar_init(split_bar + 8 * s, 128);
+      mbar_init(split_bar + 8 * s, 4);     // one arrival per splitter warp
       mbar_init(empty_bar + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar + 8 * a, 1);
-      mbar_init(tempty_bar + 8 * a, 128);
+      mbar_init(tempty_bar + 8 * a, 4);    // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -226,7 +226,8 @@ gemm_tc_kernel(const __grid_constant__ Params p) {
           split_tile(st + L.a_hi, st + L.a_lo, A_TILE_BYTES, tid);
           split_tile(st + L.b_hi, st + L.b_lo, L.b_bytes, tid);
           fence_proxy_async();                   // generic-proxy writes → visible to the tensor core (async proxy)
-          mbar_arrive(split_bar + 8 * stage);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(split_bar + 8 * stage);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -298,7 +299,8 @@ gemm_tc_kernel(const __grid_constant__ Params p) {
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar + 8 * acc);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }

@@ -508,3 +508,56 @@ def softmax_ce_sum(logits: torch.Tensor, labels: torch.Tensor, dlogits: Optional
                                       _rowmajor(dlogits, "dlogits") if need_grad else 0, _p(loss_out), _stream()),
           "b2_softmax_ce_sum_f32")
     return loss_out, dlogits
+
+
+# ----------------------------------------------------------------------------- PCA
+def sym_eig(Cm: torch.Tensor, max_sweeps: int = 20, tol: float = 2e-6):
+    """Eigen-decomposition of a symmetric matrix (destroyed) by parallel one-sided Jacobi.
+    Returns (evals [g] descending, evecs [g,g] rows = eigenvectors in the same order, sweeps)."""
+    _chk(Cm, torch.float32, "C", 2)
+    g = Cm.shape[0]
+    if Cm.shape[1] != g or not Cm.is_contiguous():
+        raise B2Error("sym_eig: need a contiguous square matrix")
+    V = torch.empty_like(Cm)
+    ev = torch.empty(g, dtype=torch.float32, device=Cm.device)
+    sweeps = C.c_int32(0)
+    ws = _workspace(64, Cm.device)
+    check(lib().b2_sym_eig_jacobi_f32(_p(Cm), _p(V), g, max_sweeps, tol, _p(ev), C.byref(sweeps), _p(ws), ws.numel(), _stream()),
+          "b2_sym_eig_jacobi_f32")
+    order = torch.argsort(ev, descending=True)
+    return ev[order], V[order], sweeps.value
+
+
+def pca(X: torch.Tensor, n_components: int, precision: Optional[str] = None):
+    """PCA of X [n_samples, n_features] like sklearn.decomposition.PCA(n_components).fit_transform (centred, no whitening).
+
+    Returns dict(scores [n,k] = U·S, components [k,f], explained_variance [k], mean [f]).  Uses the Gram matrix when
+    n_samples <= n_features, the covariance matrix otherwise; signs follow sklearn's u-based svd_flip.
+    """
+    _chk(X, torch.float32, "X", 2)
+    n, f = X.shape
+    k = int(n_components)
+    mean = colsum(X) / float(n)
+    if n <= f:
+        # Gram side: K = Xc Xcᵀ with Xc = X - 1·meanᵀ  → K = X Xᵀ - s 1ᵀ - 1 sᵀ + (m·m) 1 1ᵀ, s = X·mean
+        Xc = X - mean                                        # n ≤ f: the centred copy is the small side's operand
+        K = gemm(Xc, Xc, transB=True, precision=precision)
+        ev, evec, _ = sym_eig(K)
+        ev = ev[:k].clamp_min(0)
+        U = evec[:k]                                          # rows = left singular vectors
+        S = ev.sqrt()
+        scores = (U * S[:, None]).t().contiguous()            # [n, k] = U·S
+        comps = gemm(U, Xc, precision=precision) / S.clamp_min(1e-30)[:, None]   # Vᵀ = Σ^-1 Uᵀ Xc
+    else:
+        Cm = gemm(X, X, transA=True, precision=precision)     # XᵀX  [f,f]
+        check(lib().b2_cov_rank1_sub_f32(_p(Cm), _p(mean), f, float(n), _stream()), "b2_cov_rank1_sub_f32")
+        ev, evec, _ = sym_eig(Cm)
+        ev = ev[:k].clamp_min(0)
+        comps = evec[:k].contiguous()                         # [k, f]
+        bias = -(comps @ mean)
+        scores = gemm(X, comps, transB=True, bias=bias.contiguous(), precision=precision)   # (X - mean)·Vᵀ
+    # sklearn svd_flip (u-based): make the largest-|.| entry of every score column positive
+    idx = scores.abs().argmax(0)
+    sign = torch.sign(scores[idx, torch.arange(k, device=X.device)])
+    sign[sign == 0] = 1
+    return {"scores": scores * sign, "components": comps * sign[:, None], "explained_variance": ev / max(n - 1, 1), "mean": mean}

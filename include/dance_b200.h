@@ -287,6 +287,21 @@ int b2_sage_edge_values_f32(const int32_t* rowptr, const int32_t* colidx, const 
 int b2_softmax_ce_sum_f32(const float* logits, int64_t ld, const int64_t* labels, int32_t n, int32_t c,
                           float* dlogits, int64_t ldd, float* loss_out, void* stream);
 
+/* ------------------------------------------------------------------------
+ * K8  PCA building blocks (WeightedFeaturePCA / CellPCA, transforms/cell_feature.py:49-75,168-194;
+ *     replaces sklearn.decomposition.PCA).  PCA = eigen-decomposition of the small Gram / covariance matrix
+ *     (built with b2_gemm_f32) by a parallel one-sided Jacobi iteration.
+ *   b2_sym_eig_jacobi_f32: W [g,g] symmetric (OVERWRITTEN), V [g,g] out: row i of V = eigenvector i,
+ *     evals[i] = eigenvalue i (unsorted).  Stops when every |<w_p,w_q>|/(|w_p||w_q|) <= tol or after
+ *     max_sweeps; synchronises the stream once per sweep.  workspace: 64 bytes.
+ *   b2_cov_rank1_sub_f32: C[i,j] -= n·mean[i]·mean[j]  (XᵀX → centred second moment)
+ *   b2_row_center_f32   : out[i,:] = X[i,:] - mean(X[i,:])
+ * ---------------------------------------------------------------------- */
+int b2_sym_eig_jacobi_f32(float* W, float* V, int32_t g, int32_t max_sweeps, float tol, float* evals,
+                          int32_t* sweeps_done_host, void* workspace, size_t workspace_bytes, void* stream);
+int b2_cov_rank1_sub_f32(float* C, const float* mean, int32_t g, float n, void* stream);
+int b2_row_center_f32(const float* X, int64_t ldx, int32_t n, int32_t g, float* out, int64_t ldo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
