@@ -20,7 +20,7 @@ _SIGNATURES = {
     "b2_version": (C.c_int, []),
     "b2_launch_count": (c_i64, []),
     "b2_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
-    "b2_spmm_csr_f32": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32, C.c_int, C.c_int, c_vp]),
+    "b2_spmm_csr_f32": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32, C.c_int, C.c_int, c_vp, c_vp]),
     "b2_csr_transpose_workspace_bytes": (c_sz, [c_i32, c_i32, c_i64]),
     "b2_csr_transpose": (C.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "b2_gemm_workspace_bytes": (c_sz, [C.c_int] * 6),
@@ -58,6 +58,11 @@ _SIGNATURES = {
     "b2_sym_eig_jacobi_f32": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_f32, c_vp, C.POINTER(c_i32), c_vp, c_sz, c_vp]),
     "b2_cov_rank1_sub_f32": (C.c_int, [c_vp, c_vp, c_i32, c_f32, c_vp]),
     "b2_row_center_f32": (C.c_int, [c_vp, c_i64, c_i32, c_i32, c_vp, c_i64, c_vp]),
+    "b2_dec_q_f32": (C.c_int, [c_vp, c_i64, c_vp, c_i32, c_i32, c_i32, c_f32, c_vp, c_i64, c_vp]),
+    "b2_dec_target_f32": (C.c_int, [c_vp, c_i64, c_vp, c_i32, c_i32, c_vp, c_i64, c_vp]),
+    "b2_dec_kl_grad_f32": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_f32, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "b2_sgd_momentum_step_f32": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_i32, c_vp]),
+    "b2_exp_adj_f32": (C.c_int, [c_vp, c_vp, c_i64, c_f32, c_vp, c_vp]),
     "b2_normalize_total_workspace_bytes": (c_sz, [c_i32, c_i32]),
     "b2_normalize_total_log1p_f32": (C.c_int, [c_vp, c_i64, c_i32, c_i32, c_f32, c_f32, C.c_int, C.c_int, c_f32, c_vp,
                                                c_sz, c_vp]),

@@ -68,15 +68,37 @@ __global__ void eye_kernel(float* V, int g) {
     V[t] = (t / g == t % g) ? 1.f : 0.f;
 }
 
-// eigenvalue = signed row norm: λ_i = <w_i, v_i>  (w_i = λ_i v_i at convergence)
+// At convergence w_i = λ_i v_i with the rows of W orthogonal to working precision (that is the stopping criterion),
+// whereas the accumulated V drifts by ~1e-7 per rotation.  So: |λ_i| = ||w_i|| (sign from <w_i, v_i>) and, for every
+// eigenvalue that is not negligibly small, the eigenvector is taken as w_i / ||w_i|| (written back into V).
 __global__ void __launch_bounds__(256)
-jacobi_evals_kernel(const float* __restrict__ W, const float* __restrict__ V, int g, float* __restrict__ evals) {
+jacobi_finish_kernel(const float* __restrict__ W, float* __restrict__ V, int g, float* __restrict__ evals,
+                     const float* __restrict__ max_norm) {
   __shared__ float red[8];
   const int i = blockIdx.x;
-  float s = 0.f;
-  for (int j = threadIdx.x; j < g; j += 256) s = fmaf(W[(size_t)i * g + j], V[(size_t)i * g + j], s);
+  float s = 0.f, nn = 0.f;
+  for (int j = threadIdx.x; j < g; j += 256) {
+    const float w = W[(size_t)i * g + j];
+    s = fmaf(w, V[(size_t)i * g + j], s);
+    nn = fmaf(w, w, nn);
+  }
   s = block_sum_256(s, red);
-  if (threadIdx.x == 0) evals[i] = s;
+  nn = sqrtf(block_sum_256(nn, red));
+  if (threadIdx.x == 0) evals[i] = s >= 0.f ? nn : -nn;
+  if (nn > 1e-5f * max_norm[0]) {
+    const float inv = (s >= 0.f ? 1.f : -1.f) / nn;
+    for (int j = threadIdx.x; j < g; j += 256) V[(size_t)i * g + j] = W[(size_t)i * g + j] * inv;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+row_norm_max_kernel(const float* __restrict__ W, int g, float* __restrict__ max_norm) {
+  __shared__ float red[8];
+  const int i = blockIdx.x;
+  float nn = 0.f;
+  for (int j = threadIdx.x; j < g; j += 256) { const float w = W[(size_t)i * g + j]; nn = fmaf(w, w, nn); }
+  nn = sqrtf(block_sum_256(nn, red));
+  if (threadIdx.x == 0) atomicMax(reinterpret_cast<int*>(max_norm), __float_as_int(nn));
 }
 
 // C[i,j] -= n * mean[i] * mean[j]      (covariance from the raw second moment: XᵀX − n·m mᵀ)
@@ -130,8 +152,12 @@ extern "C" int b2_sym_eig_jacobi_f32(float* W, float* V, int32_t g, int32_t max_
     if (!(h > tol)) { ++sweep; break; }
   }
   if (sweeps_done_host) *sweeps_done_host = sweep;
-  jacobi_evals_kernel<<<g, 256, 0, st>>>(W, V, g, evals);
-  B2_CHECK_LAUNCH("jacobi_evals_kernel");
+  float* max_norm = off_max + 4;
+  B2_CHECK_CUDA(cudaMemsetAsync(max_norm, 0, sizeof(float), st));
+  row_norm_max_kernel<<<g, 256, 0, st>>>(W, g, max_norm);
+  B2_CHECK_LAUNCH("row_norm_max_kernel");
+  jacobi_finish_kernel<<<g, 256, 0, st>>>(W, V, g, evals, max_norm);
+  B2_CHECK_LAUNCH("jacobi_finish_kernel");
   return B2_OK;
 }
 

@@ -20,7 +20,8 @@ template <int G, int VPL>
 __global__ void __launch_bounds__(256)
 spmm_csr_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                 const float* __restrict__ vals, const float4* __restrict__ X4, int64_t ldx4,
-                float4* __restrict__ Y4, int64_t ldy4, int32_t n_rows, int32_t F4, int reduce, int act) {
+                float4* __restrict__ Y4, int64_t ldy4, int32_t n_rows, int32_t F4, int reduce, int act,
+                const float4* __restrict__ bias4) {
   constexpr int RPW = 32 / G;  // rows per warp
   // gathers issued back-to-back before the FMAs consume them (register budget: TCH*VPL float4)
   constexpr int TCH = VPL >= 4 ? 2 : (VPL == 2 ? 4 : (G < 8 ? G : 8));
@@ -169,6 +170,7 @@ spmm_csr_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
           // DGL fn.mean divides the sum by the in-degree
           o.x = o.x * scale; o.y = o.y * scale; o.z = o.z * scale; o.w = o.w * scale;
         }
+        if (bias4) { const float4 bb = __ldg(bias4 + j); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
         o.x = apply_act(o.x, act); o.y = apply_act(o.y, act);
         o.z = apply_act(o.z, act); o.w = apply_act(o.w, act);
         stg_stream_f4(Y4 + row * ldy4 + j, o);
@@ -180,7 +182,7 @@ spmm_csr_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
 template <int G, int VPL>
 static int launch_spmm(const int32_t* rowptr, const int32_t* colidx, const float* vals, const float* X,
                        int64_t ldx, float* Y, int64_t ldy, int32_t n_rows, int32_t F, int reduce, int act,
-                       cudaStream_t st) {
+                       const float* bias, cudaStream_t st) {
   constexpr int RPW = 32 / G;
   const int threads = 256;
   const int64_t warps_needed = ceil_div<int64_t>(n_rows, RPW);
@@ -190,7 +192,7 @@ static int launch_spmm(const int32_t* rowptr, const int32_t* colidx, const float
   if (blocks < 1) blocks = 1;
   spmm_csr_kernel<G, VPL><<<(unsigned)blocks, threads, 0, st>>>(
       rowptr, colidx, vals, reinterpret_cast<const float4*>(X), ldx / 4, reinterpret_cast<float4*>(Y),
-      ldy / 4, n_rows, F / 4, reduce, act);
+      ldy / 4, n_rows, F / 4, reduce, act, reinterpret_cast<const float4*>(bias));
   B2_CHECK_LAUNCH("spmm_csr_kernel");
   return B2_OK;
 }
@@ -199,7 +201,7 @@ static int launch_spmm(const int32_t* rowptr, const int32_t* colidx, const float
 
 extern "C" int b2_spmm_csr_f32(const int32_t* rowptr, const int32_t* colidx, const float* vals,
                                const float* X, int64_t ldx, float* Y, int64_t ldy, int32_t n_rows,
-                               int32_t n_cols, int32_t F, int reduce, int act, void* stream) {
+                               int32_t n_cols, int32_t F, int reduce, int act, const float* bias, void* stream) {
   using namespace b2;
   B2_REQUIRE(rowptr && colidx && X && Y, "b2_spmm_csr_f32: null pointer");
   B2_REQUIRE(n_rows >= 0 && n_cols >= 0, "b2_spmm_csr_f32: negative shape");
@@ -210,10 +212,11 @@ extern "C" int b2_spmm_csr_f32(const int32_t* rowptr, const int32_t* colidx, con
   B2_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0,
              "b2_spmm_csr_f32: X/Y must be 16-byte aligned");
   B2_REQUIRE(reduce == 0 || reduce == 1, "b2_spmm_csr_f32: reduce must be 0 (sum) or 1 (mean)");
+  B2_REQUIRE(!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "b2_spmm_csr_f32: bias must be 16-byte aligned");
   if (n_rows == 0) return B2_OK;
   cudaStream_t st = as_stream(stream);
   const int F4 = F / 4;
-#define B2_SPMM_CASE(G, VPL) return launch_spmm<G, VPL>(rowptr, colidx, vals, X, ldx, Y, ldy, n_rows, F, reduce, act, st)
+#define B2_SPMM_CASE(G, VPL) return launch_spmm<G, VPL>(rowptr, colidx, vals, X, ldx, Y, ldy, n_rows, F, reduce, act, bias, st)
   if (F4 <= 2) B2_SPMM_CASE(2, 1);
   if (F4 <= 4) B2_SPMM_CASE(4, 1);
   if (F4 <= 8) B2_SPMM_CASE(8, 1);

@@ -171,7 +171,7 @@ class CSR:
 
 
 def spmm(A: CSR, X: torch.Tensor, reduce: str = "sum", act: Optional[str] = None,
-         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``Y = act(A @ X)`` (reduce='sum') or row-mean (reduce='mean')."""
     _chk(X, torch.float32, "X", 2)
     ldx = _rowmajor(X, "X")
@@ -184,7 +184,7 @@ def spmm(A: CSR, X: torch.Tensor, reduce: str = "sum", act: Optional[str] = None
     _chk(out, torch.float32, "out", 2)
     colidx_ptr = _p(A.colidx) if A.nnz else _p(A.rowptr)  # an empty matrix has no colidx storage; never dereferenced
     check(lib().b2_spmm_csr_f32(_p(A.rowptr), colidx_ptr, _p(A.vals) if A.nnz else None, _p(X), ldx, _p(out), _rowmajor(out, "out"),
-                                n_rows, n_cols, F, {"sum": 0, "mean": 1}[reduce], ACT[act], _stream()), "b2_spmm_csr_f32")
+                                n_rows, n_cols, F, {"sum": 0, "mean": 1}[reduce], ACT[act], _p(bias), _stream()), "b2_spmm_csr_f32")
     return out
 
 
@@ -561,3 +561,48 @@ def pca(X: torch.Tensor, n_components: int, precision: Optional[str] = None):
     sign = torch.sign(scores[idx, torch.arange(k, device=X.device)])
     sign[sign == 0] = 1
     return {"scores": scores * sign, "components": comps * sign[:, None], "explained_variance": ev / max(n - 1, 1), "mean": mean}
+
+
+# ----------------------------------------------------------------------------- SpaGCN (DEC head)
+def dec_q(z, mu, alpha: float = 0.2):
+    n, h = z.shape
+    K = mu.shape[0]
+    q = torch.empty((n, K), dtype=torch.float32, device=z.device)
+    check(lib().b2_dec_q_f32(_p(z), _rowmajor(z, "z"), _p(mu), n, K, h, alpha, _p(q), K, _stream()), "b2_dec_q_f32")
+    return q
+
+
+def dec_target(q):
+    n, K = q.shape
+    p = torch.empty_like(q)
+    cs = colsum(q)
+    check(lib().b2_dec_target_f32(_p(q), _rowmajor(q, "q"), _p(cs), n, K, _p(p), K, _stream()), "b2_dec_target_f32")
+    return p
+
+
+def dec_kl_grad(z, mu, p, alpha: float = 0.2, dz=None, dmu=None, loss=None, q_out=None):
+    n, h = z.shape
+    K = mu.shape[0]
+    dz = torch.empty((n, h), dtype=torch.float32, device=z.device) if dz is None else dz
+    dmu = torch.empty((K, h), dtype=torch.float32, device=z.device) if dmu is None else dmu
+    loss = torch.empty(1, dtype=torch.float32, device=z.device) if loss is None else loss
+    check(lib().b2_dec_kl_grad_f32(_p(z), _rowmajor(z, "z"), _p(mu), _p(p), _rowmajor(p, "p"), n, K, h, alpha, _p(q_out),
+                                   _rowmajor(q_out, "q_out") if q_out is not None else 0, _p(dz), _rowmajor(dz, "dz"), _p(dmu), _p(loss),
+                                   _stream()), "b2_dec_kl_grad_f32")
+    return loss, dz, dmu
+
+
+def sgd_momentum_step(param, grad, buf, step: int, lr: float, momentum: float = 0.9, weight_decay: float = 0.0):
+    check(lib().b2_sgd_momentum_step_f32(_p(param), _p(grad), _p(buf), param.numel(), lr, momentum, weight_decay, step, _stream()),
+          "b2_sgd_momentum_step_f32")
+
+
+def exp_adj(D: torch.Tensor, l: float, want_matrix: bool = True, want_sum: bool = False):
+    """exp(-D²/(2l²)) elementwise on a dense distance matrix and / or its total sum (fp64)."""
+    _chk(D, torch.float32, "D")
+    if not D.is_contiguous():
+        raise B2Error("exp_adj: D must be contiguous")
+    out = torch.empty_like(D) if want_matrix else None
+    acc = torch.zeros(1, dtype=torch.float64, device=D.device) if want_sum else None
+    check(lib().b2_exp_adj_f32(_p(D), _p(out), D.numel(), float(l), _p(acc), _stream()), "b2_exp_adj_f32")
+    return out, acc

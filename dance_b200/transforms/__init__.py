@@ -3,3 +3,5 @@ from .interface import AnnDataTransform  # noqa: F401
 from .misc import Compose, SetConfig  # noqa: F401
 from .normalize import Log1P, NormalizeTotal, NormalizeTotalLog1P  # noqa: F401
 from . import pp  # noqa: F401
+from .cell_feature import CellPCA, WeightedFeaturePCA  # noqa: F401
+from .graph import CellFeatureGraph, PCACellFeatureGraph  # noqa: F401

@@ -14,6 +14,7 @@ import torch
 from .. import ops
 from ..graph import GraphLite
 from .base import BaseTransform
+from .cell_feature import WeightedFeaturePCA
 
 
 class CellFeatureGraph(BaseTransform):
@@ -43,4 +44,23 @@ class CellFeatureGraph(BaseTransform):
         cell_feature = data.get_feature(return_type="torch", channel=self.cell_feature_channel, mod=self.mod, channel_type="obsm")
         g.ndata["features"] = torch.vstack((gene_feature, cell_feature))
         data.data.uns[self.out] = g
+        return data
+
+
+class PCACellFeatureGraph(BaseTransform):
+    """WeightedFeaturePCA followed by CellFeatureGraph (cell_feature_graph.py:83-112)."""
+
+    _DISPLAY_ATTRS = ("n_components", "split_name")
+
+    def __init__(self, n_components: int = 400, split_name: Optional[str] = None, *, normalize_edges: bool = True,
+                 feat_norm_mode: Optional[str] = None, feat_norm_axis: int = 0, mod: Optional[str] = None, log_level="WARNING"):
+        super().__init__(log_level=log_level)
+        self.n_components, self.split_name, self.normalize_edges = n_components, split_name, normalize_edges
+        self.feat_norm_mode, self.feat_norm_axis, self.mod = feat_norm_mode, feat_norm_axis, mod
+
+    def __call__(self, data):
+        WeightedFeaturePCA(self.n_components, self.split_name, feat_norm_mode=self.feat_norm_mode, feat_norm_axis=self.feat_norm_axis,
+                           log_level=self.log_level)(data)
+        CellFeatureGraph(cell_feature_channel="WeightedFeaturePCA", mod=self.mod, normalize_edges=self.normalize_edges,
+                         log_level=self.log_level)(data)
         return data

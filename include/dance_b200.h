@@ -53,7 +53,7 @@ int64_t b2_launch_count(void);
 int b2_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* ------------------------------------------------------------------------
- * K1/K2  CSR SpMM  Y[n_rows,F] = act( rowscale ⊙ (A · X) )  (+ mean reduce)
+ * K1/K2  CSR SpMM  Y[n_rows,F] = act( reduce(A · X) + bias )
  * replaces: torch.spmm(adj, support)      scgnn2.py:500, spagcn.py:359,
  *           scdsc.py:498; DGL update_all(u_mul_e, sum|mean)  gnn.py:90,
  *           graphsc.py:463-465.
@@ -65,7 +65,7 @@ int b2_device_info(int* sm_count, int* cc_major, int* cc_minor);
 int b2_spmm_csr_f32(const int32_t* rowptr, const int32_t* colidx, const float* vals,
                     const float* X, int64_t ldx, float* Y, int64_t ldy,
                     int32_t n_rows, int32_t n_cols, int32_t F,
-                    int reduce, int act, void* stream);
+                    int reduce, int act, const float* bias /* length F or NULL, added before act */, void* stream);
 
 /* CSR transpose (deterministic: entries of each output row ordered by source
  * row).  Used to obtain Aᵀ for the SpMM backward of non-symmetric graphs
@@ -301,6 +301,25 @@ int b2_sym_eig_jacobi_f32(float* W, float* V, int32_t g, int32_t max_sweeps, flo
                           int32_t* sweeps_done_host, void* workspace, size_t workspace_bytes, void* stream);
 int b2_cov_rank1_sub_f32(float* C, const float* mean, int32_t g, float n, void* stream);
 int b2_row_center_f32(const float* X, int64_t ldx, int32_t n, int32_t g, float* out, int64_t ldo, void* stream);
+
+/* ------------------------------------------------------------------------
+ * SpaGCN deep-embedded-clustering head (modules/spatial/spatial_domain/spagcn.py:369-425, K <= 64 clusters)
+ *   b2_dec_q_f32       : q_ij = u_ij / Σ_j u_ij, u = ((1 + |z_i-mu_j|²/alpha) + 1e-8)^-(alpha+1) / 2       (:391-397)
+ *   b2_dec_target_f32  : p = (q² / colsum(q)) row-normalised                                             (:408-425)
+ *   b2_dec_kl_grad_f32 : loss = mean_i Σ_j p log(p/(q+1e-6)) (:399-406) and its gradients dz [n,h], dmu [K,h]
+ *                        (both overwritten); q_out optional (argmax → labels).
+ *   b2_sgd_momentum_step_f32 : torch.optim.SGD(momentum, weight_decay) as used at spagcn.py:463; step is 1-based.
+ *   b2_exp_adj_f32     : out = exp(-D²/(2 l²)) elementwise (spagcn.py:807-809) and/or its total sum in fp64
+ *                        (calculate_p / search_l, spagcn.py:249-251).
+ * ---------------------------------------------------------------------- */
+int b2_dec_q_f32(const float* z, int64_t ldz, const float* mu, int32_t n, int32_t K, int32_t h, float alpha,
+                 float* q, int64_t ldq, void* stream);
+int b2_dec_target_f32(const float* q, int64_t ldq, const float* colsum, int32_t n, int32_t K, float* p, int64_t ldp, void* stream);
+int b2_dec_kl_grad_f32(const float* z, int64_t ldz, const float* mu, const float* p, int64_t ldp, int32_t n, int32_t K, int32_t h,
+                       float alpha, float* q_out, int64_t ldq, float* dz, int64_t lddz, float* dmu, float* loss_out, void* stream);
+int b2_sgd_momentum_step_f32(float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
+                             float weight_decay, int32_t step, void* stream);
+int b2_exp_adj_f32(const float* D, float* out, int64_t n_elem, float l, double* sum_out_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -69,3 +69,26 @@ def scgnn2():
 def matrix():
     """The reference's ``dance/utils/matrix.py`` (numba pairwise distance, normalize)."""
     return _load("dance.utils.matrix", "dance/utils/matrix.py")
+
+
+def spagcn():
+    """The reference's ``dance/modules/spatial/spatial_domain/spagcn.py`` (SimpleGCDEC, GraphConvolution, search_l …).
+    Extra stubs per SURVEY App. C: scanpy, dance.modules.base, dance.transforms(.graph); the real dance.utils.matrix;
+    ``sklearn.utils.issparse`` was removed after sklearn 1.3 → shimmed with scipy's."""
+    if "dance_ref_spagcn" in sys.modules:
+        return sys.modules["dance_ref_spagcn"]
+    _install_stubs()
+    import scipy.sparse
+    import sklearn.utils
+    if not hasattr(sklearn.utils, "issparse"):
+        sklearn.utils.issparse = scipy.sparse.issparse
+    _stub("scanpy", pp=types.SimpleNamespace(), tl=types.SimpleNamespace(), AnnData=object)
+    _stub("dance.modules")
+    _stub("dance.modules.base", BaseClusteringMethod=object)
+    dummy = type("Dummy", (), {"__init__": lambda self, *a, **k: None})
+    _stub("dance.transforms", AnnDataTransform=dummy, CellPCA=dummy, Compose=dummy, FilterGenesMatch=dummy, SetConfig=dummy)
+    _stub("dance.transforms.graph", SpaGCNGraph=dummy, SpaGCNGraph2D=dummy)
+    _stub("dance.utils.matrix_placeholder")
+    sys.modules["dance.utils"].matrix = matrix()
+    sys.modules["dance.utils.matrix"] = matrix()
+    return _load("dance_ref_spagcn", "dance/modules/spatial/spatial_domain/spagcn.py")

@@ -38,7 +38,7 @@ def test_error_reporting_without_gpu():
     lib = _lib.lib()
     assert lib.b2_version() >= 100
     # argument validation happens before any CUDA call, so it can be exercised on the CPU box
-    rc = lib.b2_spmm_csr_f32(None, None, None, None, 0, None, 0, 1, 1, 4, 0, 0, None)
+    rc = lib.b2_spmm_csr_f32(None, None, None, None, 0, None, 0, 1, 1, 4, 0, 0, None, None)
     assert rc == -1
     assert b"null pointer" in lib.b2_last_error()
 

@@ -118,3 +118,34 @@ def test_scdeepsort_training_matches_oracle(cuda, precision):
     model2 = ScDeepSort(F, 200, 1, device="cuda", batch_size=100, precision=precision, seed=0)
     model2.fit(gr, labels, epochs=3, lr=1e-3, weight_decay=0, val_ratio=0.2)
     assert model2.predict(gr).shape == (n, ) and model2.history[-1][0] < model2.history[0][0]
+
+
+def test_scdeepsort_example_flow_end_to_end(cuda):
+    """The flow of examples/single_modality/cell_type_annotation/scdeepsort.py:40-75 on synthetic data (BASELINE
+    config 0 at reduced size): PCACellFeatureGraph + SetConfig pipeline → train/test subgraphs → fit → score."""
+    from dance_b200.data import AnnDataLite, Data
+    from dance_b200.modules.scdeepsort import ScDeepSort
+    from dance_b200.transforms import Compose, PCACellFeatureGraph, SetConfig
+    rng = np.random.default_rng(0)
+    n, g, C = 1500, 300, 5
+    types = rng.integers(0, C, size=n)
+    base = rng.lognormal(0, 1, size=(C, g))
+    X = rng.poisson(base[types] * rng.lognormal(0, 0.3, size=(n, 1))).astype(np.float32)
+    X = np.log1p(X / X.sum(1, keepdims=True).clip(1) * 1e4).astype(np.float32)
+    y = np.eye(C, dtype=np.float32)[types]
+    data = Data(AnnDataLite(X, obsm={"cell_type": y}), train_size=1200)
+    Compose(PCACellFeatureGraph(n_components=64, split_name="train"), SetConfig({"label_channel": "cell_type"}))(data)
+    graph = data.data.uns["CellFeatureGraph"]
+    y_all = data.get_y(return_type="torch")
+    num_genes = data.shape[1]
+    gene_ids = torch.arange(num_genes)
+    train_ids = torch.tensor(data.train_idx) + num_genes
+    test_ids = torch.tensor(data.test_idx) + num_genes
+    g_train = graph.subgraph(torch.concat((gene_ids, train_ids)))
+    g_test = graph.subgraph(torch.concat((gene_ids, test_ids)))
+    model = ScDeepSort(64, 32, 1, "synthetic", "tissue", batch_size=200, device="cuda", seed=0)
+    model.fit(g_train, y_all[data.train_idx].argmax(1), epochs=15, lr=1e-2, weight_decay=0, val_ratio=0.2)
+    acc = model.score(g_test, y_all[data.test_idx].numpy())
+    assert acc > 0.9, acc
+    pred, unsure = model.predict(g_test, return_unsure=True)
+    assert pred.shape == (300, ) and unsure.dtype == bool

@@ -16,6 +16,12 @@ def test_repr_and_hexdigest():
     assert len(c.hexdigest()) == 32 and c.hexdigest() != Compose(s, t).hexdigest()
     assert NormalizeTotal(target_sum=30, max_fraction=0.99).func_kwargs["exclude_highly_expressed"] is True
     assert Log1P().name == "Log1P"
+    # reference tests/transforms/test_basics.py:5-22
+    from dance_b200.transforms import CellPCA, PCACellFeatureGraph, WeightedFeaturePCA
+    assert repr(CellPCA(n_components=100)) == "CellPCA(n_components=100)"
+    assert repr(WeightedFeaturePCA(n_components=100, split_name="train")) == (
+        "WeightedFeaturePCA(n_components=100, split_name='train', feat_norm_mode=None, feat_norm_axis=0)")
+    assert repr(PCACellFeatureGraph(n_components=100, split_name="train")) == "PCACellFeatureGraph(n_components=100, split_name='train')"
     with pytest.raises(TypeError):
         Compose(t, "not a transform")
 
