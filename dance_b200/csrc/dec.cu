@@ -64,7 +64,8 @@ dec_target_kernel(const float* __restrict__ q, int64_t ldq, const float* __restr
 __global__ void __launch_bounds__(256)
 dec_kl_grad_kernel(const float* __restrict__ z, int64_t ldz, const float* __restrict__ mu, const float* __restrict__ p,
                    int64_t ldp, int32_t n, int32_t K, int32_t h, float alpha, float* __restrict__ q_out, int64_t ldq,
-                   float* __restrict__ dz, int64_t lddz, float* __restrict__ dmu, float* __restrict__ loss_out) {
+                   float* __restrict__ dz, int64_t lddz, float* __restrict__ dmu, float* __restrict__ loss_out,
+                   int32_t* __restrict__ labels_out) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -90,6 +91,18 @@ dec_kl_grad_kernel(const float* __restrict__ z, int64_t ldz, const float* __rest
       }
     }
     gq = warp_sum(gq);
+    if (labels_out) {   // torch.argmax(q, dim=1): first index of the maximum
+      float bv = qv[0]; int bj = lane;
+      if (lane + 32 < K && qv[1] > bv) { bv = qv[1]; bj = lane + 32; }
+      if (lane >= K) { bv = -1.f; bj = 0x7fffffff; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+        if (ov > bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
+      }
+      if (lane == 0) labels_out[i] = bj;
+    }
     // dL/d(d²_ij)
     float cij[2];
 #pragma unroll
@@ -137,21 +150,21 @@ sgd_momentum_kernel(float* __restrict__ p, const float* __restrict__ g, float* _
 
 // Σ_ij exp(-D_ij² / (2 l²)) over a dense distance matrix (SpaGCN.calculate_p / search_l, spagcn.py:249-251)
 __global__ void __launch_bounds__(256)
-exp_adj_sum_kernel(const float* __restrict__ D, int64_t total, float inv2l2, double* __restrict__ acc) {
+exp_adj_sum_kernel(const float* __restrict__ D, int64_t total, float two_l2, double* __restrict__ acc) {
   double local = 0.0;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const float d = D[t];
-    local += (double)expf(-d * d * inv2l2);
+    local += (double)expf(-(d * d) / two_l2);
   }
   local = warp_sum(local);
   if ((threadIdx.x & 31) == 0) atomicAdd(acc, local);
 }
 
 __global__ void __launch_bounds__(256)
-exp_adj_kernel(const float* __restrict__ D, float* __restrict__ out, int64_t total, float inv2l2) {
+exp_adj_kernel(const float* __restrict__ D, float* __restrict__ out, int64_t total, float two_l2) {
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const float d = D[t];
-    out[t] = expf(-d * d * inv2l2);   // np.exp(-1 * adj**2 / (2 * l**2)), spagcn.py:807-809
+    out[t] = expf(-(d * d) / two_l2);   // np.exp(-1 * adj**2 / (2 * l**2)), spagcn.py:807-809
   }
 }
 
@@ -187,12 +200,12 @@ extern "C" int b2_dec_target_f32(const float* q, int64_t ldq, const float* colsu
 
 extern "C" int b2_dec_kl_grad_f32(const float* z, int64_t ldz, const float* mu, const float* p, int64_t ldp, int32_t n,
                                   int32_t K, int32_t h, float alpha, float* q_out, int64_t ldq, float* dz, int64_t lddz,
-                                  float* dmu, float* loss_out, void* stream) {
+                                  float* dmu, float* loss_out, int32_t* labels_out, void* stream) {
   B2_REQUIRE(z && mu && p && dz && dmu && loss_out && n > 0 && K > 0 && K <= DEC_MAXK && h > 0, "b2_dec_kl_grad_f32: bad arguments");
   cudaStream_t st = as_stream(stream);
   B2_CHECK_CUDA(cudaMemsetAsync(dmu, 0, sizeof(float) * (size_t)K * h, st));
   B2_CHECK_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
-  dec_kl_grad_kernel<<<dec_grid(n), 256, 0, st>>>(z, ldz, mu, p, ldp, n, K, h, alpha, q_out, ldq, dz, lddz, dmu, loss_out);
+  dec_kl_grad_kernel<<<dec_grid(n), 256, 0, st>>>(z, ldz, mu, p, ldp, n, K, h, alpha, q_out, ldq, dz, lddz, dmu, loss_out, labels_out);
   B2_CHECK_LAUNCH("dec_kl_grad_kernel");
   return B2_OK;
 }
@@ -210,22 +223,22 @@ extern "C" int b2_sgd_momentum_step_f32(float* param, const float* grad, float* 
   return B2_OK;
 }
 
-extern "C" int b2_exp_adj_f32(const float* D, float* out, int64_t n_elem, float l, double* sum_out_dev, void* stream) {
-  B2_REQUIRE(D && n_elem >= 0 && l > 0.f && (out || sum_out_dev), "b2_exp_adj_f32: bad arguments");
+extern "C" int b2_exp_adj_f32(const float* D, float* out, int64_t n_elem, double l, double* sum_out_dev, void* stream) {
+  B2_REQUIRE(D && n_elem >= 0 && l > 0.0 && (out || sum_out_dev), "b2_exp_adj_f32: bad arguments");
   if (n_elem == 0) return B2_OK;
   cudaStream_t st = as_stream(stream);
-  const float inv2l2 = 1.f / (2.f * l * l);
+  const float two_l2 = (float)(2.0 * (l * l));   // numpy: fp32 array / python float → the scalar is rounded to fp32
   int64_t blocks = ceil_div<int64_t>(n_elem, 2048);
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   if (sum_out_dev) {
     B2_CHECK_CUDA(cudaMemsetAsync(sum_out_dev, 0, sizeof(double), st));
-    exp_adj_sum_kernel<<<(unsigned)blocks, 256, 0, st>>>(D, n_elem, inv2l2, sum_out_dev);
+    exp_adj_sum_kernel<<<(unsigned)blocks, 256, 0, st>>>(D, n_elem, two_l2, sum_out_dev);
     B2_CHECK_LAUNCH("exp_adj_sum_kernel");
   }
   if (out) {
-    exp_adj_kernel<<<(unsigned)blocks, 256, 0, st>>>(D, out, n_elem, inv2l2);
+    exp_adj_kernel<<<(unsigned)blocks, 256, 0, st>>>(D, out, n_elem, two_l2);
     B2_CHECK_LAUNCH("exp_adj_kernel");
   }
   return B2_OK;

@@ -32,6 +32,37 @@ class AnnDataLite:
         import copy
         return copy.deepcopy(self)
 
+    @property
+    def var_names(self):
+        """Gene identifiers: ``var["names"]`` (or the index of a DataFrame ``var``); defaults to "0".."g-1"."""
+        import pandas as pd
+        if hasattr(self.var, "index"):
+            return pd.Index(self.var.index.astype(str))
+        if isinstance(self.var, dict) and "names" in self.var:
+            return pd.Index(np.asarray(self.var["names"]).astype(str))
+        return pd.Index([str(i) for i in range(self.n_vars)])
+
+    def _inplace_subset_var(self, index):
+        """Keep the genes selected by a boolean mask, integer positions or names (AnnData._inplace_subset_var)."""
+        index = np.asarray(index)
+        if index.dtype == bool:
+            keep = np.flatnonzero(index)
+        elif index.dtype.kind in "iu":
+            keep = index
+        else:
+            keep = self.var_names.get_indexer(index.astype(str))
+            if (keep < 0).any():
+                raise KeyError("unknown gene names in _inplace_subset_var")
+        self.X = self.X[:, keep]
+        if hasattr(self.var, "iloc"):
+            self.var = self.var.iloc[keep]
+        elif isinstance(self.var, dict):
+            self.var = {k: (np.asarray(v)[keep] if np.ndim(v) >= 1 and len(v) == self.n_vars else v) for k, v in self.var.items()}
+        self.varm = {k: v[keep] for k, v in self.varm.items()}
+        self.varp = {k: v[keep][:, keep] for k, v in self.varp.items()}
+        self.layers = {k: v[:, keep] for k, v in self.layers.items()}
+        self.n_vars = len(keep)
+
 
 _CONFIG_KEYS = ("feature_mod", "feature_channel", "feature_channel_type", "label_mod", "label_channel", "label_channel_type")
 

@@ -511,7 +511,7 @@ def softmax_ce_sum(logits: torch.Tensor, labels: torch.Tensor, dlogits: Optional
 
 
 # ----------------------------------------------------------------------------- PCA
-def sym_eig(Cm: torch.Tensor, max_sweeps: int = 20, tol: float = 2e-6):
+def sym_eig(Cm: torch.Tensor, max_sweeps: int = 30, tol: float = 4e-6):
     """Eigen-decomposition of a symmetric matrix (destroyed) by parallel one-sided Jacobi.
     Returns (evals [g] descending, evecs [g,g] rows = eigenvectors in the same order, sweeps)."""
     _chk(Cm, torch.float32, "C", 2)
@@ -580,7 +580,7 @@ def dec_target(q):
     return p
 
 
-def dec_kl_grad(z, mu, p, alpha: float = 0.2, dz=None, dmu=None, loss=None, q_out=None):
+def dec_kl_grad(z, mu, p, alpha: float = 0.2, dz=None, dmu=None, loss=None, q_out=None, labels_out=None):
     n, h = z.shape
     K = mu.shape[0]
     dz = torch.empty((n, h), dtype=torch.float32, device=z.device) if dz is None else dz
@@ -588,7 +588,7 @@ def dec_kl_grad(z, mu, p, alpha: float = 0.2, dz=None, dmu=None, loss=None, q_ou
     loss = torch.empty(1, dtype=torch.float32, device=z.device) if loss is None else loss
     check(lib().b2_dec_kl_grad_f32(_p(z), _rowmajor(z, "z"), _p(mu), _p(p), _rowmajor(p, "p"), n, K, h, alpha, _p(q_out),
                                    _rowmajor(q_out, "q_out") if q_out is not None else 0, _p(dz), _rowmajor(dz, "dz"), _p(dmu), _p(loss),
-                                   _stream()), "b2_dec_kl_grad_f32")
+                                   _p(labels_out), _stream()), "b2_dec_kl_grad_f32")
     return loss, dz, dmu
 
 

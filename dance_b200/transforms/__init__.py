@@ -4,4 +4,5 @@ from .misc import Compose, SetConfig  # noqa: F401
 from .normalize import Log1P, NormalizeTotal, NormalizeTotalLog1P  # noqa: F401
 from . import pp  # noqa: F401
 from .cell_feature import CellPCA, WeightedFeaturePCA  # noqa: F401
-from .graph import CellFeatureGraph, PCACellFeatureGraph  # noqa: F401
+from .filter import FilterGenesMatch  # noqa: F401
+from .graph import CellFeatureGraph, PCACellFeatureGraph, SpaGCNGraph, SpaGCNGraph2D  # noqa: F401

@@ -2,7 +2,9 @@
 
 ``CellFeatureGraph`` keeps the reference's constructor, ``out`` channel (``uns["CellFeatureGraph"]``), node
 ordering (genes first), edge order, weights and node data names (reference
-dance/transforms/graph/cell_feature_graph.py:12-79, incl. the ``cell_id``/``feat_id`` naming quirk :56-59)."""
+dance/transforms/graph/cell_feature_graph.py:12-79, incl. the ``cell_id``/``feat_id`` naming quirk :56-59).
+``SpaGCNGraph`` / ``SpaGCNGraph2D`` (dance/transforms/graph/spatial_graph.py:13-76) produce the dense spot-to-spot
+euclidean distance matrices with the pairwise-distance kernel (``utils/matrix.py:164-180`` in the reference)."""
 from __future__ import annotations
 
 from typing import Optional
@@ -63,4 +65,58 @@ class PCACellFeatureGraph(BaseTransform):
                            log_level=self.log_level)(data)
         CellFeatureGraph(cell_feature_channel="WeightedFeaturePCA", mod=self.mod, normalize_edges=self.normalize_edges,
                          log_level=self.log_level)(data)
+        return data
+
+
+def _pairwise_distance_host(x: np.ndarray) -> np.ndarray:
+    """``pairwise_distance(x.astype(float32), dist_func_id=0)`` on the device, returned as the fp32 host matrix the
+    reference stores in ``obsp``."""
+    X = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).cuda()
+    return ops.pairwise_l2_dense(X).cpu().numpy()
+
+
+class SpaGCNGraph(BaseTransform):
+    """Distance over (x, y, z) where z is the histology colour summary of each spot's pixel window
+    (spatial_graph.py:13-62 ≡ spagcn.py:81-116).  The window means are a few thousand small uint8 slices of a host
+    image and stay on the host, as in the reference; the N×N distance matrix is the device kernel."""
+
+    _DISPLAY_ATTRS = ("alpha", "beta")
+
+    def __init__(self, alpha, beta, *, channels=("spatial", "spatial_pixel", "image"), channel_types=("obsm", "obsm", "uns"), **kwargs):
+        super().__init__(**kwargs)
+        self.alpha, self.beta = alpha, beta
+        self.channels, self.channel_types = channels, channel_types
+
+    def __call__(self, data):
+        xy = data.get_feature(return_type="numpy", channel=self.channels[0], channel_type=self.channel_types[0])
+        xy_pixel = data.get_feature(return_type="numpy", channel=self.channels[1], channel_type=self.channel_types[1])
+        img = data.get_feature(return_type="numpy", channel=self.channels[2], channel_type=self.channel_types[2])
+        g = np.zeros((xy.shape[0], 3))
+        beta_half = round(self.beta / 2)
+        x_lim, y_lim = img.shape[:2]
+        for i, (x_pixel, y_pixel) in enumerate(xy_pixel):
+            top, left = max(0, x_pixel - beta_half), max(0, y_pixel - beta_half)
+            bottom, right = min(x_lim, x_pixel + beta_half + 1), min(y_lim, y_pixel + beta_half + 1)
+            g[i] = np.mean(img[top:bottom, left:right], axis=(0, 1))
+        g_var = g.var(0)
+        self.logger.info(f"Variances of c0, c1, c2 = {g_var}")
+        z = (g * g_var).sum(1, keepdims=True) / g_var.sum()
+        z = (z - z.mean()) / z.std()
+        z *= xy.std(0).max() * self.alpha
+        xyz = np.hstack((xy, z)).astype(np.float32)
+        self.logger.info(f"Varirances of x, y, z = {xyz.var(0)}")
+        data.data.obsp[self.out] = _pairwise_distance_host(xyz)
+        return data
+
+
+class SpaGCNGraph2D(BaseTransform):
+    """Distance over the pixel coordinates only (spatial_graph.py:66-76)."""
+
+    def __init__(self, *, channel: str = "spatial_pixel", **kwargs):
+        super().__init__(**kwargs)
+        self.channel = channel
+
+    def __call__(self, data):
+        x = data.get_feature(channel=self.channel, channel_type="obsm", return_type="numpy")
+        data.data.obsp[self.out] = _pairwise_distance_host(x.astype(np.float32))
         return data

@@ -307,7 +307,7 @@ int b2_row_center_f32(const float* X, int64_t ldx, int32_t n, int32_t g, float* 
  *   b2_dec_q_f32       : q_ij = u_ij / Σ_j u_ij, u = ((1 + |z_i-mu_j|²/alpha) + 1e-8)^-(alpha+1) / 2       (:391-397)
  *   b2_dec_target_f32  : p = (q² / colsum(q)) row-normalised                                             (:408-425)
  *   b2_dec_kl_grad_f32 : loss = mean_i Σ_j p log(p/(q+1e-6)) (:399-406) and its gradients dz [n,h], dmu [K,h]
- *                        (both overwritten); q_out optional (argmax → labels).
+ *                        (both overwritten); q_out and labels_out (= argmax_j q_ij, first maximum, :527) optional.
  *   b2_sgd_momentum_step_f32 : torch.optim.SGD(momentum, weight_decay) as used at spagcn.py:463; step is 1-based.
  *   b2_exp_adj_f32     : out = exp(-D²/(2 l²)) elementwise (spagcn.py:807-809) and/or its total sum in fp64
  *                        (calculate_p / search_l, spagcn.py:249-251).
@@ -316,10 +316,11 @@ int b2_dec_q_f32(const float* z, int64_t ldz, const float* mu, int32_t n, int32_
                  float* q, int64_t ldq, void* stream);
 int b2_dec_target_f32(const float* q, int64_t ldq, const float* colsum, int32_t n, int32_t K, float* p, int64_t ldp, void* stream);
 int b2_dec_kl_grad_f32(const float* z, int64_t ldz, const float* mu, const float* p, int64_t ldp, int32_t n, int32_t K, int32_t h,
-                       float alpha, float* q_out, int64_t ldq, float* dz, int64_t lddz, float* dmu, float* loss_out, void* stream);
+                       float alpha, float* q_out, int64_t ldq, float* dz, int64_t lddz, float* dmu, float* loss_out,
+                       int32_t* labels_out, void* stream);
 int b2_sgd_momentum_step_f32(float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
                              float weight_decay, int32_t step, void* stream);
-int b2_exp_adj_f32(const float* D, float* out, int64_t n_elem, float l, double* sum_out_dev, void* stream);
+int b2_exp_adj_f32(const float* D, float* out, int64_t n_elem, double l, double* sum_out_dev, void* stream);
 
 #ifdef __cplusplus
 }

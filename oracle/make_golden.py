@@ -175,8 +175,91 @@ def _matrix_fixture():
     np.savez_compressed(OUT / "pairwise.npz", X=X, D=D)
 
 
+def _spagcn_fixture():
+    """SpaGCN (spagcn.py): search_l / calculate_p, SimpleGCDEC forward / target / KL loss / autograd gradients, and the
+    reference's own ``fit`` (Adam, mu frozen because the optimiser is created before ``self.mu`` exists, spagcn.py:464-495),
+    ``fit`` with SGD, the early-stop rule, and ``fit_with_init`` (mu trained)."""
+    import copy
+    import logging
+    logging.getLogger("dance").setLevel(logging.WARNING)
+    ref = ref_loader.spagcn()
+    mx = ref_loader.matrix()
+    rng = np.random.default_rng(11)
+    side, h, K = 16, 12, 3
+    gx, gy = np.meshgrid(np.arange(side), np.arange(side), indexing="ij")
+    xy = np.stack([gx.ravel() * 10 + rng.integers(-2, 3, side * side), gy.ravel() * 10 + rng.integers(-2, 3, side * side)], 1)
+    n = xy.shape[0]
+    domain = (xy[:, 0] > 55).astype(int) + (xy[:, 1] > 95).astype(int)
+    centers = rng.normal(scale=2.0, size=(K, h))
+    X = (centers[domain] + rng.normal(scale=1.0, size=(n, h))).astype(np.float32)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        D = mx.pairwise_distance(xy.astype(np.float32), 0)
+    l = ref.search_l(0.5, D, start=0.01, end=1000, tol=0.01, max_run=100)
+    p_at_l = ref.calculate_p(D, l)
+    adj_exp = np.exp(-1 * (D**2) / (2 * (l**2)))
+    out = dict(xy=xy, X=X, D=D, l=np.float64(l), p_at_l=np.float64(p_at_l), adj_exp=adj_exp, K=K)
+
+    def fresh():
+        torch.manual_seed(3)
+        return ref.SimpleGCDEC(h, h)
+
+    m0 = fresh()
+    out["W0"] = m0.gc.weight.detach().numpy().copy()
+    out["b0"] = m0.gc.bias.detach().numpy().copy()
+
+    # run A: reference fit, Adam, never stops early (tol < 0)
+    np.random.seed(0)
+    mA = fresh()
+    mA.fit(X, adj_exp, lr=0.005, epochs=25, weight_decay=0, opt="admin", init="kmeans", n_clusters=K, init_spa=True, tol=-1.0)
+    init_y = np.asarray(mA.trajectory[0]).astype(np.int64)
+    out.update(init_y=init_y, mu=mA.mu.detach().numpy().copy(), A_W=mA.gc.weight.detach().numpy().copy(),
+               A_b=mA.gc.bias.detach().numpy().copy())
+    zA, qA = mA.predict(X, adj_exp)
+    out.update(A_z=zA.detach().numpy(), A_q=qA.detach().numpy())
+
+    # one restated step at the initial state for kernel-level checks (reference forward / target / loss + autograd)
+    m1 = fresh()
+    m1.mu = torch.nn.Parameter(torch.tensor(out["mu"]))
+    z, q = m1(torch.FloatTensor(X), torch.FloatTensor(adj_exp))
+    p = m1.target_distribution(q).data
+    loss = m1.loss_function(p, q)
+    z.retain_grad()
+    loss.backward()
+    out.update(s_z=z.detach().numpy(), s_q=q.detach().numpy(), s_p=p.numpy(), s_loss=np.float64(loss.item()),
+               s_dz=z.grad.numpy(), s_dW=m1.gc.weight.grad.numpy(), s_db=m1.gc.bias.grad.numpy(), s_dmu=m1.mu.grad.numpy())
+
+    # run B: Adam with weight decay and the default stopping tolerance
+    np.random.seed(0)
+    mB = fresh()
+    mB.fit(X, adj_exp, lr=0.005, epochs=40, weight_decay=5e-4, opt="admin", init="kmeans", n_clusters=K, init_spa=True, tol=1e-3)
+    assert np.array_equal(np.asarray(mB.trajectory[0]), init_y)
+    out.update(B_W=mB.gc.weight.detach().numpy().copy(), B_b=mB.gc.bias.detach().numpy().copy())
+
+    # run C: SGD with momentum
+    np.random.seed(0)
+    mC = fresh()
+    mC.fit(X, adj_exp, lr=0.01, epochs=12, opt="sgd", init="kmeans", n_clusters=K, init_spa=True, tol=-1.0)
+    assert np.array_equal(np.asarray(mC.trajectory[0]), init_y)
+    out.update(C_W=mC.gc.weight.detach().numpy().copy(), C_b=mC.gc.bias.detach().numpy().copy())
+
+    # run D: fit_with_init on top of a fresh model that already owns mu (so mu is in the optimiser)
+    mD = fresh()
+    mD.mu = torch.nn.Parameter(torch.zeros(K, h))
+    mD.fit_with_init(X, adj_exp, init_y, lr=0.01, epochs=8, update_interval=1, opt="sgd")
+    out.update(D_W=mD.gc.weight.detach().numpy().copy(), D_b=mD.gc.bias.detach().numpy().copy(),
+               D_mu=mD.mu.detach().numpy().copy())
+    np.savez_compressed(OUT / "spagcn_dec.npz", **out)
+
+
 def main():
+    import sys
     OUT.mkdir(parents=True, exist_ok=True)
+    if "spagcn" in sys.argv[1:]:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            _spagcn_fixture()
+        return
     ref = ref_loader.scgnn2()
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
@@ -185,6 +268,7 @@ def main():
         _gat_fixture(ref, X, _KNN_IDX, adj_train)
         _feature_ae_fixture(ref)
         _matrix_fixture()
+        _spagcn_fixture()
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)
 

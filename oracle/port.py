@@ -373,6 +373,97 @@ def matrix_normalize(mat: np.ndarray, mode: str = "normalize", axis: int = 0, ep
 
 
 # --------------------------------------------------------------------------- synthetic data
+# ---------------------------------------------------------------------------------------------------------------
+# SpaGCN (reference dance/modules/spatial/spatial_domain/spagcn.py)
+# ---------------------------------------------------------------------------------------------------------------
+def spagcn_calculate_p(adj: np.ndarray, l: float) -> float:
+    """spagcn.py:249-251 — mean row sum of exp(-adj²/2l²), minus the self term."""
+    adj_exp = np.exp(-1 * (adj**2) / (2 * (l**2)))
+    return float(np.mean(np.sum(adj_exp, 1)) - 1)
+
+
+def spagcn_search_l(p, adj, start=0.01, end=1000, tol=0.01, max_run=100):
+    """spagcn.py:254-287 — bisection on l."""
+    run = 0
+    p_low, p_high = spagcn_calculate_p(adj, start), spagcn_calculate_p(adj, end)
+    if p_low > p + tol or p_high < p - tol:
+        return None
+    if abs(p_low - p) <= tol:
+        return start
+    if abs(p_high - p) <= tol:
+        return end
+    while (p_low + tol) < p < (p_high - tol):
+        run += 1
+        if run > max_run:
+            return None
+        mid = (start + end) / 2
+        p_mid = spagcn_calculate_p(adj, mid)
+        if abs(p_mid - p) <= tol:
+            return mid
+        if p_mid <= p:
+            start, p_low = mid, p_mid
+        else:
+            end, p_high = mid, p_mid
+    return None
+
+
+def spagcn_forward(X, adj, W, b, mu, alpha: float = 0.2):
+    """GraphConvolution.forward :357-363 + SimpleGCDEC.forward :391-397 (torch tensors, autograd-capable)."""
+    z = torch.mm(adj, torch.mm(X, W)) + b
+    q = 1.0 / ((1.0 + torch.sum((z.unsqueeze(1) - mu)**2, dim=2) / alpha) + 1e-8)
+    q = q**(alpha + 1.0) / 2.0
+    q = q / torch.sum(q, dim=1, keepdim=True)
+    return z, q
+
+
+def spagcn_target(q):
+    """target_distribution :408-425."""
+    p = q**2 / torch.sum(q, dim=0)
+    return p / torch.sum(p, dim=1, keepdim=True)
+
+
+def spagcn_kl(p, q):
+    """loss_function :399-406."""
+    return torch.mean(torch.sum(p * torch.log(p / (q + 1e-6)), dim=1))
+
+
+def spagcn_group_means(features: np.ndarray, y: np.ndarray) -> np.ndarray:
+    """Cluster centres in sorted-label order (groupby("Group").mean(), :499-503)."""
+    return np.stack([features[y == c].mean(0) for c in np.unique(y)]).astype(np.float32)
+
+
+def spagcn_fit(X, adj, W, b, init_y, lr, epochs, update_interval=3, weight_decay=0.0, opt="admin", tol=1e-3, alpha=0.2,
+               train_mu=False, mu=None):
+    """The training loop of SimpleGCDEC.fit (:505-534; ``train_mu=False`` — mu is not in the optimiser) or of
+    fit_with_init (:563-574; ``train_mu=True``, no stopping rule).  Returns (W, b, mu, epochs_run)."""
+    X, adj = torch.as_tensor(X), torch.as_tensor(adj)
+    W = torch.nn.Parameter(torch.as_tensor(W).clone())
+    b = torch.nn.Parameter(torch.as_tensor(b).clone())
+    with torch.no_grad():
+        feats = (torch.mm(adj, torch.mm(X, W)) + b).numpy()
+    mu_t = torch.nn.Parameter(torch.as_tensor(spagcn_group_means(feats, np.asarray(init_y))))
+    params = [W, b] + ([mu_t] if train_mu else [])
+    optim = torch.optim.SGD(params, lr=lr, momentum=0.9) if opt == "sgd" else torch.optim.Adam(params, lr=lr, weight_decay=weight_decay)
+    y_last = np.asarray(init_y)
+    done = 0
+    for epoch in range(epochs):
+        if epoch % update_interval == 0:
+            with torch.no_grad():
+                p = spagcn_target(spagcn_forward(X, adj, W, b, mu_t, alpha)[1])
+        optim.zero_grad()
+        _, q = spagcn_forward(X, adj, W, b, mu_t, alpha)
+        spagcn_kl(p, q).backward()
+        optim.step()
+        done = epoch + 1
+        if not train_mu:
+            y = torch.argmax(q, dim=1).numpy()
+            delta = np.sum(y != y_last).astype(np.float32) / X.shape[0]
+            y_last = y
+            if epoch > 0 and (epoch - 1) % update_interval == 0 and delta < tol:
+                break
+    return W.detach().numpy(), b.detach().numpy(), mu_t.detach().numpy(), done
+
+
 def synthetic_embedding(n: int, d: int = 128, n_clusters: int = 10, seed: int = 0) -> np.ndarray:
     """Z[N,d]: mixture of `n_clusters` unit-variance Gaussians, centres ~ N(0, 3²)."""
     rng = np.random.default_rng(seed)

@@ -42,7 +42,11 @@ def cuda():
     return torch.device("cuda:0")
 
 
+def _host(a):
+    return a.detach().cpu().numpy() if hasattr(a, "detach") else a
+
+
 def rel_err(a, b):
-    a = np.asarray(a, dtype=np.float64)
-    b = np.asarray(b, dtype=np.float64)
+    a = np.asarray(_host(a), dtype=np.float64)
+    b = np.asarray(_host(b), dtype=np.float64)
     return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)

@@ -21,7 +21,7 @@ def test_sym_eig_jacobi(cuda, g):
     assert np.allclose(ev, ref, rtol=2e-5, atol=1e-4 * ref[0])
     assert np.abs(V @ V.T - np.eye(g)).max() < 1e-4                       # orthonormal rows
     assert rel_err(V @ Cm.astype(np.float64) @ V.T, np.diag(ev)) < 1e-4   # diagonalises C
-    assert sweeps <= 15
+    assert sweeps <= 20
 
 
 @pytest.mark.parametrize("n,f,k", [(500, 40, 10), (60, 300, 20), (1000, 200, 50)])

@@ -177,3 +177,33 @@ def test_graph_ae_gat_golden(golden):
     assert abs(loss.item() - float(gg["loss"])) < 1e-6 * float(gg["loss"])
     for k_, v in sd.items():
         assert rel_err(v.grad.numpy(), gg["grad." + k_]) < 1e-5, k_
+
+
+def test_spagcn_golden(golden):
+    """The SpaGCN restatement against the reference's own search_l / forward / autograd / fit outputs."""
+    g = golden("spagcn_dec")
+    X, D, adj = g["X"], g["D"], g["adj_exp"]
+    assert abs(port.spagcn_calculate_p(D, float(g["l"])) - float(g["p_at_l"])) < 1e-6
+    assert port.spagcn_search_l(0.5, D) == float(g["l"])
+    assert np.array_equal(np.exp(-1 * (D**2) / (2 * (float(g["l"])**2))), adj)
+    mu = torch.tensor(g["mu"], requires_grad=True)
+    W = torch.tensor(g["W0"], requires_grad=True)
+    b = torch.tensor(g["b0"], requires_grad=True)
+    z, q = port.spagcn_forward(torch.tensor(X), torch.tensor(adj), W, b, mu)
+    p = port.spagcn_target(q).detach()
+    loss = port.spagcn_kl(p, q)
+    loss.backward()
+    for name, val in (("s_z", z), ("s_q", q), ("s_p", p), ("s_dW", W.grad), ("s_db", b.grad), ("s_dmu", mu.grad)):
+        assert np.allclose(val.detach().numpy(), g[name], rtol=1e-5, atol=1e-7), name
+    assert abs(loss.item() - float(g["s_loss"])) < 1e-7
+    assert np.allclose(port.spagcn_group_means(g["s_z"], g["init_y"]), g["mu"], rtol=1e-5, atol=1e-6)
+    # whole training runs: Adam with frozen mu (A), Adam + weight decay + stop rule (B), SGD (C), fit_with_init (D)
+    Wa, ba, mua, _ = port.spagcn_fit(X, adj, g["W0"], g["b0"], g["init_y"], 0.005, 25, tol=-1.0)
+    assert np.allclose(Wa, g["A_W"], rtol=1e-4, atol=1e-6) and np.allclose(ba, g["A_b"], rtol=1e-4, atol=1e-6)
+    assert np.allclose(mua, g["mu"], rtol=1e-5, atol=1e-6)
+    Wb, bb, _, n_b = port.spagcn_fit(X, adj, g["W0"], g["b0"], g["init_y"], 0.005, 40, weight_decay=5e-4, tol=1e-3)
+    assert np.allclose(Wb, g["B_W"], rtol=1e-4, atol=1e-6) and np.allclose(bb, g["B_b"], rtol=1e-4, atol=1e-6)
+    Wc, bc, _, _ = port.spagcn_fit(X, adj, g["W0"], g["b0"], g["init_y"], 0.01, 12, opt="sgd", tol=-1.0)
+    assert np.allclose(Wc, g["C_W"], rtol=1e-4, atol=1e-6) and np.allclose(bc, g["C_b"], rtol=1e-4, atol=1e-6)
+    Wd, bd, mud, _ = port.spagcn_fit(X, adj, g["W0"], g["b0"], g["init_y"], 0.01, 8, update_interval=1, opt="sgd", train_mu=True)
+    assert np.allclose(Wd, g["D_W"], rtol=1e-4, atol=1e-6) and np.allclose(mud, g["D_mu"], rtol=1e-4, atol=1e-6)
