@@ -47,6 +47,9 @@ _SIGNATURES = {
                                            c_vp, c_vp, c_i64, c_vp, c_vp]),
     "b2_gat_aggregate_bwd_f32": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64,
                                            c_i32, c_i32, c_i32, C.c_int, c_f32, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "b2_gat_aggregate_bwd_tied_f32": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64,
+                                                c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32, C.c_int, c_f32, c_vp, c_i64, c_vp, c_i64,
+                                                c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b2_gat_combine_fwd_f32": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i32, c_i32, c_i32, C.c_int, C.c_int, c_vp, c_i64, c_vp]),
     "b2_gat_combine_bwd_f32": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32, C.c_int, C.c_int, c_vp, c_i64, c_vp, c_i64,
                                          c_vp]),
@@ -61,6 +64,10 @@ _SIGNATURES = {
     "b2_dec_q_f32": (C.c_int, [c_vp, c_i64, c_vp, c_i32, c_i32, c_i32, c_f32, c_vp, c_i64, c_vp]),
     "b2_dec_target_f32": (C.c_int, [c_vp, c_i64, c_vp, c_i32, c_i32, c_vp, c_i64, c_vp]),
     "b2_dec_kl_grad_f32": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_f32, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "b2_clip_grad_norm_f32": (C.c_int, [c_vp, c_i64, c_f32, c_f32, c_vp, c_vp, c_vp]),
+    "b2_radius_graph_workspace_bytes": (c_sz, [c_i32]),
+    "b2_radius_graph_count": (C.c_int, [c_vp, c_i64, c_i32, c_i32, C.c_double, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "b2_radius_graph_fill": (C.c_int, [c_vp, c_i64, c_i32, c_i32, C.c_double, c_vp, c_vp, c_vp]),
     "b2_sgd_momentum_step_f32": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_i32, c_vp]),
     "b2_exp_adj_f32": (C.c_int, [c_vp, c_vp, c_i64, C.c_double, c_vp, c_vp]),
     "b2_normalize_total_workspace_bytes": (c_sz, [c_i32, c_i32]),

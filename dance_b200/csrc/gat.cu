@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(256)
 gat_bwd_target_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                       const float* __restrict__ H, int64_t ldh, const float* __restrict__ s_src,
                       const float* __restrict__ s_trg, const float* __restrict__ alpha,
-                      const float* __restrict__ dOut, int64_t lddo, int32_t n, int32_t nh, int32_t F, int act,
+                      const float* __restrict__ dOut, int64_t lddo, const float* __restrict__ H2, int64_t ldh2,
+                      const float* __restrict__ dOut2, int64_t lddo2, int32_t n, int32_t nh, int32_t F, int act,
                       float slope, float* __restrict__ dpre_edge, float* __restrict__ ds_trg) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -164,6 +165,8 @@ gat_bwd_target_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restr
         const int32_t u = colidx[p];
         float d = 0.f;
         for (int f = lane; f < F; f += 32) d = fmaf(dOut[v * lddo + h * F + f], H[(int64_t)u * ldh + h * F + f], d);
+        if (H2)   // tied attention: the same α also weights a second layer's messages (stagate.py:197)
+          for (int f = lane; f < F; f += 32) d = fmaf(dOut2[v * lddo2 + h * F + f], H2[(int64_t)u * ldh2 + h * F + f], d);
         d = warp_sum(d);
         t = fmaf(alpha[(int64_t)p * nh + h], d, t);
       }
@@ -172,6 +175,8 @@ gat_bwd_target_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restr
         const int32_t u = colidx[p];
         float d = 0.f;
         for (int f = lane; f < F; f += 32) d = fmaf(dOut[v * lddo + h * F + f], H[(int64_t)u * ldh + h * F + f], d);
+        if (H2)   // tied attention: the same α also weights a second layer's messages (stagate.py:197)
+          for (int f = lane; f < F; f += 32) d = fmaf(dOut2[v * lddo2 + h * F + f], H2[(int64_t)u * ldh2 + h * F + f], d);
         d = warp_sum(d);
         const float a = alpha[(int64_t)p * nh + h];
         const float pre = s_src[(int64_t)u * nh + h] + s_trg[v * nh + h];
@@ -189,8 +194,10 @@ gat_bwd_target_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restr
 __global__ void __launch_bounds__(256)
 gat_bwd_source_kernel(const int32_t* __restrict__ t_rowptr, const int32_t* __restrict__ t_colidx,
                       const int32_t* __restrict__ t_perm, const float* __restrict__ alpha,
-                      const float* __restrict__ dpre_edge, const float* __restrict__ dOut, int64_t lddo, int32_t n,
-                      int32_t nh, int32_t F, float* __restrict__ dH, int64_t lddh, float* __restrict__ ds_src) {
+                      const float* __restrict__ dpre_edge, const float* __restrict__ dOut, int64_t lddo,
+                      const float* __restrict__ dOut2, int64_t lddo2, int32_t n, int32_t nh, int32_t F,
+                      float* __restrict__ dH, int64_t lddh, float* __restrict__ dH2, int64_t lddh2,
+                      float* __restrict__ ds_src) {
   constexpr int MAXV = 16;
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -198,9 +205,9 @@ gat_bwd_source_kernel(const int32_t* __restrict__ t_rowptr, const int32_t* __res
   const int W = nh * F;
   for (int64_t u = warp; u < n; u += nwarps) {
     const int32_t s = t_rowptr[u], e = t_rowptr[u + 1];
-    float acc[MAXV];
+    float acc[MAXV], acc2[MAXV];
 #pragma unroll
-    for (int t = 0; t < MAXV; ++t) acc[t] = 0.f;
+    for (int t = 0; t < MAXV; ++t) { acc[t] = 0.f; acc2[t] = 0.f; }
     float ssrc = 0.f;  // lanes < nh accumulate ds_src for their head
     for (int32_t q = s; q < e; ++q) {
       const int32_t v = t_colidx[q];
@@ -208,14 +215,21 @@ gat_bwd_source_kernel(const int32_t* __restrict__ t_rowptr, const int32_t* __res
 #pragma unroll
       for (int t = 0; t < MAXV; ++t) {
         const int c = lane + 32 * t;
-        if (c < W) acc[t] = fmaf(alpha[(int64_t)p * nh + c / F], dOut[(int64_t)v * lddo + c], acc[t]);
+        if (c < W) {
+          const float a = alpha[(int64_t)p * nh + c / F];
+          acc[t] = fmaf(a, dOut[(int64_t)v * lddo + c], acc[t]);
+          if (dOut2) acc2[t] = fmaf(a, dOut2[(int64_t)v * lddo2 + c], acc2[t]);
+        }
       }
       if (lane < nh) ssrc += dpre_edge[(int64_t)p * nh + lane];
     }
 #pragma unroll
     for (int t = 0; t < MAXV; ++t) {
       const int c = lane + 32 * t;
-      if (c < W) dH[u * lddh + c] = acc[t];
+      if (c < W) {
+        dH[u * lddh + c] = acc[t];
+        if (dH2) dH2[u * lddh2 + c] = acc2[t];
+      }
     }
     if (lane < nh) ds_src[u * nh + lane] = ssrc;
   }
@@ -360,13 +374,13 @@ extern "C" int b2_gat_aggregate_fwd_f32(const int32_t* rowptr, const int32_t* co
   return B2_OK;
 }
 
-extern "C" int b2_gat_aggregate_bwd_f32(const int32_t* rowptr, const int32_t* colidx, const int32_t* t_rowptr,
-                                        const int32_t* t_colidx, const int32_t* t_perm, const float* H, int64_t ldh,
-                                        const float* a_src, const float* a_trg, const float* s_src, const float* s_trg,
-                                        const float* alpha, const float* dOut, int64_t lddo, int32_t n, int32_t nheads,
-                                        int32_t F, int score_act, float slope, float* dH, int64_t lddh, float* da_src,
-                                        float* da_trg, float* ds_src_ws, float* ds_trg_ws, float* dpre_edge_ws,
-                                        void* stream) {
+static int gat_aggregate_bwd_impl(const int32_t* rowptr, const int32_t* colidx, const int32_t* t_rowptr,
+                                  const int32_t* t_colidx, const int32_t* t_perm, const float* H, int64_t ldh,
+                                  const float* a_src, const float* a_trg, const float* s_src, const float* s_trg,
+                                  const float* alpha, const float* dOut, int64_t lddo, const float* H2, int64_t ldh2,
+                                  const float* dOut2, int64_t lddo2, int32_t n, int32_t nheads, int32_t F, int score_act,
+                                  float slope, float* dH, int64_t lddh, float* dH2, int64_t lddh2, float* da_src,
+                                  float* da_trg, float* ds_src_ws, float* ds_trg_ws, float* dpre_edge_ws, void* stream) {
   B2_REQUIRE(rowptr && colidx && t_rowptr && t_colidx && t_perm && H && a_src && a_trg && s_src && s_trg && alpha && dOut &&
                  dH && da_src && da_trg && ds_src_ws && ds_trg_ws && dpre_edge_ws,
              "b2_gat_aggregate_bwd_f32: null pointer");
@@ -374,11 +388,11 @@ extern "C" int b2_gat_aggregate_bwd_f32(const int32_t* rowptr, const int32_t* co
   if (n == 0) return B2_OK;
   cudaStream_t st = as_stream(stream);
   const int W = nheads * F;
-  gat_bwd_target_kernel<<<warp_rows_grid(n), 256, 0, st>>>(rowptr, colidx, H, ldh, s_src, s_trg, alpha, dOut, lddo, n, nheads, F,
-                                                          score_act, slope, dpre_edge_ws, ds_trg_ws);
+  gat_bwd_target_kernel<<<warp_rows_grid(n), 256, 0, st>>>(rowptr, colidx, H, ldh, s_src, s_trg, alpha, dOut, lddo, H2, ldh2, dOut2,
+                                                          lddo2, n, nheads, F, score_act, slope, dpre_edge_ws, ds_trg_ws);
   B2_CHECK_LAUNCH("gat_bwd_target_kernel");
-  gat_bwd_source_kernel<<<warp_rows_grid(n), 256, 0, st>>>(t_rowptr, t_colidx, t_perm, alpha, dpre_edge_ws, dOut, lddo, n, nheads,
-                                                          F, dH, lddh, ds_src_ws);
+  gat_bwd_source_kernel<<<warp_rows_grid(n), 256, 0, st>>>(t_rowptr, t_colidx, t_perm, alpha, dpre_edge_ws, dOut, lddo,
+                                                          dH2 ? dOut2 : nullptr, lddo2, n, nheads, F, dH, lddh, dH2, lddh2, ds_src_ws);
   B2_CHECK_LAUNCH("gat_bwd_source_kernel");
   B2_CHECK_CUDA(cudaMemsetAsync(da_src, 0, sizeof(float) * W, st));
   B2_CHECK_CUDA(cudaMemsetAsync(da_trg, 0, sizeof(float) * W, st));
@@ -390,6 +404,32 @@ extern "C" int b2_gat_aggregate_bwd_f32(const int32_t* rowptr, const int32_t* co
   gat_bwd_scores_kernel<<<grid, 256, 0, st>>>(H, ldh, a_src, a_trg, ds_src_ws, ds_trg_ws, n, nheads, F, dH, lddh, da_src, da_trg);
   B2_CHECK_LAUNCH("gat_bwd_scores_kernel");
   return B2_OK;
+}
+
+extern "C" int b2_gat_aggregate_bwd_f32(const int32_t* rowptr, const int32_t* colidx, const int32_t* t_rowptr,
+                                        const int32_t* t_colidx, const int32_t* t_perm, const float* H, int64_t ldh,
+                                        const float* a_src, const float* a_trg, const float* s_src, const float* s_trg,
+                                        const float* alpha, const float* dOut, int64_t lddo, int32_t n, int32_t nheads,
+                                        int32_t F, int score_act, float slope, float* dH, int64_t lddh, float* da_src,
+                                        float* da_trg, float* ds_src_ws, float* ds_trg_ws, float* dpre_edge_ws,
+                                        void* stream) {
+  return gat_aggregate_bwd_impl(rowptr, colidx, t_rowptr, t_colidx, t_perm, H, ldh, a_src, a_trg, s_src, s_trg, alpha, dOut, lddo,
+                                nullptr, 0, nullptr, 0, n, nheads, F, score_act, slope, dH, lddh, nullptr, 0, da_src, da_trg,
+                                ds_src_ws, ds_trg_ws, dpre_edge_ws, stream);
+}
+
+extern "C" int b2_gat_aggregate_bwd_tied_f32(const int32_t* rowptr, const int32_t* colidx, const int32_t* t_rowptr,
+                                             const int32_t* t_colidx, const int32_t* t_perm, const float* H, int64_t ldh,
+                                             const float* a_src, const float* a_trg, const float* s_src, const float* s_trg,
+                                             const float* alpha, const float* dOut, int64_t lddo, const float* H2, int64_t ldh2,
+                                             const float* dOut2, int64_t lddo2, int32_t n, int32_t nheads, int32_t F,
+                                             int score_act, float slope, float* dH, int64_t lddh, float* dH2, int64_t lddh2,
+                                             float* da_src, float* da_trg, float* ds_src_ws, float* ds_trg_ws,
+                                             float* dpre_edge_ws, void* stream) {
+  B2_REQUIRE(H2 && dOut2, "b2_gat_aggregate_bwd_tied_f32: the second layer's H2 / dOut2 are required (dH2 may be NULL)");
+  return gat_aggregate_bwd_impl(rowptr, colidx, t_rowptr, t_colidx, t_perm, H, ldh, a_src, a_trg, s_src, s_trg, alpha, dOut, lddo,
+                                H2, ldh2, dOut2, lddo2, n, nheads, F, score_act, slope, dH, lddh, dH2, lddh2, da_src, da_trg,
+                                ds_src_ws, ds_trg_ws, dpre_edge_ws, stream);
 }
 
 extern "C" int b2_gat_combine_fwd_f32(const float* agg, int64_t ldagg, const float* skip, int64_t ldskip, const float* bias,

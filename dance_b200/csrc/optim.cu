@@ -63,9 +63,52 @@ reparam_bwd_kernel(const float* __restrict__ dz, int64_t lddz, const float* __re
   }
 }
 
+// torch.nn.utils.clip_grad_norm_(params, max_norm) over one flat gradient bucket (stagate.py:221), with an optional
+// pre-scale folded in (the engines carry sum-reduced loss gradients; the mean's 1/numel is applied here):
+//   g ← s·g ; total = ||g||₂ ; g ← g · min(1, max_norm / (total + 1e-6))
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ acc) {
+  double local = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = (double)g[i];
+    local += v * v;
+  }
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0 && local != 0.0) atomicAdd(acc, local);
+}
+
+__global__ void __launch_bounds__(256)
+clip_scale_kernel(float* __restrict__ g, int64_t n, float pre_scale, float max_norm, const double* __restrict__ acc,
+                  float* __restrict__ norm_out) {
+  const float total = (float)(sqrt(acc[0]) * (double)fabsf(pre_scale));
+  float coef = max_norm / (total + 1e-6f);
+  coef = coef < 1.f ? coef : 1.f;
+  if (max_norm <= 0.f) coef = 1.f;     // max_norm <= 0: scale only
+  if (norm_out && blockIdx.x == 0 && threadIdx.x == 0) norm_out[0] = total;
+  const float f = pre_scale * coef;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) g[i] *= f;
+}
+
 }  // namespace b2
 
 using namespace b2;
+
+extern "C" int b2_clip_grad_norm_f32(float* grad, int64_t n, float pre_scale, float max_norm, double* sumsq_ws,
+                                     float* norm_out, void* stream) {
+  B2_REQUIRE(grad && sumsq_ws && n >= 0, "b2_clip_grad_norm_f32: bad arguments");
+  if (n == 0) return B2_OK;
+  cudaStream_t st = as_stream(stream);
+  int64_t blocks = ceil_div<int64_t>(n, 1024);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  B2_CHECK_CUDA(cudaMemsetAsync(sumsq_ws, 0, sizeof(double), st));
+  sumsq_kernel<<<(unsigned)blocks, 256, 0, st>>>(grad, n, sumsq_ws);
+  B2_CHECK_LAUNCH("sumsq_kernel");
+  clip_scale_kernel<<<(unsigned)blocks, 256, 0, st>>>(grad, n, pre_scale, max_norm, sumsq_ws, norm_out);
+  B2_CHECK_LAUNCH("clip_scale_kernel");
+  return B2_OK;
+}
+
 
 extern "C" int b2_adam_step_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                                 float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,

@@ -428,8 +428,8 @@ def gat_aggregate_fwd(T: CSR, H, s_src, s_trg, nheads: int, score_act="leakyrelu
 
 
 def gat_aggregate_bwd(T: CSR, Tt: CSR, t_perm, H, a_src, a_trg, s_src, s_trg, alpha, dOut, nheads: int,
-                      score_act="leakyrelu", slope=0.2):
-    """Returns (dH, da_src, da_trg)."""
+                      score_act="leakyrelu", slope=0.2, H2=None, dOut2=None, want_dH2=True):
+    """Returns (dH, da_src, da_trg), or (dH, da_src, da_trg, dH2 | None) with a tied second layer (H2, dOut2)."""
     n, W = H.shape
     F = W // nheads
     dev = H.device
@@ -439,6 +439,15 @@ def gat_aggregate_bwd(T: CSR, Tt: CSR, t_perm, H, a_src, a_trg, s_src, s_trg, al
     ds_s = torch.empty(n * nheads, dtype=torch.float32, device=dev)
     ds_t = torch.empty(n * nheads, dtype=torch.float32, device=dev)
     dpre = torch.empty(max(T.nnz, 1) * nheads, dtype=torch.float32, device=dev)
+    if H2 is not None:
+        dH2 = torch.empty((n, W), dtype=torch.float32, device=dev) if want_dH2 else None
+        check(lib().b2_gat_aggregate_bwd_tied_f32(_p(T.rowptr), _p(T.colidx), _p(Tt.rowptr), _p(Tt.colidx), _p(t_perm), _p(H),
+                                                  _rowmajor(H, "H"), _p(a_src), _p(a_trg), _p(s_src), _p(s_trg), _p(alpha), _p(dOut),
+                                                  _rowmajor(dOut, "dOut"), _p(H2), _rowmajor(H2, "H2"), _p(dOut2),
+                                                  _rowmajor(dOut2, "dOut2"), n, nheads, F, SCORE_ACT[score_act], slope, _p(dH),
+                                                  _rowmajor(dH, "dH"), _p(dH2), _rowmajor(dH2, "dH2") if want_dH2 else 0, _p(da_src), _p(da_trg),
+                                                  _p(ds_s), _p(ds_t), _p(dpre), _stream()), "b2_gat_aggregate_bwd_tied_f32")
+        return dH, da_src, da_trg, dH2
     check(lib().b2_gat_aggregate_bwd_f32(_p(T.rowptr), _p(T.colidx), _p(Tt.rowptr), _p(Tt.colidx), _p(t_perm), _p(H),
                                          _rowmajor(H, "H"), _p(a_src), _p(a_trg), _p(s_src), _p(s_trg), _p(alpha), _p(dOut),
                                          _rowmajor(dOut, "dOut"), n, nheads, F, SCORE_ACT[score_act], slope, _p(dH),
@@ -606,3 +615,29 @@ def exp_adj(D: torch.Tensor, l: float, want_matrix: bool = True, want_sum: bool 
     acc = torch.zeros(1, dtype=torch.float64, device=D.device) if want_sum else None
     check(lib().b2_exp_adj_f32(_p(D), _p(out), D.numel(), float(l), _p(acc), _stream()), "b2_exp_adj_f32")
     return out, acc
+
+
+def clip_grad_norm_(grad: torch.Tensor, max_norm: float, pre_scale: float = 1.0, norm_out: Optional[torch.Tensor] = None):
+    """In-place ``clip_grad_norm_`` over one flat bucket (after multiplying it by ``pre_scale``)."""
+    _chk(grad, torch.float32, "grad")
+    ws = torch.empty(1, dtype=torch.float64, device=grad.device)
+    check(lib().b2_clip_grad_norm_f32(_p(grad), grad.numel(), float(pre_scale), float(max_norm), _p(ws), _p(norm_out), _stream()),
+          "b2_clip_grad_norm_f32")
+    return grad
+
+
+def radius_graph(X: torch.Tensor, radius: float) -> "CSR":
+    """Unit-weight CSR of all pairs within ``radius`` (self included); ``X`` is [n, d<=4] float64 on the device."""
+    _chk(X, torch.float64, "X", 2)
+    n, d = X.shape
+    ws = _workspace(lib().b2_radius_graph_workspace_bytes(n), X.device)
+    rowptr = torch.empty(n + 1, dtype=torch.int32, device=X.device)
+    nnz = C.c_int64(0)
+    check(lib().b2_radius_graph_count(_p(X), _rowmajor(X, "X"), n, d, float(radius), _p(rowptr), C.addressof(nnz), _p(ws),
+                                      ws.numel(), _stream()), "b2_radius_graph_count")
+    colidx = torch.empty(max(nnz.value, 1), dtype=torch.int32, device=X.device)[:nnz.value]
+    if nnz.value:
+        check(lib().b2_radius_graph_fill(_p(X), _rowmajor(X, "X"), n, d, float(radius), _p(rowptr), _p(colidx), _stream()),
+              "b2_radius_graph_fill")
+    vals = torch.ones(nnz.value, dtype=torch.float32, device=X.device)
+    return CSR(rowptr, colidx, vals, (n, n))

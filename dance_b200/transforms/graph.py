@@ -120,3 +120,36 @@ class SpaGCNGraph2D(BaseTransform):
         x = data.get_feature(channel=self.channel, channel_type="obsm", return_type="numpy")
         data.data.obsp[self.out] = _pairwise_distance_host(x.astype(np.float32))
         return data
+
+
+class StagateGraph(BaseTransform):
+    """STAGATE spatial graph (spatial_graph.py:113-151): ``radius`` → all spot pairs within ``radius`` (self included,
+    sklearn ``radius_neighbors_graph``), ``knn`` → the ``n_neighbors`` nearest spots of every spot, the spot itself being
+    the first of them (sklearn ``kneighbors_graph`` on its own training data).  Unit weights, scipy CSR in ``obsp``.
+    Exact ties at the k-th distance are broken by the lower spot index (sklearn's tree order is unspecified there)."""
+
+    _MODELS = ("radius", "knn")
+    _DISPLAY_ATTRS = ("model_name", "radius", "n_neighbors")
+
+    def __init__(self, model_name: str = "radius", *, radius: float = 1, n_neighbors: int = 5, channel: str = "spatial_pixel",
+                 channel_type: str = "obsm", **kwargs):
+        super().__init__(**kwargs)
+        if not isinstance(model_name, str) or (model_name.lower() not in self._MODELS):
+            raise ValueError(f"Unknown model {model_name!r}, available options are {self._MODELS}")
+        self.model_name, self.radius, self.n_neighbors = model_name, radius, n_neighbors
+        self.channel, self.channel_type = channel, channel_type
+
+    def __call__(self, data):
+        xy = np.asarray(data.get_feature(return_type="numpy", channel=self.channel, channel_type=self.channel_type))
+        n = xy.shape[0]
+        if self.model_name.lower() == "radius":
+            A = ops.radius_graph(torch.as_tensor(np.ascontiguousarray(xy, dtype=np.float64)).cuda(), float(self.radius))
+            indptr, indices = A.rowptr.cpu().numpy(), A.colidx.cpu().numpy()
+        else:
+            k = int(self.n_neighbors)
+            idx, _ = ops.knn(torch.as_tensor(np.ascontiguousarray(xy, dtype=np.float32)).cuda(), k, include_rank0=True, return_dist=False)
+            indices = np.sort(idx.cpu().numpy(), axis=1).reshape(-1)
+            indptr = np.arange(0, n * k + 1, k, dtype=np.int32)
+        adj = sp.csr_matrix((np.ones(len(indices), dtype=np.float64), indices, indptr), shape=(n, n))
+        data.data.obsp[self.out] = adj
+        return data

@@ -151,6 +151,11 @@ int b2_gae_loss_grad_f32(const float* z, int64_t ldz, const float* mu, const flo
 int b2_adam_step_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                      int64_t n, float lr, float beta1, float beta2, float eps,
                      float weight_decay, int32_t step, void* stream);
+/* torch.nn.utils.clip_grad_norm_ on one flat gradient bucket (stagate.py:221):
+ *   g ← pre_scale·g ; total = ||g||₂ ; g ← g·min(1, max_norm/(total+1e-6))   (max_norm <= 0: scale only)
+ * sumsq_ws: one device double of scratch; norm_out (device, optional) receives the total norm. */
+int b2_clip_grad_norm_f32(float* grad, int64_t n, float pre_scale, float max_norm, double* sumsq_ws,
+                          float* norm_out, void* stream);
 
 /* ------------------------------------------------------------------------
  * Elementwise helpers on the GCN path
@@ -252,6 +257,19 @@ int b2_gat_aggregate_bwd_f32(const int32_t* rowptr, const int32_t* colidx,
                              int score_act, float slope,
                              float* dH, int64_t lddh, float* da_src, float* da_trg,
                              float* ds_src_ws, float* ds_trg_ws, float* dpre_edge_ws, void* stream);
+/* Tied attention (STAGATE, stagate.py:197: conv3 reuses conv1's node scores, so the SAME edge coefficients α weight
+ * two layers' messages).  As above, plus the second layer's projected features H2 / upstream gradient dOut2:
+ *   dα_e = <dOut[v],H[u]> + <dOut2[v],H2[u]> ;  dH2[u] = Σ α dOut2[v] (message path only — the scores depend on H;
+ *   pass dH2 = NULL when the caller already has it). */
+int b2_gat_aggregate_bwd_tied_f32(const int32_t* rowptr, const int32_t* colidx,
+                                  const int32_t* t_rowptr, const int32_t* t_colidx, const int32_t* t_perm,
+                                  const float* H, int64_t ldh, const float* a_src, const float* a_trg,
+                                  const float* s_src, const float* s_trg, const float* alpha,
+                                  const float* dOut, int64_t lddo, const float* H2, int64_t ldh2,
+                                  const float* dOut2, int64_t lddo2, int32_t n, int32_t nheads, int32_t F,
+                                  int score_act, float slope,
+                                  float* dH, int64_t lddh, float* dH2, int64_t lddh2, float* da_src, float* da_trg,
+                                  float* ds_src_ws, float* ds_trg_ws, float* dpre_edge_ws, void* stream);
 /* skip connection + concat | head-mean + bias + activation (scgnn2.py:1189-1215):
  *   concat: out[n, nheads*F] = act(agg + skip + bias) ; else out[n,F] = act(mean_h(agg + skip) + bias)
  *   skip may be NULL.  Backward: dpre [n, nheads*F] = d(agg) = d(skip); dact [n, OW] (optional) is the
@@ -262,6 +280,18 @@ int b2_gat_combine_fwd_f32(const float* agg, int64_t ldagg, const float* skip, i
 int b2_gat_combine_bwd_f32(const float* dout, int64_t lddo, const float* out, int64_t ldo,
                            int32_t n, int32_t nheads, int32_t F, int concat, int act,
                            float* dpre, int64_t ldp, float* dact, int64_t ldact, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Radius graph over spot coordinates — StagateGraph(model_name="radius"):
+ * NearestNeighbors(radius=r).fit(X).radius_neighbors_graph(X) (transforms/graph/spatial_graph.py:143-151).
+ *   X [n, d] fp64 (1 <= d <= 4), A_ij = 1 iff Σ_c (x_ic - x_jc)² <= r² in fp64 (sklearn's reduced-distance test), self
+ *   included.  `count` writes rowptr [n+1] and returns nnz (synchronises); `fill` writes colidx [nnz], ascending per row.
+ * ---------------------------------------------------------------------- */
+size_t b2_radius_graph_workspace_bytes(int32_t n);
+int b2_radius_graph_count(const double* X, int64_t ldx, int32_t n, int32_t d, double radius, int32_t* rowptr,
+                          int64_t* nnz_host, void* workspace, size_t workspace_bytes, void* stream);
+int b2_radius_graph_fill(const double* X, int64_t ldx, int32_t n, int32_t d, double radius, const int32_t* rowptr,
+                         int32_t* colidx, void* stream);
 
 /* ------------------------------------------------------------------------
  * K10 CellFeatureGraph (transforms/graph/cell_feature_graph.py:34-79)

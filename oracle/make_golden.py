@@ -252,13 +252,62 @@ def _spagcn_fixture():
     np.savez_compressed(OUT / "spagcn_dec.npz", **out)
 
 
+def _stagate_fixture():
+    """STAGATE (stagate.py): the reference's GATConv / Stagate.forward / pretrain executed on oracle/pyg_lite.py, plus
+    sklearn's radius / kNN graphs as used by StagateGraph (spatial_graph.py:143-151)."""
+    from sklearn.neighbors import NearestNeighbors
+    ref = ref_loader.stagate()
+    rng = np.random.default_rng(17)
+    side = 14
+    gx, gy = np.meshgrid(np.arange(side), np.arange(side), indexing="ij")
+    xy = np.stack([gx.ravel() * 100 + (gy.ravel() % 2) * 50 + rng.integers(-3, 4, side * side),
+                   gy.ravel() * 87 + rng.integers(-3, 4, side * side)], 1).astype(np.int64)
+    n = xy.shape[0]
+    dims = [36, 24, 8]
+    dom = (xy[:, 0] > 650).astype(int) + (xy[:, 1] > 600).astype(int)
+    X = (rng.normal(scale=1.5, size=(3, dims[0]))[dom] + rng.normal(size=(n, dims[0]))).astype(np.float32)
+    adj_r = NearestNeighbors(radius=150).fit(xy).radius_neighbors_graph(xy).tocsr()
+    adj_r.sort_indices()
+    adj_k = NearestNeighbors(n_neighbors=5).fit(xy).kneighbors_graph(xy).tocsr()
+    adj_k.sort_indices()
+    out = dict(xy=xy, X=X, dims=np.array(dims), radius=np.float64(150), r_indptr=adj_r.indptr, r_indices=adj_r.indices,
+               k_indptr=adj_k.indptr, k_indices=adj_k.indices)
+    edge = np.vstack(np.nonzero(adj_r))
+    out["edge_index"] = edge
+
+    torch.manual_seed(5)
+    m = ref.Stagate(dims, device="cpu")
+    for k, v in m.state_dict().items():
+        out["init." + k] = v.numpy().copy()
+    xt, et = torch.from_numpy(X), torch.from_numpy(edge.astype(np.int64))
+    z, rec = m(xt, et)
+    loss = torch.nn.functional.mse_loss(xt, rec)
+    loss.backward()
+    out.update(f_z=z.detach().numpy(), f_rec=rec.detach().numpy(), f_loss=np.float64(loss.item()))
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            out["grad." + k] = p.grad.numpy().copy()
+    total = torch.nn.utils.clip_grad_norm_(m.parameters(), 5)
+    out["grad_norm"] = np.float64(total.item())
+    m.zero_grad()
+
+    # pretrain with a clipping threshold small enough to be active
+    m.pretrain(X, edge, lr=1e-3, weight_decay=1e-4, epochs=8, gradient_clipping=0.05)
+    for k, v in m.state_dict().items():
+        out["fit." + k] = v.numpy().copy()
+    out["fit_rep"] = m.rep.copy()
+    np.savez_compressed(OUT / "stagate.npz", **out)
+
+
 def main():
     import sys
     OUT.mkdir(parents=True, exist_ok=True)
-    if "spagcn" in sys.argv[1:]:
+    only = [a for a in sys.argv[1:] if a in ("spagcn", "stagate")]
+    if only:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            _spagcn_fixture()
+            for a in only:
+                {"spagcn": _spagcn_fixture, "stagate": _stagate_fixture}[a]()
         return
     ref = ref_loader.scgnn2()
     with warnings.catch_warnings():
@@ -269,6 +318,7 @@ def main():
         _feature_ae_fixture(ref)
         _matrix_fixture()
         _spagcn_fixture()
+        _stagate_fixture()
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)
 

@@ -92,3 +92,32 @@ def spagcn():
     sys.modules["dance.utils"].matrix = matrix()
     sys.modules["dance.utils.matrix"] = matrix()
     return _load("dance_ref_spagcn", "dance/modules/spatial/spatial_domain/spagcn.py")
+
+
+def stagate():
+    """The reference's ``dance/modules/spatial/spatial_domain/stagate.py`` (GATConv, Stagate) on top of the restated PyG
+    primitives in ``oracle/pyg_lite.py``; scanpy / dance.transforms / dance.modules.base are stubbed."""
+    if "dance_ref_stagate" in sys.modules:
+        return sys.modules["dance_ref_stagate"]
+    _install_stubs()
+    from . import pyg_lite
+    _stub("scanpy", pp=types.SimpleNamespace(highly_variable_genes=None, normalize_total=None, log1p=None), tl=types.SimpleNamespace(),
+          AnnData=object)
+    _stub("torch_geometric")
+    _stub("torch_geometric.nn")
+    _stub("torch_geometric.nn.conv", MessagePassing=pyg_lite.MessagePassing)
+    _stub("torch_geometric.utils", add_self_loops=pyg_lite.add_self_loops, remove_self_loops=pyg_lite.remove_self_loops,
+          softmax=pyg_lite.softmax)
+
+    class BasePretrain:
+
+        def _pretrain(self, *args, force_pretrain=False, **kwargs):
+            self.pretrain(*args, **kwargs)          # modules/base.py:80-108 minus the on-disk cache
+            self._is_pretrained = True
+
+    _stub("dance.modules")
+    _stub("dance.modules.base", BaseClusteringMethod=type("BaseClusteringMethod", (), {}), BasePretrain=BasePretrain)
+    dummy = type("Dummy", (), {"__init__": lambda self, *a, **k: None})
+    _stub("dance.transforms", AnnDataTransform=dummy, Compose=dummy, SetConfig=dummy, CellPCA=dummy, FilterGenesMatch=dummy)
+    _stub("dance.transforms.graph", StagateGraph=dummy, SpaGCNGraph=dummy, SpaGCNGraph2D=dummy)
+    return _load("dance_ref_stagate", "dance/modules/spatial/spatial_domain/stagate.py")

@@ -1,0 +1,126 @@
+"""STAGATE path (BASELINE config 5): StagateGraph (radius / kNN), the sigmoid-score per-target-softmax GAT layer with tied
+attention, gradient clipping and the aliased-weight Adam updates — against fixtures produced by the REFERENCE's own
+``Stagate`` code running on the restated PyG primitives (oracle/pyg_lite.py; parity unpinned at the PyG boundary)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def _model(g, cuda, precision=None):
+    from dance_b200.modules.stagate import Stagate
+    m = Stagate([int(v) for v in g["dims"]], device=cuda, precision=precision)
+    m.load_state_dict({k[5:]: g[k] for k in g.files if k.startswith("init.")})
+    return m
+
+
+def test_stagate_graph_matches_sklearn(cuda, golden):
+    from dance_b200.data import AnnDataLite, Data
+    from dance_b200.transforms import StagateGraph
+    g = golden("stagate")
+    ad = AnnDataLite(np.zeros((g["xy"].shape[0], 3), np.float32), obsm={"spatial_pixel": g["xy"]})
+    data = Data(ad)
+    StagateGraph("radius", radius=float(g["radius"]))(data)
+    A = ad.obsp["StagateGraph"]
+    assert np.array_equal(A.indptr, g["r_indptr"]) and np.array_equal(A.indices, g["r_indices"])      # structure: bit-exact
+    assert A.dtype == np.float64 and np.all(A.data == 1.0)
+    StagateGraph("knn", n_neighbors=5, out="knn")(data)
+    K = ad.obsp["knn"]
+    assert np.array_equal(K.indptr, g["k_indptr"]) and np.array_equal(K.indices, g["k_indices"])
+    assert repr(StagateGraph("radius", radius=150)) == "StagateGraph(model_name='radius', radius=150, n_neighbors=5)"
+    with pytest.raises(ValueError):
+        StagateGraph("delaunay")
+
+
+def test_radius_graph_edge_cases(cuda):
+    from dance_b200 import ops
+    rng = np.random.default_rng(0)
+    X = rng.uniform(0, 50, size=(700, 3))
+    X[10] = X[11]                                           # duplicate point
+    for r in (0.0, 3.0, 7.5, 1e3):
+        A = ops.radius_graph(torch.as_tensor(X).to(cuda), r)
+        d2 = ((X[:, None, :] - X[None, :, :])**2)
+        s = d2[..., 0]
+        for c in range(1, 3):
+            s = s + d2[..., c]
+        ref = sp.csr_matrix(s <= r * r)
+        ref.sort_indices()
+        assert np.array_equal(A.rowptr.cpu().numpy(), ref.indptr) and np.array_equal(A.colidx.cpu().numpy(), ref.indices), r
+    E = ops.radius_graph(torch.zeros((0, 2), dtype=torch.float64, device=cuda), 1.0)
+    assert E.nnz == 0 and E.rowptr.numel() == 1
+
+
+def test_clip_grad_norm_matches_torch(cuda):
+    from dance_b200 import ops
+    rng = np.random.default_rng(3)
+    g0 = rng.normal(size=5000).astype(np.float32)
+    for max_norm, scale in ((5.0, 1.0), (0.3, 1.0), (0.3, 0.01)):
+        p = torch.nn.Parameter(torch.zeros(5000))
+        p.grad = torch.tensor(g0 * scale)
+        total = torch.nn.utils.clip_grad_norm_([p], max_norm)
+        g = torch.tensor(g0).to(cuda)
+        nrm = torch.zeros(1, device=cuda)
+        ops.clip_grad_norm_(g, max_norm, pre_scale=scale, norm_out=nrm)
+        assert abs(nrm.item() - total.item()) < 1e-5 * total.item()
+        assert np.allclose(g.cpu().numpy(), p.grad.numpy(), rtol=2e-6, atol=1e-9)
+
+
+def test_forward_and_gradients_match_reference(cuda, golden):
+    g = golden("stagate")
+    m = _model(g, cuda)
+    z, rec = m(g["X"], g["edge_index"])
+    assert rel_err(z, g["f_z"]) < TOL and rel_err(rec, g["f_rec"]) < TOL
+    # one training step with lr=0 leaves the weights alone and exposes the clipped gradients
+    X = m._to_dev(g["X"])
+    m._train_step(X, lr=0.0, weight_decay=0.0, gradient_clipping=1e9)
+    G = m.params.g
+    assert abs(m.last_loss.item() - float(g["f_loss"])) < 1e-5 * float(g["f_loss"])
+    assert abs(m.last_grad_norm.item() - float(g["grad_norm"])) < TOL * float(g["grad_norm"])
+    assert rel_err(G["conv1.lin_src"], g["grad.conv1.lin_src"]) < TOL
+    assert rel_err(G["conv1.att_src"], g["grad.conv1.att_src"].reshape(-1)) < TOL
+    assert rel_err(G["conv1.att_dst"], g["grad.conv1.att_dst"].reshape(-1)) < TOL
+    assert rel_err(G["conv2.lin_src"], g["grad.conv2.lin_src"]) < TOL
+    assert rel_err(G["conv3.lin_src.T"], g["grad.conv3.lin_src"].T) < TOL
+    assert rel_err(G["conv4.lin_src.T"], g["grad.conv4.lin_src"].T) < TOL
+
+
+def test_pretrain_matches_reference(cuda, golden):
+    g = golden("stagate")
+    m = _model(g, cuda)
+    m.pretrain(g["X"], g["edge_index"], lr=1e-3, weight_decay=1e-4, epochs=8, gradient_clipping=0.05)
+    sd = m.state_dict()
+    for k in ("conv1.lin_src", "conv1.att_src", "conv1.att_dst", "conv2.lin_src", "conv3.lin_src", "conv4.lin_src"):
+        assert rel_err(sd[k], g["fit." + k]) < TOL, k
+    for k in ("conv2.att_src", "conv4.att_dst"):
+        assert np.array_equal(sd[k].cpu().numpy(), g["fit." + k])          # never trained
+    assert rel_err(m.rep, g["fit_rep"]) < TOL
+
+
+def test_stagate_fit_end_to_end(cuda):
+    """Default widths (512 hidden, 30 out) on a planted 4-domain layout: tensor-core GEMMs, tied GAT, GMM clustering."""
+    from dance_b200 import ops
+    from dance_b200.data import AnnDataLite, Data
+    from dance_b200.modules.stagate import Stagate
+    from dance_b200.transforms import StagateGraph
+    rng = np.random.default_rng(4)
+    side, G = 40, 200
+    gx, gy = np.meshgrid(np.arange(side), np.arange(side), indexing="ij")
+    xy = np.stack([gx.ravel() * 100 + rng.integers(-5, 6, side * side), gy.ravel() * 100 + rng.integers(-5, 6, side * side)], 1)
+    dom = (gx.ravel() >= side // 2).astype(int) * 2 + (gy.ravel() >= side // 2).astype(int)
+    X = (rng.normal(scale=1.0, size=(4, G))[dom] + rng.normal(scale=1.0, size=(side * side, G))).astype(np.float32)
+    data = Data(AnnDataLite(X, obsm={"spatial_pixel": xy}))
+    StagateGraph("radius", radius=150)(data)
+    adj = data.data.obsp["StagateGraph"]
+    edge = np.vstack(np.nonzero(adj))
+    m = Stagate([G, 512, 30], device=cuda, seed=0)
+    ops.reset_counters()
+    score = m.fit_score((X, edge), dom, epochs=60, num_cluster=4, random_state=0)
+    assert ops.counters()["launches"] > 60 * 15
+    assert m.rep.shape == (side * side, 30) and np.isfinite(m.rep).all()
+    assert score > 0.9
