@@ -630,6 +630,9 @@ def radius_graph(X: torch.Tensor, radius: float) -> "CSR":
     """Unit-weight CSR of all pairs within ``radius`` (self included); ``X`` is [n, d<=4] float64 on the device."""
     _chk(X, torch.float64, "X", 2)
     n, d = X.shape
+    if n == 0:
+        return CSR(torch.zeros(1, dtype=torch.int32, device=X.device), torch.empty(0, dtype=torch.int32, device=X.device),
+                   torch.empty(0, dtype=torch.float32, device=X.device), (0, 0))
     ws = _workspace(lib().b2_radius_graph_workspace_bytes(n), X.device)
     rowptr = torch.empty(n + 1, dtype=torch.int32, device=X.device)
     nnz = C.c_int64(0)

@@ -32,7 +32,18 @@ def test_stagate_graph_matches_sklearn(cuda, golden):
     assert A.dtype == np.float64 and np.all(A.data == 1.0)
     StagateGraph("knn", n_neighbors=5, out="knn")(data)
     K = ad.obsp["knn"]
-    assert np.array_equal(K.indptr, g["k_indptr"]) and np.array_equal(K.indices, g["k_indices"])
+    assert np.array_equal(K.indptr, g["k_indptr"])
+    # rows whose 5th and 6th nearest spots are at exactly the same distance have no unique answer (sklearn's tree order vs
+    # our lower-index rule): there the neighbour DISTANCES must agree; everywhere else the indices are bit-exact
+    xy = g["xy"].astype(np.float64)
+    d2 = ((xy[:, None, :] - xy[None, :, :])**2).sum(-1)
+    srt = np.sort(d2, axis=1)
+    tie = srt[:, 4] == srt[:, 5]
+    assert 0 < tie.sum() < 10
+    mine, ref = K.indices.reshape(-1, 5), g["k_indices"].reshape(-1, 5)
+    assert np.array_equal(mine[~tie], ref[~tie])
+    for i in np.flatnonzero(tie):
+        assert np.array_equal(np.sort(d2[i, mine[i]]), np.sort(d2[i, ref[i]]))
     assert repr(StagateGraph("radius", radius=150)) == "StagateGraph(model_name='radius', radius=150, n_neighbors=5)"
     with pytest.raises(ValueError):
         StagateGraph("delaunay")
