@@ -64,6 +64,13 @@ _SIGNATURES = {
     "b2_dec_q_f32": (C.c_int, [c_vp, c_i64, c_vp, c_i32, c_i32, c_i32, c_f32, c_vp, c_i64, c_vp]),
     "b2_dec_target_f32": (C.c_int, [c_vp, c_i64, c_vp, c_i32, c_i32, c_vp, c_i64, c_vp]),
     "b2_dec_kl_grad_f32": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_f32, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "b2_matrix_normalize_workspace_bytes": (c_sz, [c_i32, c_i32, C.c_int]),
+    "b2_matrix_normalize_f32": (C.c_int, [c_vp, c_i64, c_i32, c_i32, C.c_int, C.c_int, c_f32, c_vp, c_i64, c_vp, c_sz, c_vp]),
+    "b2_pearson_corr_workspace_bytes": (c_sz, [c_i32]),
+    "b2_pearson_corr_f32": (C.c_int, [c_vp, c_i64, c_i32, c_i32, c_vp, c_i64, c_vp, c_sz, c_vp]),
+    "b2_threshold_graph_workspace_bytes": (c_sz, [c_i32]),
+    "b2_threshold_graph_count": (C.c_int, [c_vp, c_i64, c_i32, c_f32, C.c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "b2_threshold_graph_fill": (C.c_int, [c_vp, c_i64, c_i32, c_f32, C.c_int, c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "b2_clip_grad_norm_f32": (C.c_int, [c_vp, c_i64, c_f32, c_f32, c_vp, c_vp, c_vp]),
     "b2_radius_graph_workspace_bytes": (c_sz, [c_i32]),
     "b2_radius_graph_count": (C.c_int, [c_vp, c_i64, c_i32, c_i32, C.c_double, c_vp, c_vp, c_vp, c_sz, c_vp]),

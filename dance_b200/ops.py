@@ -644,3 +644,51 @@ def radius_graph(X: torch.Tensor, radius: float) -> "CSR":
               "b2_radius_graph_fill")
     vals = torch.ones(nnz.value, dtype=torch.float32, device=X.device)
     return CSR(rowptr, colidx, vals, (n, n))
+
+
+NORM_MODE = {"normalize": 0, "standardize": 1, "minmax": 2, "l2": 3}
+
+
+def matrix_normalize(X: torch.Tensor, mode: str = "normalize", axis: int = 0, eps: float = -1.0, out: Optional[torch.Tensor] = None):
+    """``dance.utils.matrix.normalize`` on a CUDA fp32 matrix (utils/matrix.py:8-67)."""
+    _chk(X, torch.float32, "X", 2)
+    if mode not in NORM_MODE:
+        raise B2Error(f"matrix_normalize: unknown mode {mode!r}")
+    if not (eps == -1 or eps > 0):
+        raise ValueError(f"Invalid {eps=!r}. Must be positive or -1, the later set zero entries to one.")
+    n, g = X.shape
+    out = torch.empty_like(X) if out is None else out
+    ws = _workspace(lib().b2_matrix_normalize_workspace_bytes(n, g, axis), X.device)
+    check(lib().b2_matrix_normalize_f32(_p(X), _rowmajor(X, "X"), n, g, NORM_MODE[mode], int(axis), float(eps), _p(out),
+                                        _rowmajor(out, "out"), _p(ws), ws.numel(), _stream()), "b2_matrix_normalize_f32")
+    return out
+
+
+def pearson_corr(X: torch.Tensor) -> torch.Tensor:
+    """float32(np.corrcoef(X.T)) for X [n, g] — fp64 arithmetic on the device."""
+    _chk(X, torch.float32, "X", 2)
+    n, g = X.shape
+    adj = torch.empty((g, g), dtype=torch.float32, device=X.device)
+    ws = torch.empty(lib().b2_pearson_corr_workspace_bytes(g), dtype=torch.uint8, device=X.device)
+    check(lib().b2_pearson_corr_f32(_p(X), _rowmajor(X, "X"), n, g, _p(adj), g, _p(ws), ws.numel(), _stream()), "b2_pearson_corr_f32")
+    return adj
+
+
+def threshold_graph(adj: torch.Tensor, threshold: float, positive_only: bool = False, normalize_edges: bool = True):
+    """Edges of a dense score matrix after thresholding: (src int32, dst int32, w fp32), row-major order."""
+    _chk(adj, torch.float32, "adj", 2)
+    g = adj.shape[0]
+    ws = torch.empty(lib().b2_threshold_graph_workspace_bytes(g), dtype=torch.uint8, device=adj.device)   # survives count → fill
+    rowptr = torch.empty(g + 1, dtype=torch.int32, device=adj.device)
+    nnz = C.c_int64(0)
+    check(lib().b2_threshold_graph_count(_p(adj), _rowmajor(adj, "adj"), g, float(threshold), int(positive_only), _p(rowptr),
+                                         C.addressof(nnz), _p(ws), ws.numel(), _stream()), "b2_threshold_graph_count")
+    E = nnz.value
+    src = torch.empty(max(E, 1), dtype=torch.int32, device=adj.device)[:E]
+    dst = torch.empty(max(E, 1), dtype=torch.int32, device=adj.device)[:E]
+    w = torch.empty(max(E, 1), dtype=torch.float32, device=adj.device)[:E]
+    if E:
+        check(lib().b2_threshold_graph_fill(_p(adj), _rowmajor(adj, "adj"), g, float(threshold), int(positive_only), _p(rowptr),
+                                            int(normalize_edges), _p(src), _p(dst), _p(w), _p(ws), ws.numel(), _stream()),
+              "b2_threshold_graph_fill")
+    return src, dst, w, rowptr

@@ -153,3 +153,33 @@ class StagateGraph(BaseTransform):
         adj = sp.csr_matrix((np.ones(len(indices), dtype=np.float64), indices, indptr), shape=(n, n))
         data.data.obsp[self.out] = adj
         return data
+
+
+class FeatureFeatureGraph(BaseTransform):
+    """Gene–gene similarity graph (feature_feature_graph.py:14-87): Pearson correlation of the gene columns, entries
+    with |r| below ``threshold`` dropped, edges in row-major order, unit weights optionally normalised like
+    ``dgl.nn.EdgeWeightNorm("both")``.  Result: ``uns[out]`` = graph with ``ndata["feat"] = Xᵀ`` and ``edata["weight"]``.
+    ``score_func`` "spearman" / "rbf" are not built."""
+
+    _DISPLAY_ATTRS = ("threshold", "positive_only", "normalize_edges", "score_func", "score_func_kwargs")
+
+    def __init__(self, threshold: float = 0.3, *, positive_only: bool = False, normalize_edges: bool = True, score_func="pearson",
+                 score_func_kwargs=None, **kwargs):
+        super().__init__(**kwargs)
+        self.threshold, self.positive_only, self.normalize_edges = threshold, positive_only, normalize_edges
+        self.score_func, self.score_func_kwargs = score_func, score_func_kwargs or {}
+
+    def __call__(self, data):
+        feat = data.get_feature(return_type="numpy")
+        if self.score_func != "pearson":
+            if self.score_func in ("spearman", "rbf"):
+                raise NotImplementedError(f"score_func={self.score_func!r} is not built (pearson is the GraphSCI default)")
+            raise ValueError(f"Unknown similarity score function {self.score_func!r}, supported options are: 'pearson', 'spearman', 'rbf'")
+        X = torch.as_tensor(np.ascontiguousarray(feat, dtype=np.float32)).cuda()
+        adj = ops.pearson_corr(X)
+        src, dst, w, _ = ops.threshold_graph(adj, self.threshold, self.positive_only, self.normalize_edges)
+        g = GraphLite(src.cpu(), dst.cpu(), adj.shape[0])
+        g.ndata["feat"] = torch.from_numpy(np.ascontiguousarray(feat.astype(np.float32).T))
+        g.edata["weight"] = w.cpu()
+        data.data.uns[self.out] = g
+        return data

@@ -282,6 +282,36 @@ int b2_gat_combine_bwd_f32(const float* dout, int64_t lddo, const float* out, in
                            float* dpre, int64_t ldp, float* dact, int64_t ldact, void* stream);
 
 /* ------------------------------------------------------------------------
+ * dance.utils.matrix.normalize (utils/matrix.py:8-67), out-of-place, along axis 0 (columns) or 1 (rows):
+ *   mode 0 "normalize" x/Σx, 1 "standardize" (x-mean)/std (population), 2 "minmax", 3 "l2" x/sqrt(Σx²)
+ *   eps == -1: zero denominators → 1 ; eps > 0: denominator + eps ; anything else is an error (:61).
+ * Statistics are accumulated in fp64.  out may alias X.
+ * ---------------------------------------------------------------------- */
+size_t b2_matrix_normalize_workspace_bytes(int32_t n_rows, int32_t n_cols, int axis);
+int b2_matrix_normalize_f32(const float* X, int64_t ldx, int32_t n_rows, int32_t n_cols, int mode, int axis, float eps,
+                            float* out, int64_t ldo, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * FeatureFeatureGraph (transforms/graph/feature_feature_graph.py:45-87)
+ *   b2_pearson_corr_f32      : adj [g,g] fp32 = float32(np.corrcoef(X.T)) for X [n cells, g genes]; fp64 arithmetic
+ *                              (:49), zero-variance genes give NaN rows/columns exactly as numpy does.
+ *   b2_threshold_graph_count : keeps entries with NOT(-thr < a < thr) (and a >= 0 if positive_only) that are nonzero
+ *                              (:62-69; NaN is kept); writes rowptr [g+1], returns nnz (synchronises).
+ *   b2_threshold_graph_fill  : COO edges in row-major order (int32 src/dst, :68-69) and weights: 1, or with
+ *                              normalize_edges dgl EdgeWeightNorm("both") = outdeg(src)^-1/2 · indeg(dst)^-1/2 (:75-78).
+ *                              Must be given the workspace `count` filled.
+ * ---------------------------------------------------------------------- */
+size_t b2_pearson_corr_workspace_bytes(int32_t g);
+int b2_pearson_corr_f32(const float* X, int64_t ldx, int32_t n, int32_t g, float* adj, int64_t lda,
+                        void* workspace, size_t workspace_bytes, void* stream);
+size_t b2_threshold_graph_workspace_bytes(int32_t g);
+int b2_threshold_graph_count(const float* adj, int64_t lda, int32_t g, float threshold, int positive_only,
+                             int32_t* rowptr, int64_t* nnz_host, void* workspace, size_t workspace_bytes, void* stream);
+int b2_threshold_graph_fill(const float* adj, int64_t lda, int32_t g, float threshold, int positive_only,
+                            const int32_t* rowptr, int normalize_edges, int32_t* src, int32_t* dst, float* w,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
  * Radius graph over spot coordinates — StagateGraph(model_name="radius"):
  * NearestNeighbors(radius=r).fit(X).radius_neighbors_graph(X) (transforms/graph/spatial_graph.py:143-151).
  *   X [n, d] fp64 (1 <= d <= 4), A_ij = 1 iff Σ_c (x_ic - x_jc)² <= r² in fp64 (sklearn's reduced-distance test), self

@@ -464,6 +464,25 @@ def spagcn_fit(X, adj, W, b, init_y, lr, epochs, update_interval=3, weight_decay
     return W.detach().numpy(), b.detach().numpy(), mu_t.detach().numpy(), done
 
 
+def feature_feature_graph(feat: np.ndarray, threshold: float = 0.3, positive_only: bool = False, normalize_edges: bool = True):
+    """FeatureFeatureGraph with the pearson score (feature_feature_graph.py:45-87); dgl.graph + EdgeWeightNorm("both")
+    restated (dgl 1.1.3, un-vendored): weight_e = outdeg_w(src)^-0.5 · indeg_w(dst)^-0.5 · w_e on unit weights.
+    Returns (src int32, dst int32, w fp32, adj fp32 after thresholding)."""
+    adj = np.corrcoef(feat.T).astype(np.float32)
+    adj[np.logical_and(adj > -threshold, adj < threshold)] = 0
+    if positive_only:
+        adj[adj < 0] = 0
+    coo = sp.coo_matrix(adj)
+    src, dst = coo.row.astype(np.int32), coo.col.astype(np.int32)
+    w = torch.ones(len(src), dtype=torch.float32)
+    if normalize_edges:
+        g = adj.shape[0]
+        out_deg = torch.zeros(g).index_add_(0, torch.from_numpy(src).long(), w)
+        in_deg = torch.zeros(g).index_add_(0, torch.from_numpy(dst).long(), w)
+        w = torch.pow(out_deg, -0.5)[torch.from_numpy(src).long()] * torch.pow(in_deg, -0.5)[torch.from_numpy(dst).long()] * w
+    return src, dst, w.numpy(), adj
+
+
 def synthetic_embedding(n: int, d: int = 128, n_clusters: int = 10, seed: int = 0) -> np.ndarray:
     """Z[N,d]: mixture of `n_clusters` unit-variance Gaussians, centres ~ N(0, 3²)."""
     rng = np.random.default_rng(seed)
