@@ -71,6 +71,10 @@ _SIGNATURES = {
     "b2_threshold_graph_workspace_bytes": (c_sz, [c_i32]),
     "b2_threshold_graph_count": (C.c_int, [c_vp, c_i64, c_i32, c_f32, C.c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "b2_threshold_graph_fill": (C.c_int, [c_vp, c_i64, c_i32, c_f32, C.c_int, c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "b2_umap_fuzzy_knn_f32": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "b2_fuzzy_union_workspace_bytes": (c_sz, [c_i32]),
+    "b2_fuzzy_union_count": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "b2_fuzzy_union_fill": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "b2_clip_grad_norm_f32": (C.c_int, [c_vp, c_i64, c_f32, c_f32, c_vp, c_vp, c_vp]),
     "b2_radius_graph_workspace_bytes": (c_sz, [c_i32]),
     "b2_radius_graph_count": (C.c_int, [c_vp, c_i64, c_i32, c_i32, C.c_double, c_vp, c_vp, c_vp, c_sz, c_vp]),

@@ -135,7 +135,7 @@ def device_info() -> Tuple[int, int, int]:
 class CSR:
     """Device CSR matrix: int32 rowptr/colidx, optional fp32 values (None = all ones)."""
 
-    __slots__ = ("rowptr", "colidx", "vals", "shape", "_t")
+    __slots__ = ("rowptr", "colidx", "vals", "shape", "_t", "sigmas", "rhos")
 
     def __init__(self, rowptr, colidx, vals, shape):
         _chk(rowptr, torch.int32, "rowptr", 1)
@@ -692,3 +692,35 @@ def threshold_graph(adj: torch.Tensor, threshold: float, positive_only: bool = F
                                             int(normalize_edges), _p(src), _p(dst), _p(w), _p(ws), ws.numel(), _stream()),
               "b2_threshold_graph_fill")
     return src, dst, w, rowptr
+
+
+def umap_connectivities(knn_idx: torch.Tensor, knn_dist: torch.Tensor) -> "CSR":
+    """scanpy/umap fuzzy-simplicial-set connectivities from a kNN table whose column 0 is the cell itself."""
+    _chk(knn_idx, torch.int32, "knn_idx", 2)
+    _chk(knn_dist, torch.float32, "knn_dist", 2)
+    n, k = knn_idx.shape
+    dev = knn_idx.device
+    vals = torch.empty((n, k), dtype=torch.float32, device=dev)
+    sig = torch.empty(n, dtype=torch.float32, device=dev)
+    rho = torch.empty(n, dtype=torch.float32, device=dev)
+    acc = torch.empty(1, dtype=torch.float64, device=dev)
+    check(lib().b2_umap_fuzzy_knn_f32(_p(knn_idx), _p(knn_dist), n, k, _p(vals), _p(sig), _p(rho), _p(acc), _stream()),
+          "b2_umap_fuzzy_knn_f32")
+    rowptr = torch.arange(0, n * k + 1, k, dtype=torch.int32, device=dev)
+    A0 = CSR(rowptr, knn_idx.reshape(-1).contiguous(), vals.reshape(-1), (n, n))
+    T, _ = csr_transpose(A0)          # Aᵀ, ascending columns
+    A, _ = csr_transpose(T)           # A again, now with ascending columns too
+    ws = torch.empty(lib().b2_fuzzy_union_workspace_bytes(n), dtype=torch.uint8, device=dev)
+    rp = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    nnz = C.c_int64(0)
+    check(lib().b2_fuzzy_union_count(_p(A.rowptr), _p(A.colidx), _p(A.vals), _p(T.rowptr), _p(T.colidx), _p(T.vals), n, _p(rp),
+                                     C.addressof(nnz), _p(ws), ws.numel(), _stream()), "b2_fuzzy_union_count")
+    E = nnz.value
+    ci = torch.empty(max(E, 1), dtype=torch.int32, device=dev)[:E]
+    cv = torch.empty(max(E, 1), dtype=torch.float32, device=dev)[:E]
+    if E:
+        check(lib().b2_fuzzy_union_fill(_p(A.rowptr), _p(A.colidx), _p(A.vals), _p(T.rowptr), _p(T.colidx), _p(T.vals), n, _p(rp),
+                                        _p(ci), _p(cv), _stream()), "b2_fuzzy_union_fill")
+    out = CSR(rp, ci, cv, (n, n))
+    out.sigmas, out.rhos = sig, rho
+    return out

@@ -5,4 +5,4 @@ from .normalize import Log1P, NormalizeTotal, NormalizeTotalLog1P  # noqa: F401
 from . import pp  # noqa: F401
 from .cell_feature import CellPCA, WeightedFeaturePCA  # noqa: F401
 from .filter import FilterGenesMatch  # noqa: F401
-from .graph import FeatureFeatureGraph, CellFeatureGraph, PCACellFeatureGraph, SpaGCNGraph, SpaGCNGraph2D, StagateGraph  # noqa: F401
+from .graph import FeatureFeatureGraph, NeighborGraph, CellFeatureGraph, PCACellFeatureGraph, SpaGCNGraph, SpaGCNGraph2D, StagateGraph  # noqa: F401

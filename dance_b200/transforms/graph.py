@@ -183,3 +183,32 @@ class FeatureFeatureGraph(BaseTransform):
         g.edata["weight"] = w.cpu()
         data.data.uns[self.out] = g
         return data
+
+
+class NeighborGraph(BaseTransform):
+    """kNN connectivity graph of the cells (neighbor_graph.py:9-57): ``scanpy.pp.neighbors(use_rep=channel, n_neighbors,
+    method="umap", metric="euclidean")`` → ``obsp[out]`` = the symmetric fuzzy-simplicial-set connectivities (scipy CSR,
+    fp32).  The neighbour search is the exact device kNN at every size (scanpy switches to approximate pynndescent above
+    4096 cells; the exact graph is what that approximates)."""
+
+    _DISPLAY_ATTRS = ("n_neighbors", "n_pcs", "knn", "random_state", "method", "metric")
+
+    def __init__(self, n_neighbors: int = 15, *, n_pcs: Optional[int] = None, knn: bool = True, random_state: int = 0,
+                 method: Optional[str] = "umap", metric: str = "euclidean", channel: Optional[str] = "CellPCA", **kwargs):
+        super().__init__(**kwargs)
+        self.n_neighbors, self.n_pcs, self.knn, self.random_state = n_neighbors, n_pcs, knn, random_state
+        self.method, self.metric, self.channel = method, metric, channel
+
+    def __call__(self, data):
+        if self.method != "umap" or self.metric != "euclidean" or not self.knn:
+            raise NotImplementedError("only method='umap', metric='euclidean', knn=True (the defaults) are built")
+        rep = data.get_feature(return_type="numpy", channel=self.channel, channel_type="obsm" if self.channel else "X")
+        if self.n_pcs is not None:
+            rep = rep[:, :self.n_pcs]
+        X = torch.as_tensor(np.ascontiguousarray(rep, dtype=np.float32)).cuda()
+        idx, dist = ops.knn(X, int(self.n_neighbors), include_rank0=True)
+        Cn = ops.umap_connectivities(idx, dist.float())
+        n = X.shape[0]
+        adj = sp.csr_matrix((Cn.vals.cpu().numpy(), Cn.colidx.cpu().numpy(), Cn.rowptr.cpu().numpy()), shape=(n, n))
+        data.data.obsp[self.out] = adj
+        return data

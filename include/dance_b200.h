@@ -282,6 +282,24 @@ int b2_gat_combine_bwd_f32(const float* dout, int64_t lddo, const float* out, in
                            float* dpre, int64_t ldp, float* dact, int64_t ldact, void* stream);
 
 /* ------------------------------------------------------------------------
+ * NeighborGraph connectivities (transforms/graph/neighbor_graph.py:50-57 → scanpy.pp.neighbors(method="umap") →
+ * umap fuzzy_simplicial_set; third-party algorithm restated, see csrc/umap.cu)
+ *   b2_umap_fuzzy_knn_f32 : knn_idx/knn_dist [n,k] (column 0 = the cell itself, ascending distances, 2 <= k <= 64)
+ *                           → membership strengths vals [n,k], sigmas [n], rhos [n]; sum_ws = one device double.
+ *   b2_fuzzy_union_*      : C = A + Aᵀ - A∘Aᵀ from A and Aᵀ in CSR with ascending columns (b2_csr_transpose gives both),
+ *                           zeros dropped; `count` writes rowptr_out and returns nnz (synchronises), `fill` the rest.
+ * ---------------------------------------------------------------------- */
+int b2_umap_fuzzy_knn_f32(const int32_t* knn_idx, const float* knn_dist, int32_t n, int32_t k, float* vals,
+                          float* sigmas, float* rhos, double* sum_ws, void* stream);
+size_t b2_fuzzy_union_workspace_bytes(int32_t n);
+int b2_fuzzy_union_count(const int32_t* rowptr_a, const int32_t* colidx_a, const float* vals_a,
+                         const int32_t* rowptr_t, const int32_t* colidx_t, const float* vals_t, int32_t n,
+                         int32_t* rowptr_out, int64_t* nnz_host, void* workspace, size_t workspace_bytes, void* stream);
+int b2_fuzzy_union_fill(const int32_t* rowptr_a, const int32_t* colidx_a, const float* vals_a,
+                        const int32_t* rowptr_t, const int32_t* colidx_t, const float* vals_t, int32_t n,
+                        const int32_t* rowptr_out, int32_t* colidx_out, float* vals_out, void* stream);
+
+/* ------------------------------------------------------------------------
  * dance.utils.matrix.normalize (utils/matrix.py:8-67), out-of-place, along axis 0 (columns) or 1 (rows):
  *   mode 0 "normalize" x/Σx, 1 "standardize" (x-mean)/std (population), 2 "minmax", 3 "l2" x/sqrt(Σx²)
  *   eps == -1: zero denominators → 1 ; eps > 0: denominator + eps ; anything else is an error (:61).

@@ -483,6 +483,65 @@ def feature_feature_graph(feat: np.ndarray, threshold: float = 0.3, positive_onl
     return src, dst, w.numpy(), adj
 
 
+def umap_connectivities(knn_idx: np.ndarray, knn_dist: np.ndarray) -> sp.csr_matrix:
+    """scanpy 1.10.1 ``_connectivity.umap`` → umap-learn 0.5 ``fuzzy_simplicial_set(set_op_mix_ratio=1,
+    local_connectivity=1)`` restated loop by loop (smooth_knn_dist, compute_membership_strengths, fuzzy union);
+    both packages are un-vendored third-party dependencies of the reference (requirements.txt:19) — parity unpinned."""
+    n, k = knn_idx.shape
+    dist = knn_dist.astype(np.float32)
+    target = np.log2(k)
+    rho = np.zeros(n, np.float32)
+    sig = np.zeros(n, np.float32)
+    mean_all = np.float32(dist.mean())
+    for i in range(n):
+        lo, hi, mid = 0.0, np.inf, 1.0
+        nz = dist[i][dist[i] > 0.0]
+        if nz.shape[0] >= 1:
+            rho[i] = nz[0]
+        elif nz.shape[0] > 0:
+            rho[i] = nz.max()
+        for _ in range(64):
+            psum = 0.0
+            for j in range(1, k):
+                d = np.float32(dist[i, j] - rho[i])
+                psum += np.exp(-(float(d) / mid)) if d > 0 else 1.0
+            if abs(psum - target) < 1e-5:
+                break
+            if psum > target:
+                hi = mid
+                mid = (lo + hi) / 2.0
+            else:
+                lo = mid
+                mid = mid * 2 if hi == np.inf else (lo + hi) / 2.0
+        sig[i] = mid
+        if rho[i] > 0.0:
+            m = np.float32(dist[i].mean())
+            if sig[i] < 1e-3 * m:
+                sig[i] = 1e-3 * m
+        elif sig[i] < 1e-3 * mean_all:
+            sig[i] = 1e-3 * mean_all
+    rows = np.repeat(np.arange(n), k)
+    cols = knn_idx.reshape(-1)
+    vals = np.zeros(n * k, np.float32)
+    for i in range(n):
+        for j in range(k):
+            if knn_idx[i, j] == i:
+                v = 0.0
+            elif dist[i, j] - rho[i] <= 0.0 or sig[i] == 0.0:
+                v = 1.0
+            else:
+                v = np.exp(-((dist[i, j] - rho[i]) / sig[i]))
+            vals[i * k + j] = v
+    res = sp.coo_matrix((vals, (rows, cols)), shape=(n, n))
+    res.eliminate_zeros()
+    tr = res.transpose()
+    prod = res.multiply(tr)
+    res = (res + tr - prod).tocsr()
+    res.eliminate_zeros()
+    res.sort_indices()
+    return res
+
+
 def synthetic_embedding(n: int, d: int = 128, n_clusters: int = 10, seed: int = 0) -> np.ndarray:
     """Z[N,d]: mixture of `n_clusters` unit-variance Gaussians, centres ~ N(0, 3²)."""
     rng = np.random.default_rng(seed)
