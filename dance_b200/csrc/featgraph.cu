@@ -35,9 +35,14 @@ fg_colsum_kernel(const float* __restrict__ X, int64_t ldx, int32_t n, int32_t g,
   }
 }
 
+// mean = sum / n by DIVISION, as np.average does: a constant gene must centre to exact zeros (→ NaN correlations)
+__global__ void fg_mean_kernel(double* __restrict__ sum, int32_t g, int32_t n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g; i += gridDim.x * blockDim.x) sum[i] = sum[i] / (double)n;
+}
+
 // C[i,j] += Σ_r (X[r,i]-m_i)(X[r,j]-m_j) over this block's slice of cells; upper-triangular tiles only (bi <= bj)
 __global__ void __launch_bounds__(256)
-fg_gram_kernel(const float* __restrict__ X, int64_t ldx, int32_t n, int32_t g, const double* __restrict__ sum,
+fg_gram_kernel(const float* __restrict__ X, int64_t ldx, int32_t n, int32_t g, const double* __restrict__ mean,
                double* __restrict__ Cm) {
   const int bi = blockIdx.y, bj = blockIdx.x;
   if (bi > bj) return;
@@ -51,15 +56,14 @@ fg_gram_kernel(const float* __restrict__ X, int64_t ldx, int32_t n, int32_t g, c
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-  const double inv_n = 1.0 / (double)n;
   for (int64_t rb = r0; rb < r1; rb += FG_K) {
     // stage FG_K cells × 64 genes for both tile sides, centred in fp64
     for (int t = threadIdx.x; t < FG_K * FG_T; t += 256) {
       const int kk = t / FG_T, cc = t % FG_T;
       const int64_t r = rb + kk;
       const int ci = bi * FG_T + cc, cj = bj * FG_T + cc;
-      sa[kk][cc] = (r < r1 && ci < g) ? (double)X[r * ldx + ci] - sum[ci] * inv_n : 0.0;
-      sb[kk][cc] = (r < r1 && cj < g) ? (double)X[r * ldx + cj] - sum[cj] * inv_n : 0.0;
+      sa[kk][cc] = (r < r1 && ci < g) ? (double)X[r * ldx + ci] - mean[ci] : 0.0;
+      sb[kk][cc] = (r < r1 && cj < g) ? (double)X[r * ldx + cj] - mean[cj] : 0.0;
     }
     __syncthreads();
 #pragma unroll
@@ -175,6 +179,8 @@ extern "C" int b2_pearson_corr_f32(const float* X, int64_t ldx, int32_t n, int32
     dim3 grid(col_tiles, splits < 1 ? 1 : splits);
     fg_colsum_kernel<<<grid, 256, 0, st>>>(X, ldx, n, g, sum);
     B2_CHECK_LAUNCH("fg_colsum_kernel");
+    fg_mean_kernel<<<ceil_div(g, 256), 256, 0, st>>>(sum, g, n);
+    B2_CHECK_LAUNCH("fg_mean_kernel");
   }
   const int tiles = ceil_div(g, FG_T);
   const int tri = tiles * (tiles + 1) / 2;

@@ -31,12 +31,13 @@ def test_matrix_normalize_reference_known_answers(cuda):
     """The golden vectors of the reference's tests/utils/test_matrix.py:10-29."""
     from dance_b200 import matrix
     mat = np.array([[1, 1], [4, 4]], dtype=np.float32)
-    assert matrix.normalize(mat, mode="normalize", axis=0).tolist() == [[0.2, 0.2], [0.8, 0.8]]
-    assert matrix.normalize(mat, mode="normalize", axis=1).tolist() == [[0.5, 0.5], [0.5, 0.5]]
-    assert matrix.normalize(mat, mode="standardize", axis=0).tolist() == [[-1, -1], [1, 1]]
-    assert matrix.normalize(mat, mode="standardize", axis=1).tolist() == [[0, 0], [0, 0]]
-    assert matrix.normalize(mat, mode="minmax", axis=0).tolist() == [[0, 0], [1, 1]]
-    assert matrix.normalize(mat, mode="minmax", axis=1).tolist() == [[0, 0], [0, 0]]
+    f32 = lambda v: np.array(v, dtype=np.float32)       # the reference's vectors, rounded to the fp32 the kernels work in
+    assert np.array_equal(matrix.normalize(mat, mode="normalize", axis=0), f32([[0.2, 0.2], [0.8, 0.8]]))
+    assert np.array_equal(matrix.normalize(mat, mode="normalize", axis=1), f32([[0.5, 0.5], [0.5, 0.5]]))
+    assert np.array_equal(matrix.normalize(mat, mode="standardize", axis=0), f32([[-1, -1], [1, 1]]))
+    assert np.array_equal(matrix.normalize(mat, mode="standardize", axis=1), f32([[0, 0], [0, 0]]))
+    assert np.array_equal(matrix.normalize(mat, mode="minmax", axis=0), f32([[0, 0], [1, 1]]))
+    assert np.array_equal(matrix.normalize(mat, mode="minmax", axis=1), f32([[0, 0], [0, 0]]))
     assert np.allclose(matrix.normalize(mat, mode="l2", axis=0), mat / np.sqrt(17.0), rtol=1e-6)
     with pytest.raises(ValueError):
         matrix.normalize(mat, mode="normalize", eps=0.0)
