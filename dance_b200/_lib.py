@@ -75,6 +75,16 @@ _SIGNATURES = {
     "b2_fuzzy_union_workspace_bytes": (c_sz, [c_i32]),
     "b2_fuzzy_union_count": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "b2_fuzzy_union_fill": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "b2_batchnorm_workspace_bytes": (c_sz, [c_i32]),
+    "b2_batchnorm_fwd_f32": (C.c_int, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, C.c_int, c_f32, c_f32, C.c_int, c_vp, c_i64,
+                                       c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "b2_batchnorm_bwd_f32": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp,
+                                       c_i64, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "b2_zinb_loss_grad_f32": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_i32, c_f32, c_f32, c_vp, c_vp,
+                                        c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "b2_adj_sample_f32": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "b2_adj_loss_grad_f32": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_f32, c_vp, c_vp, c_vp]),
+    "b2_adj_reparam_bwd_f32": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_vp, c_vp, c_vp]),
     "b2_clip_grad_norm_f32": (C.c_int, [c_vp, c_i64, c_f32, c_f32, c_vp, c_vp, c_vp]),
     "b2_radius_graph_workspace_bytes": (c_sz, [c_i32]),
     "b2_radius_graph_count": (C.c_int, [c_vp, c_i64, c_i32, c_i32, C.c_double, c_vp, c_vp, c_vp, c_sz, c_vp]),

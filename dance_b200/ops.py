@@ -724,3 +724,74 @@ def umap_connectivities(knn_idx: torch.Tensor, knn_dist: torch.Tensor) -> "CSR":
     out = CSR(rp, ci, cv, (n, n))
     out.sigmas, out.rhos = sig, rho
     return out
+
+
+# ----------------------------------------------------------------------------- GraphSCI path
+def batchnorm_fwd(X, gamma, beta, running_mean, running_var, training: bool, momentum: float = 0.1, eps: float = 1e-5,
+                  act: Optional[str] = None):
+    """nn.BatchNorm1d (+ optional fused ReLU); returns (out, save_mean, save_invstd)."""
+    _chk(X, torch.float32, "X", 2)
+    n, c = X.shape
+    out = torch.empty_like(X)
+    sm = torch.empty(c, dtype=torch.float32, device=X.device)
+    si = torch.empty(c, dtype=torch.float32, device=X.device)
+    ws = _workspace(lib().b2_batchnorm_workspace_bytes(c), X.device)
+    check(lib().b2_batchnorm_fwd_f32(_p(X), _rowmajor(X, "X"), n, c, _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+                                     int(training), momentum, eps, ACT[act], _p(out), _rowmajor(out, "out"), _p(sm), _p(si), _p(ws),
+                                     ws.numel(), _stream()), "b2_batchnorm_fwd_f32")
+    return out, sm, si
+
+
+def batchnorm_bwd(dY, Y, X, gamma, save_mean, save_invstd, act: Optional[str] = None, training: bool = True, dgamma=None, dbeta=None):
+    """Returns (dX, dgamma, dbeta); ``Y`` (the forward output) is only read for the fused ReLU."""
+    n, c = X.shape
+    dX = torch.empty_like(X)
+    dgamma = torch.empty(c, dtype=torch.float32, device=X.device) if dgamma is None else dgamma
+    dbeta = torch.empty(c, dtype=torch.float32, device=X.device) if dbeta is None else dbeta
+    ws = _workspace(lib().b2_batchnorm_workspace_bytes(c), X.device)
+    check(lib().b2_batchnorm_bwd_f32(_p(dY), _rowmajor(dY, "dY"), _p(Y), _rowmajor(Y, "Y") if Y is not None else 0, _p(X),
+                                     _rowmajor(X, "X"), n, c, _p(gamma), _p(save_mean), _p(save_invstd), ACT[act], int(training), _p(dX),
+                                     _rowmajor(dX, "dX"), _p(dgamma), _p(dbeta), _p(ws), ws.numel(), _stream()), "b2_batchnorm_bwd_f32")
+    return dX, dgamma, dbeta
+
+
+def zinb_loss_grad(a_pi, b_disp, c_mean, Y, size_factors, mask=None, le: float = 1.0, ke: float = 1.0, want_grad: bool = True,
+                   want_outputs: bool = False):
+    """Returns (acc3 fp64 {Σnll, Σmse, count}, (d_a, d_b, d_c) | None, (mean, disp, pi) | None)."""
+    n, g = a_pi.shape
+    dev = a_pi.device
+    acc = torch.empty(3, dtype=torch.float64, device=dev)
+    grads = tuple(torch.empty_like(a_pi) for _ in range(3)) if want_grad else (None, None, None)
+    outs = tuple(torch.empty_like(a_pi) for _ in range(3)) if want_outputs else (None, None, None)
+    if mask is not None:
+        if mask.dtype == torch.bool:
+            mask = mask.view(torch.uint8)
+        _chk(mask, torch.uint8, "mask", 2)
+    check(lib().b2_zinb_loss_grad_f32(_p(a_pi), _p(b_disp), _p(c_mean), _rowmajor(a_pi, "a_pi"), _p(Y), _rowmajor(Y, "Y"),
+                                      _p(size_factors), _p(mask), mask.stride(0) if mask is not None else 0, n, g, le, ke, _p(grads[0]),
+                                      _p(grads[1]), _p(grads[2]), g, _p(outs[0]), _p(outs[1]), _p(outs[2]), g, _p(acc), _stream()),
+          "b2_zinb_loss_grad_f32")
+    return acc, (grads if want_grad else None), (outs if want_outputs else None)
+
+
+def adj_sample(mu, log_std, eps):
+    z = torch.empty_like(mu)
+    check(lib().b2_adj_sample_f32(_p(mu), _p(log_std), _p(eps), mu.numel(), _p(z), _stream()), "b2_adj_sample_f32")
+    return z
+
+
+def adj_loss_grad(z, mu, log_std, target, class_weight, coef_ce: float = 0.0, want_grad: bool = True):
+    """Returns (acc2 fp64 {Σ CE, Σ KL terms}, dz | None) for the [g, g] adjacency logits."""
+    g = z.shape[0]
+    acc = torch.empty(2, dtype=torch.float64, device=z.device)
+    dz = torch.empty_like(z) if want_grad else None
+    check(lib().b2_adj_loss_grad_f32(_p(z), _p(mu), _p(log_std), _p(target), _p(class_weight), g, coef_ce, _p(dz), _p(acc), _stream()),
+          "b2_adj_loss_grad_f32")
+    return acc, dz
+
+
+def adj_reparam_bwd(dz, mu, log_std, eps, coef_kl: float):
+    dmu, dls = torch.empty_like(mu), torch.empty_like(mu)
+    check(lib().b2_adj_reparam_bwd_f32(_p(dz), _p(mu), _p(log_std), _p(eps), mu.numel(), coef_kl, _p(dmu), _p(dls), _stream()),
+          "b2_adj_reparam_bwd_f32")
+    return dmu, dls

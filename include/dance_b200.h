@@ -400,6 +400,40 @@ int b2_sgd_momentum_step_f32(float* param, const float* grad, float* momentum_bu
                              float weight_decay, int32_t step, void* stream);
 int b2_exp_adj_f32(const float* D, float* out, int64_t n_elem, double l, double* sum_out_dev, void* stream);
 
+/* ------------------------------------------------------------------------
+ * GraphSCI (modules/single_modality/imputation/graphsci.py)
+ *   b2_batchnorm_fwd/bwd_f32 : nn.BatchNorm1d over the rows of X [n, c] inside buildNetwork (:37-45); training → batch
+ *       statistics (biased variance to normalise, running stats updated with momentum and the unbiased variance),
+ *       eval → running statistics.  `act` 0 | 1 (ReLU) is fused after the affine transform.  save_mean / save_invstd [c]
+ *       feed the backward.  Workspace: b2_batchnorm_workspace_bytes(c).
+ *   b2_zinb_loss_grad_f32    : the three decoder heads' activations (Sigmoid :107, DispActivation :48-54, MeanActivation
+ *       :57-63) + ZINB negative log-likelihood + reconstruction MSE over the masked entries (get_loss :463-483):
+ *       acc3 = {Σ nll, Σ (mean·sf − y)², #masked}; with d_a/d_b/d_c the gradients of
+ *       le·nll_mean + ke·(0.5/g)·mse_mean w.r.t. the three pre-activations.  mask: bytes [n, g] or NULL (all).
+ *   b2_adj_sample_f32        : z = μ + exp(log_std)·ε  (torch.normal(mean, exp(log_std)) :130 with explicit noise)
+ *   b2_adj_loss_grad_f32     : acc2 = {Σ_i −Σ_c w_c t_ic log_softmax(z_i)_c, Σ (1 + 2ls − μ² − e^{2ls})} (F.cross_entropy with
+ *       probability targets and class weights :461, kl_adj :479-480); dz = coef_ce·∂CE_sum/∂z (optional).
+ *   b2_adj_reparam_bwd_f32   : dμ = dz − 2·coef_kl·μ ; dlog_std = dz·ε·e^{ls} + coef_kl·(2 − 2e^{2ls}).
+ * ---------------------------------------------------------------------- */
+size_t b2_batchnorm_workspace_bytes(int32_t c);
+int b2_batchnorm_fwd_f32(const float* X, int64_t ldx, int32_t n, int32_t c, const float* gamma, const float* beta,
+                         float* running_mean, float* running_var, int training, float momentum, float eps, int act,
+                         float* out, int64_t ldo, float* save_mean, float* save_invstd,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int b2_batchnorm_bwd_f32(const float* dY, int64_t lddy, const float* Y, int64_t ldy, const float* X, int64_t ldx,
+                         int32_t n, int32_t c, const float* gamma, const float* save_mean, const float* save_invstd,
+                         int act, int training, float* dX, int64_t lddx, float* dgamma, float* dbeta,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int b2_zinb_loss_grad_f32(const float* a_pi, const float* b_disp, const float* c_mean, int64_t ld,
+                          const float* Y, int64_t ldy, const float* size_factors, const uint8_t* mask, int64_t ldm,
+                          int32_t n, int32_t g, float le, float ke, float* d_a, float* d_b, float* d_c, int64_t ldd,
+                          float* mean_out, float* disp_out, float* pi_out, int64_t ldo, double* acc3, void* stream);
+int b2_adj_sample_f32(const float* mu, const float* log_std, const float* eps, int64_t n_elem, float* z, void* stream);
+int b2_adj_loss_grad_f32(const float* z, const float* mu, const float* log_std, const float* target,
+                         const float* class_weight, int32_t g, float coef_ce, float* dz, double* acc2, void* stream);
+int b2_adj_reparam_bwd_f32(const float* dz, const float* mu, const float* log_std, const float* eps, int64_t n_elem,
+                           float coef_kl, float* dmu, float* dlog_std, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -299,15 +299,82 @@ def _stagate_fixture():
     np.savez_compressed(OUT / "stagate.npz", **out)
 
 
+def _graphsci_fixture():
+    """GraphSCI (graphsci.py): the reference's own GNNModel / AEModel / get_loss / fit running on oracle/dgl_lite.py, with
+    dropout = 0 and ``torch.normal`` replaced by mean + std·ε for a recorded ε sequence (train, eval, train, eval, …)."""
+    import contextlib
+    import io
+    import os
+    import tempfile
+    from . import dgl_lite
+    ref = ref_loader.graphsci()
+    rng = np.random.default_rng(23)
+    n, g = 260, 48
+    lat = rng.gamma(2.0, 1.0, size=(n, 5))
+    load = rng.gamma(1.0, 0.6, size=(5, g))
+    X = rng.poisson(lat @ load * rng.lognormal(0, 0.3, size=(n, 1))).astype(np.float32)
+    X[X.sum(1) == 0, 0] = 1
+    Xl = np.log1p(X)
+    src, dst, w, _ = port.feature_feature_graph(Xl, 0.2, False, True)
+    mask = rng.random((n, g)) < 0.9
+    train_idx = np.arange(n)[: int(0.9 * n)]
+    n_eps = 9
+    eps = rng.normal(size=(n_eps, g, g)).astype(np.float32)
+    out = dict(X=X, Xl=Xl, src=src, dst=dst, w=w, mask=mask, train_idx=train_idx, eps=eps)
+
+    def graph():
+        gr = dgl_lite.Graph(src, dst, g)
+        gr.edata["weight"] = torch.tensor(w)
+        gr.ndata["feat"] = torch.tensor(Xl.T.copy())
+        return gr
+
+    def fresh():
+        torch.manual_seed(7)
+        return ref.GraphSCI(num_cells=n, num_genes=g, dataset="fixture", dropout=0.0)
+
+    real_normal = torch.normal
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            m = fresh()
+            for scope, sd in (("aemodel", m.aemodel.state_dict()), ("gnnmodel", m.gnnmodel.state_dict())):
+                for k, v in sd.items():
+                    out[f"init.{scope}.{k}"] = v.numpy().copy()
+            for n_epochs, tag in ((1, "e1"), (4, "e4")):
+                m = fresh()
+                it = iter(eps)
+                torch.normal = lambda mean, std: mean + std * torch.from_numpy(next(it))
+                with contextlib.redirect_stdout(io.StringIO()):
+                    m.fit(torch.tensor(Xl), torch.tensor(X), graph(), mask=mask.copy(), n_epochs=n_epochs, lr=1e-3, weight_decay=1e-5,
+                          train_idx=train_idx)
+                out[f"{tag}.losses"] = np.array([m.loss_adj, m.loss_exp, m.kl, m.train_loss, m.valid_loss], dtype=np.float64)
+                for scope, mod in (("aemodel", m.aemodel), ("gnnmodel", m.gnnmodel)):
+                    for k, v in mod.state_dict().items():
+                        out[f"{tag}.{scope}.{k}"] = v.numpy().copy()
+                    if tag == "e1":
+                        for k, prm in mod.named_parameters():
+                            if prm.grad is not None:
+                                out[f"grad.{scope}.{k}"] = prm.grad.numpy().copy()
+                if tag == "e4":
+                    with torch.no_grad():
+                        pred = m.predict(torch.tensor(Xl), torch.tensor(X), graph(), mask=mask.copy())
+                    out["e4.predict"] = pred.numpy().copy()
+        finally:
+            torch.normal = real_normal
+            os.chdir(cwd)
+    np.savez_compressed(OUT / "graphsci.npz", **out)
+
+
 def main():
     import sys
     OUT.mkdir(parents=True, exist_ok=True)
-    only = [a for a in sys.argv[1:] if a in ("spagcn", "stagate")]
+    only = [a for a in sys.argv[1:] if a in ("spagcn", "stagate", "graphsci")]
     if only:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             for a in only:
-                {"spagcn": _spagcn_fixture, "stagate": _stagate_fixture}[a]()
+                {"spagcn": _spagcn_fixture, "stagate": _stagate_fixture, "graphsci": _graphsci_fixture}[a]()
         return
     ref = ref_loader.scgnn2()
     with warnings.catch_warnings():
@@ -319,6 +386,7 @@ def main():
         _matrix_fixture()
         _spagcn_fixture()
         _stagate_fixture()
+        _graphsci_fixture()
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)
 

@@ -121,3 +121,27 @@ def stagate():
     _stub("dance.transforms", AnnDataTransform=dummy, Compose=dummy, SetConfig=dummy, CellPCA=dummy, FilterGenesMatch=dummy)
     _stub("dance.transforms.graph", StagateGraph=dummy, SpaGCNGraph=dummy, SpaGCNGraph2D=dummy)
     return _load("dance_ref_stagate", "dance/modules/spatial/spatial_domain/stagate.py")
+
+
+def graphsci():
+    """The reference's ``dance/modules/single_modality/imputation/graphsci.py`` (AEModel, GNNModel, GraphSCI.get_loss /
+    train / evaluate) on top of ``oracle/dgl_lite.py``'s GraphConv; scanpy / dance.transforms / dance.modules.base stubbed."""
+    if "dance_ref_graphsci" in sys.modules:
+        return sys.modules["dance_ref_graphsci"]
+    _install_stubs()
+    from . import dgl_lite
+    _stub("scanpy", pp=types.SimpleNamespace(log1p=None, normalize_total=None, highly_variable_genes=None), tl=types.SimpleNamespace(),
+          AnnData=object)
+    _stub("dgl", graph=lambda data, num_nodes=None: dgl_lite.Graph(data[0], data[1], num_nodes))
+    _stub("dgl.nn", GraphConv=dgl_lite.GraphConv)
+    _stub("dance.modules")
+    _stub("dance.modules.base", BaseRegressionMethod=type("BaseRegressionMethod", (), {}), BaseClusteringMethod=type("B", (), {}),
+          BasePretrain=type("P", (), {}))
+    dummy = type("Dummy", (), {"__init__": lambda self, *a, **k: None})
+    names = ("AnnDataTransform", "CellwiseMaskData", "Compose", "FilterCellsScanpy", "FilterGenesScanpy", "SaveRaw", "SetConfig",
+             "CellPCA", "FilterGenesMatch")
+    _stub("dance.transforms", **{k: dummy for k in names})
+    _stub("dance.transforms.filter", FilterGenesTopK=dummy)
+    _stub("dance.transforms.graph", FeatureFeatureGraph=dummy, StagateGraph=dummy, SpaGCNGraph=dummy, SpaGCNGraph2D=dummy)
+    _stub("dance.transforms.misc", UpdateRaw=dummy)
+    return _load("dance_ref_graphsci", "dance/modules/single_modality/imputation/graphsci.py")

@@ -1,0 +1,177 @@
+"""GraphSCI path (BASELINE config 3): BatchNorm / ZINB / adjacency-loss kernels against torch autograd, and whole training
+runs against fixtures produced by the REFERENCE's own GraphSCI code on the restated dgl GraphConv (oracle/dgl_lite.py;
+parity unpinned at the dgl boundary), dropout = 0 and an explicit ε sequence."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def _c(a, cuda):
+    return torch.as_tensor(np.ascontiguousarray(a)).to(cuda)
+
+
+@pytest.mark.parametrize("act", [None, "relu"])
+def test_batchnorm_matches_torch(cuda, act):
+    from dance_b200 import ops
+    rng = np.random.default_rng(0)
+    n, c = 777, 70
+    x = torch.tensor(rng.normal(size=(n, c)).astype(np.float32) * 2 + 1, requires_grad=True)
+    bn = torch.nn.BatchNorm1d(c)
+    with torch.no_grad():
+        bn.weight.copy_(torch.tensor(rng.uniform(0.5, 1.5, c).astype(np.float32)))
+        bn.bias.copy_(torch.tensor(rng.normal(size=c).astype(np.float32)))
+    rm, rv = torch.zeros(c, device=cuda), torch.ones(c, device=cuda)
+    y = bn(x)
+    y = torch.relu(y) if act else y
+    up = torch.tensor(rng.normal(size=(n, c)).astype(np.float32))
+    y.backward(up)
+    out, sm, si = ops.batchnorm_fwd(x.detach().to(cuda), bn.weight.detach().to(cuda), bn.bias.detach().to(cuda), rm, rv, True, act=act)
+    assert rel_err(out, y.detach()) < 1e-5
+    assert rel_err(rm, bn.running_mean) < 1e-5 and rel_err(rv, bn.running_var) < 1e-5
+    dX, dg, db = ops.batchnorm_bwd(up.to(cuda), out, x.detach().to(cuda), bn.weight.detach().to(cuda), sm, si, act=act)
+    assert rel_err(dX, x.grad) < TOL and rel_err(dg, bn.weight.grad) < TOL and rel_err(db, bn.bias.grad) < TOL
+    # eval mode: running statistics
+    bn.eval()
+    ye = bn(x.detach())
+    oe, _, _ = ops.batchnorm_fwd(x.detach().to(cuda), bn.weight.detach().to(cuda), bn.bias.detach().to(cuda), rm, rv, False, act=None)
+    assert rel_err(oe, ye.detach()) < 1e-5
+
+
+def _zinb_ref(a, b, c, y, sf, mask, le, ke):
+    """graphsci.py:93-112 activations + get_loss :463-483, torch (autograd)."""
+    pi = torch.sigmoid(a)
+    disp = torch.clamp(F.softplus(b), 1e-4, 1e4)
+    mean = torch.clamp(torch.exp(c), 1e-5, 1e6)
+    z_exp = mean * sf.reshape(-1, 1)
+    eps = 1e-10
+    m = mean * sf.reshape(-1, 1)
+    disp = torch.clamp(disp, max=1e6)
+    t1 = torch.lgamma(disp + eps) + torch.lgamma(y + 1) - torch.lgamma(y + disp + eps)
+    t2 = (disp + y) * torch.log(1.0 + (m / (disp + eps))) + (y * (torch.log(disp + eps) - torch.log(m + eps)))
+    nb = t1 + t2
+    zero_nb = torch.pow(disp / (disp + m + eps), disp)
+    zero_case = -torch.log(pi + ((1 - pi) * zero_nb) + eps)
+    loss = torch.where(torch.lt(y, 1e-8), zero_case, nb)
+    loss_exp = le * torch.mean(loss[mask])
+    kl_exp = 0.5 / y.shape[1] * torch.mean(F.mse_loss(z_exp, y, reduction="none")[mask])
+    return loss_exp, kl_exp, mean, disp, pi
+
+
+def test_zinb_loss_and_gradients_match_autograd(cuda):
+    from dance_b200 import ops
+    rng = np.random.default_rng(1)
+    n, g = 300, 41
+    a, b, c = (torch.tensor(rng.normal(size=(n, g)).astype(np.float32) * 1.5, requires_grad=True) for _ in range(3))
+    y = torch.tensor(rng.poisson(1.2, size=(n, g)).astype(np.float32))
+    sf = torch.tensor(rng.lognormal(0, 0.3, n).astype(np.float32))
+    mask = torch.tensor(rng.random((n, g)) < 0.85)
+    le, ke = 1.3, 0.7
+    loss_exp, kl_exp, mean, disp, pi = _zinb_ref(a, b, c, y, sf, mask, le, ke)
+    (loss_exp + ke * kl_exp).backward()
+    acc, grads, outs = ops.zinb_loss_grad(a.detach().to(cuda), b.detach().to(cuda), c.detach().to(cuda), y.to(cuda), sf.to(cuda), mask.to(cuda),
+                                          le, ke, want_grad=True, want_outputs=True)
+    nll, mse, cnt = acc.cpu().tolist()
+    assert cnt == int(mask.sum())
+    assert abs(le * nll / cnt - loss_exp.item()) < 1e-5 * abs(loss_exp.item())
+    assert abs(0.5 / g * mse / cnt - kl_exp.item()) < 1e-5 * abs(kl_exp.item())
+    for got, ref in zip(outs, (mean, disp, pi)):
+        assert rel_err(got, ref.detach()) < 1e-5
+    for got, ref in zip(grads, (a.grad, b.grad, c.grad)):
+        assert rel_err(got, ref) < TOL
+
+
+def test_adjacency_loss_matches_autograd(cuda):
+    from dance_b200 import ops
+    rng = np.random.default_rng(2)
+    g, n_cells = 67, 500
+    mu = torch.tensor(rng.normal(size=(g, g)).astype(np.float32) * 0.5, requires_grad=True)
+    ls = torch.tensor(rng.normal(size=(g, g)).astype(np.float32) * 0.3 - 1, requires_grad=True)
+    eps = torch.tensor(rng.normal(size=(g, g)).astype(np.float32))
+    adj = torch.tensor((rng.random((g, g)) < 0.2).astype(np.float32))
+    adj.fill_diagonal_(1.0)
+    pos_weight = (g * g - adj.sum(1)) / adj.sum(1)
+    norm_adj = g * g / float((g * g - adj.sum()) * 2)
+    la, ka = 0.9, 1.1
+    z = mu + torch.exp(ls) * eps
+    loss_adj = la * norm_adj * torch.mean(F.cross_entropy(z, adj, pos_weight))                   # graphsci.py:455-461
+    kl_adj = (0.5 / n_cells) * torch.mean(torch.sum(1 + 2 * ls - torch.square(mu) - torch.square(torch.exp(ls)), 1))
+    up = torch.tensor(rng.normal(size=(g, g)).astype(np.float32)) * 1e-3                        # gradient arriving from the AE side
+    (loss_adj - ka * kl_adj + (z * up).sum()).backward()
+    muc, lsc, epc = mu.detach().to(cuda), ls.detach().to(cuda), eps.to(cuda)
+    zc = ops.adj_sample(muc, lsc, epc)
+    assert rel_err(zc, z.detach()) < 1e-6
+    acc, dz = ops.adj_loss_grad(zc, muc, lsc, adj.to(cuda), pos_weight.to(cuda), coef_ce=la * norm_adj / g)
+    ce, kls = acc.cpu().tolist()
+    assert abs(la * norm_adj * ce / g - loss_adj.item()) < 1e-5 * abs(loss_adj.item())
+    assert abs(0.5 / n_cells * kls / g - kl_adj.item()) < 1e-5 * abs(kl_adj.item())
+    dmu, dls = ops.adj_reparam_bwd(dz + up.to(cuda), muc, lsc, epc, coef_kl=-ka * 0.5 / (n_cells * g))
+    assert rel_err(dmu, mu.grad) < TOL and rel_err(dls, ls.grad) < TOL
+
+
+class _G:
+    """Minimal graph object (edges / num_nodes), what GraphSCI.fit touches."""
+
+    def __init__(self, src, dst, n):
+        self.s, self.d, self.n = torch.as_tensor(src), torch.as_tensor(dst), n
+
+    def edges(self):
+        return self.s, self.d
+
+    def num_nodes(self):
+        return self.n
+
+
+def _fresh(g, cuda):
+    from dance_b200.modules.graphsci import GraphSCI
+    n, G = g["X"].shape
+    m = GraphSCI(num_cells=n, num_genes=G, dataset="fixture", dropout=0.0, gpu=0, seed=1)
+    m.load_state_dict({scope: {k[len(f"init.{scope}."):]: g[k] for k in g.files if k.startswith(f"init.{scope}.")}
+                       for scope in ("aemodel", "gnnmodel")})
+    return m
+
+
+def test_graphsci_first_step_losses_and_gradients(cuda, golden):
+    g = golden("graphsci")
+    m = _fresh(g, cuda)
+    G = _G(g["src"], g["dst"], g["X"].shape[1])
+    m.fit(g["Xl"], g["X"], G, mask=g["mask"], n_epochs=1, lr=1e-3, weight_decay=1e-5, train_idx=g["train_idx"], eps_sequence=list(g["eps"]))
+    ref = g["e1.losses"]
+    got = np.array([m.loss_adj, m.loss_exp, m.kl, m.train_loss, m.valid_loss])
+    assert np.allclose(got, ref, rtol=TOL), (got, ref)
+    for k in g.files:
+        if k.startswith("grad."):
+            name = k[len("grad."):]
+            assert rel_err(m.params.g[name], g[k]) < 5e-4, name            # fp32 chains through BN/ZINB; see the weights below at 1e-4
+    sd = m.state_dict()
+    for scope in ("aemodel", "gnnmodel"):
+        for k, v in sd[scope].items():
+            refv = g[f"e1.{scope}.{k}"]
+            if k.endswith("num_batches_tracked"):
+                assert int(v) == int(refv)
+            else:
+                assert rel_err(v, refv) < TOL, (scope, k)
+
+
+def test_graphsci_fit_and_predict_match_reference(cuda, golden):
+    g = golden("graphsci")
+    m = _fresh(g, cuda)
+    G = _G(g["src"], g["dst"], g["X"].shape[1])
+    eps = list(g["eps"])
+    m.fit(g["Xl"], g["X"], G, mask=g["mask"], n_epochs=4, lr=1e-3, weight_decay=1e-5, train_idx=g["train_idx"], eps_sequence=eps[:8])
+    got = np.array([m.loss_adj, m.loss_exp, m.kl, m.train_loss, m.valid_loss])
+    assert np.allclose(got, g["e4.losses"], rtol=2e-4), (got, g["e4.losses"])
+    sd = m.state_dict()
+    for scope in ("aemodel", "gnnmodel"):
+        for k, v in sd[scope].items():
+            if not k.endswith("num_batches_tracked"):
+                assert rel_err(v, g[f"e4.{scope}.{k}"]) < 2e-4, (scope, k)
+    pred = m.predict(g["Xl"], g["X"], G, mask=g["mask"], eps=torch.as_tensor(eps[8]))
+    assert rel_err(pred, g["e4.predict"]) < 1e-3
+    assert m.score(torch.tensor(g["Xl"]), pred, mask=g["mask"], metric="RMSE", test_idx=np.arange(234, 260)) >= 0.0
