@@ -252,6 +252,12 @@ bool eligible(int32_t n, int32_t d, int32_t n_rows);
 int launch(const float* z, int64_t ldz, int32_t n, int32_t d, int32_t row_begin, int32_t n_rows, float coef, float* dz,
            double* loss_acc, void* ws, size_t ws_bytes, cudaStream_t st);
 }  // namespace gtc
+namespace gtch {   // gae_tch.cu: fp16-split tcgen05 version (half the MMA count of gae_tc.cu)
+size_t workspace_bytes(int32_t n);
+bool eligible(int32_t n, int32_t d, int32_t n_rows);
+int launch(const float* z, int64_t ldz, int32_t n, int32_t d, int32_t row_begin, int32_t n_rows, float coef, float* dz,
+           double* loss_acc, void* ws, size_t ws_bytes, cudaStream_t st);
+}  // namespace gtch
 
 template <int D>
 static int launch_gae_edges(const float* z, int64_t ldz, const int32_t* rp, const int32_t* ci, int32_t row_begin, int32_t n_rows,
@@ -307,7 +313,8 @@ extern "C" int b2_mse_sum_loss_grad_f32(const float* recon, const float* target,
 
 extern "C" size_t b2_gae_loss_workspace_bytes(int32_t n, int32_t d) {
   // 256 B of accumulators + the hi/lo tf32 split of z (padded to 32 columns) for the tensor-core path
-  return 256 + (d <= 32 ? gtc::workspace_bytes(n) : 0);
+  const size_t a = gtc::workspace_bytes(n), b = gtch::workspace_bytes(n);
+  return 256 + (d <= 32 ? (a > b ? a : b) : 0);
 }
 
 extern "C" int b2_gae_loss_grad_f32(const float* z, int64_t ldz, const float* mu, const float* logvar, int64_t ldm,
@@ -329,7 +336,12 @@ extern "C" int b2_gae_loss_grad_f32(const float* z, int64_t ldz, const float* mu
   int rc;
   // large problems: the all-pairs part runs on tcgen05 (gae_tc.cu); the CUDA-core kernel serves small graphs
   bool tc_done = false;
-  if (gtc::eligible(n, d, n_rows) && workspace_bytes >= 256 + gtc::workspace_bytes(n)) {
+  if (gtch::eligible(n, d, n_rows) && workspace_bytes >= 256 + gtch::workspace_bytes(n)) {
+    rc = gtch::launch(z, ldz, n, d, row_begin, n_rows, coef, dz, acc, reinterpret_cast<char*>(workspace) + 256, workspace_bytes - 256, st);
+    if (rc == B2_OK) tc_done = true;
+    else if (rc != B2_ERR_UNSUPPORTED) return rc;
+  }
+  if (!tc_done && gtc::eligible(n, d, n_rows) && workspace_bytes >= 256 + gtc::workspace_bytes(n)) {
     rc = gtc::launch(z, ldz, n, d, row_begin, n_rows, coef, dz, acc, reinterpret_cast<char*>(workspace) + 256, workspace_bytes - 256, st);
     if (rc == B2_OK) tc_done = true;
     else if (rc != B2_ERR_UNSUPPORTED) return rc;
