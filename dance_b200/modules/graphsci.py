@@ -264,6 +264,8 @@ class GraphSCI:
             valid_mask[va] = True
         self.train_data_masked = X_masked
         self._feat = X_masked.t().contiguous()                                         # graph.ndata["feat"] = masked.T (:270)
+        if mask is not None and hasattr(graph, "ndata"):
+            graph.ndata["feat"] = self._feat                                           # the reference mutates the caller's graph too
         n_counts = Xraw.sum(1)
         self.size_factors = (n_counts / torch.median(n_counts)).contiguous()
         self.weight_decay = weight_decay
@@ -295,7 +297,7 @@ class GraphSCI:
         G, N = self.G, self.N
         P, Gd = self.params.p, self.params.g
         pr = self.precision
-        z, ls, mu, gc = self._gnn_forward(self._feat, True, eps_train)
+        z, ls, mu, gc = self._gnn_forward(self._graph_feat(graph), True, eps_train)
         a_pi, b_disp, c_mean, ac = self._ae_forward(X, z, True)
         acc3, (d_a, d_b, d_c), _ = ops.zinb_loss_grad(a_pi, b_disp, c_mean, Xraw, self.size_factors, train_mask, float(le), float(ke))
         acc2, dz_ce = ops.adj_loss_grad(z, mu, ls, self.adj, self.pos_weight, coef_ce=float(la) * self.norm_adj / G)
@@ -372,7 +374,7 @@ class GraphSCI:
         X, Xraw = _t(features, self.device), _t(features_raw, self.device)
         if mask is not None and not isinstance(mask, torch.Tensor):
             mask = torch.from_numpy(np.asarray(mask).astype(bool)).to(self.device).view(torch.uint8)
-        feat = self._feat if getattr(self, "_feat", None) is not None and X.shape == self.train_data_masked.shape else X.t().contiguous()
+        feat = self._graph_feat(graph)
         z, ls, mu, _ = self._gnn_forward(feat, False, eps)
         a_pi, b_disp, c_mean, _ = self._ae_forward(X, z, False)
         acc3, _, (mean, _, _) = ops.zinb_loss_grad(a_pi, b_disp, c_mean, Xraw, self.size_factors, mask, float(le), float(ke), want_grad=False,
@@ -381,6 +383,18 @@ class GraphSCI:
         *_, loss = self._losses(acc3, acc2, le, la, ke, ka)
         z_exp = mean * self.size_factors.view(-1, 1)
         return loss, z, z_exp
+
+    def _graph_feat(self, graph):
+        """Node features the GNN consumes: ``graph.ndata["feat"]`` ([genes, cells], as in the reference :126) when the graph
+        object carries them, else the masked training matrix bound by ``fit``."""
+        nd = getattr(graph, "ndata", None)
+        if nd is not None and "feat" in nd:
+            f = nd["feat"]
+            if not (isinstance(f, torch.Tensor) and f.is_cuda and f.dtype == torch.float32 and f.is_contiguous()):
+                f = _t(f, self.device)
+                nd["feat"] = f
+            return f
+        return self._feat
 
     def save_model(self):
         self.best_state = self.state_dict()
@@ -398,8 +412,6 @@ class GraphSCI:
         data = _t(data, self.device)
         if mask is not None:
             data = self.maskdata(data, mask)
-        self._feat = data.t().contiguous() if tuple(data.shape) == (self.N, self.G) else self._feat
-        self.train_data_masked = data
         _, _, z_exp = self.evaluate(data, data_raw, graph, eps=eps)
         return z_exp
 
