@@ -425,11 +425,14 @@ def main():
         # the exact N×N decoder is SFU/FMA-bound; report it on the tensor roofline with its matmul flops (2·d per logit, S and G·Z)
         dec_flops = 2.0 * 2 * EMB * float(n_loc) * N
         ach = dec_flops / (dec_total * 1e-3) / 1e12 if dec_total else 0.0
-        roofline = {"kernel": "gae_allpairs_kernel (matrix-free z·zᵀ BCE decoder)", "bound": "tensor", "achieved": ach,
+        roofline = {"kernel": "gae_allpairs_tch_kernel (matrix-free z·zᵀ BCE decoder: tcgen05 kind::f16 hi/lo split, S and G in TMEM)",
+                    "bound": "tensor", "achieved": ach,
                     "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": None,
                     "launches": dec_n, "ms_total": dec_total, "peak_source": peaks["source"],
-                    "note": "dominant kernel of the step; bound by SFU (exp/log/rcp per logit) + FP32 FMA, not by HBM or the tensor pipe — "
-                            "see roofline_spmm / roofline_gemm for the HBM- and tensor-bound kernels"}
+                    "note": "dominant kernel of the step; algorithmic flops = the two K=16 products per logit (S and G·Z). Its real ceiling is "
+                            "the per-logit elementwise work (2 MUFU + 9 ALU instructions on 16 warps, ncu: issue 58 %, XU 58 %), not the tensor "
+                            "pipe (10 % active) or HBM — see DESIGN.md §decoder and profiles/; roofline_spmm / roofline_gemm are the HBM- and "
+                            "tensor-bound kernels"}
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
