@@ -216,9 +216,12 @@ gae_allpairs_tch_kernel(const __grid_constant__ Params p) {
       };
       int stage_s = 0, stage_d = 0;
       uint32_t phase_s = 0;
-      if (n_tiles > 0) { issue_s(0, 0, 0); if (++stage_s == STAGES) { stage_s = 0; phase_s ^= 1; } }
+      // S runs TWO tiles ahead of dZ: the group that finishes tile t needs S(t+2) next, and the tensor pipe executes in order,
+      // so S(t+2) must be queued BEFORE dZ(t) (it only needs the group to have copied S(t) out of the shared buffer, which
+      // happens at the start of its work on tile t) — otherwise every group idles for a dZ + S round trip per tile.
+      for (int t0 = 0; t0 < 2 && t0 < n_tiles; ++t0) { issue_s(t0, stage_s, phase_s); if (++stage_s == STAGES) { stage_s = 0; phase_s ^= 1; } }
       for (int t = 0; t < n_tiles; ++t) {
-        if (t + 1 < n_tiles) { issue_s(t + 1, stage_s, phase_s); if (++stage_s == STAGES) { stage_s = 0; phase_s ^= 1; } }
+        if (t + 2 < n_tiles) { issue_s(t + 2, stage_s, phase_s); if (++stage_s == STAGES) { stage_s = 0; phase_s ^= 1; } }
         const int b = t & 1;
         mbar_wait(g_full + 8 * b, (t >> 1) & 1);
         tc_fence_after();

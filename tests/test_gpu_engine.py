@@ -93,12 +93,14 @@ def test_full_size_properties_spmm_linearity_and_symmetry(cuda):
     assert int(A.rowptr[-1].item()) == A.nnz and A.nnz >= n * (k + 1)
     rows = torch.repeat_interleave(torch.arange(n, device=cuda), (A.rowptr[1:] - A.rowptr[:-1]).long())
     assert torch.all(idx.min() >= 0) and torch.all(A.colidx[1:][rows[1:] == rows[:-1]] > A.colidx[:-1][rows[1:] == rows[:-1]])  # sorted, unique
-    x, y = torch.randn(n, 32, device=cuda), torch.randn(n, 32, device=cuda)
+    gen = torch.Generator(device=cuda).manual_seed(0)
+    x, y = torch.randn(n, 32, device=cuda, generator=gen), torch.randn(n, 32, device=cuda, generator=gen)
     Ax, Ay = ops.spmm(A, x), ops.spmm(A, y)
     lin = ops.spmm(A, 2 * x + y)
     assert rel_err(lin.cpu().numpy(), (2 * Ax + Ay).cpu().numpy()) < 1e-5
     lhs, rhs = (Ax.double() * y.double()).sum().item(), (x.double() * Ay.double()).sum().item()
-    assert abs(lhs - rhs) < 1e-6 * max(abs(lhs), 1.0)
+    # x and y are independent, so ⟨Âx, y⟩ is a heavily cancelling sum: the fp32 rounding of Âx / Ây is measured against ‖Âx‖‖y‖
+    assert abs(lhs - rhs) < 1e-6 * (Ax.double().norm() * y.double().norm()).item()
     # D^-1/2 (A+I) D^-1/2 applied to sqrt(deg) returns sqrt(deg)
     deg = (A.rowptr[1:] - A.rowptr[:-1]).float().sqrt().unsqueeze(1).repeat(1, 4).contiguous()
     assert rel_err(ops.spmm(A, deg).cpu().numpy(), deg.cpu().numpy()) < 1e-5
