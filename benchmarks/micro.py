@@ -109,6 +109,93 @@ def main():
             out.append(dict(kernel="normalize_total_log1p", n=nn, g=g, ms=med, alg_GBps=alg / med / 1e6,
                             frac_hbm=alg / med / 1e6 / PEAKS["hbm_gbs"]))
             print(json.dumps(out[-1]), flush=True)
+    if want("cellgene"):
+        nn, g = 100_000, 2000
+        X = (torch.rand(nn, g, device=dev) < 0.1).float() * torch.rand(nn, g, device=dev)
+        med, best = timeit(lambda: ops.cellgene_graph(X, True), iters=3, warmup=1)
+        nnz = int((X != 0).sum().item())
+        alg = 2.0 * nn * g * 4 + (2 * nnz + nn + g) * (8 + 8 + 4)            # two passes over X + the edge list written once
+        out.append(dict(kernel="cellgene_graph (CellFeatureGraph)", n=nn, g=g, nnz=nnz, ms=med, alg_GBps=alg / med / 1e6,
+                        frac_hbm=alg / med / 1e6 / PEAKS["hbm_gbs"]))
+        print(json.dumps(out[-1]), flush=True)
+    if want("pearson"):
+        for nn, g in ((100_000, 2000), ):
+            X = torch.randn(nn, g, device=dev)
+            med, best = timeit(lambda: ops.pearson_corr(X), iters=3, warmup=1)
+            out.append(dict(kernel="pearson_corr (FeatureFeatureGraph, fp64 SIMT Gram, upper triangle)", n=nn, g=g, ms=med,
+                            fp64_TFLOPs=float(g) * (g + 64) * nn / med / 1e9))
+            print(json.dumps(out[-1]), flush=True)
+    if want("matnorm"):
+        nn, g = 200_000, 2000
+        X = torch.rand(nn, g, device=dev)
+        Y = torch.empty_like(X)
+        for mode, axis, passes in (("normalize", 0, 2), ("standardize", 0, 3), ("l2", 1, 2)):
+            med, best = timeit(lambda: ops.matrix_normalize(X, mode, axis, -1.0, out=Y), flush=flush)
+            alg = (passes + 1.0) * nn * g * 4
+            out.append(dict(kernel="matrix_normalize", mode=mode, axis=axis, n=nn, g=g, ms=med, alg_GBps=alg / med / 1e6,
+                            frac_hbm=alg / med / 1e6 / PEAKS["hbm_gbs"]))
+            print(json.dumps(out[-1]), flush=True)
+    if want("umap"):
+        nn, k = 1_000_000, 15
+        idx = torch.randint(0, nn, (nn, k), device=dev, dtype=torch.int32)
+        idx[:, 0] = torch.arange(nn, device=dev, dtype=torch.int32)
+        dist = torch.sort(torch.rand(nn, k, device=dev), dim=1).values
+        dist[:, 0] = 0
+        med, best = timeit(lambda: ops.umap_connectivities(idx, dist), iters=3, warmup=1)
+        out.append(dict(kernel="umap_connectivities (smooth-kNN bisection + 2 CSR transposes + fuzzy union)", n=nn, k=k, ms=med,
+                        edges_per_s=nn * k / med * 1e3))
+        print(json.dumps(out[-1]), flush=True)
+    if want("radius"):
+        nn = 200_000
+        xy = torch.rand(nn, 2, device=dev, dtype=torch.float64) * (nn**0.5) * 100
+        med, best = timeit(lambda: ops.radius_graph(xy, 150.0), iters=3, warmup=1)
+        out.append(dict(kernel="radius_graph (StagateGraph, brute force fp64)", n=nn, ms=med, pair_tests_per_s=2.0 * nn * nn / med * 1e3))
+        print(json.dumps(out[-1]), flush=True)
+    if want("gat"):
+        nn, k = 200_000, 6
+        A = random_knn_graph(nn, k, dev)
+        T = ops.CSR(A.rowptr, A.colidx, None, A.shape)
+        H = torch.randn(nn, 512, device=dev)
+        a_s, a_t = torch.randn(512, device=dev) * 0.05, torch.randn(512, device=dev) * 0.05
+        s_src, s_trg = ops.gat_scores(H, a_s, a_t, 1)
+        med, best = timeit(lambda: ops.gat_aggregate_fwd(T, H, s_src, s_trg, 1, score_act="sigmoid", shift="segment"), flush=flush)
+        alg = T.nnz * 4 + 2.0 * nn * 512 * 4 + T.nnz * 4
+        out.append(dict(kernel="gat_aggregate_fwd (STAGATE layer, F=512)", n=nn, nnz=T.nnz, ms=med, alg_GBps=alg / med / 1e6,
+                        frac_hbm=alg / med / 1e6 / PEAKS["hbm_gbs"], gather_GBps=T.nnz * 512 * 4 / med / 1e6))
+        print(json.dumps(out[-1]), flush=True)
+    if want("zinb"):
+        nn, g = 100_000, 2000
+        a, b, c = (torch.randn(nn, g, device=dev) for _ in range(3))
+        y = torch.poisson(torch.rand(nn, g, device=dev) * 2)
+        sf = torch.rand(nn, device=dev) + 0.5
+        med, best = timeit(lambda: ops.zinb_loss_grad(a, b, c, y, sf, None, 1.0, 1.0), flush=flush)
+        alg = (2 * 4 + 3) * nn * g * 4.0            # loss pass reads a,b,c,y; grad pass reads them again and writes three gradients
+        out.append(dict(kernel="zinb_loss_grad (GraphSCI heads + NLL + gradients)", n=nn, g=g, ms=med, alg_GBps=alg / med / 1e6,
+                        frac_hbm=alg / med / 1e6 / PEAKS["hbm_gbs"]))
+        print(json.dumps(out[-1]), flush=True)
+    if want("batchnorm"):
+        nn, g = 200_000, 2000
+        X = torch.randn(nn, g, device=dev)
+        gam, bet, rm, rv = torch.ones(g, device=dev), torch.zeros(g, device=dev), torch.zeros(g, device=dev), torch.ones(g, device=dev)
+        med, best = timeit(lambda: ops.batchnorm_fwd(X, gam, bet, rm, rv, True), flush=flush)
+        alg = 4.0 * nn * g * 4                      # two statistics passes + read + write
+        out.append(dict(kernel="batchnorm_fwd (training)", n=nn, c=g, ms=med, alg_GBps=alg / med / 1e6, frac_hbm=alg / med / 1e6 / PEAKS["hbm_gbs"]))
+        print(json.dumps(out[-1]), flush=True)
+    if want("dec"):
+        nn, h, K = 1_000_000, 50, 10
+        z, mu = torch.randn(nn, h, device=dev), torch.randn(K, h, device=dev)
+        p = ops.dec_target(ops.dec_q(z, mu))
+        med, best = timeit(lambda: ops.dec_kl_grad(z, mu, p), flush=flush)
+        alg = nn * (2.0 * h + K) * 4
+        out.append(dict(kernel="dec_kl_grad (SpaGCN DEC head: loss + dz + dmu + argmax)", n=nn, h=h, K=K, ms=med, alg_GBps=alg / med / 1e6,
+                        frac_hbm=alg / med / 1e6 / PEAKS["hbm_gbs"]))
+        print(json.dumps(out[-1]), flush=True)
+    if want("pca"):
+        nn, g, k = 100_000, 2000, 50
+        X = torch.randn(nn, g, device=dev)
+        med, best = timeit(lambda: ops.pca(X, k), iters=2, warmup=1)
+        out.append(dict(kernel="pca (CellPCA: covariance GEMM + Jacobi eigensolver + projection)", n=nn, g=g, k=k, ms=med))
+        print(json.dumps(out[-1]), flush=True)
     Path("gpurun_out").mkdir(exist_ok=True)
     json.dump(out, open("gpurun_out/micro.json", "w"), indent=1)
 

@@ -88,6 +88,47 @@ gat_aggregate_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __re
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int W = nh * F;
   const float gshift = shift_mode == 0 ? *gmax : 0.f;
+  if ((F & 31) == 0) {
+    // Wide heads (F a multiple of 32, e.g. STAGATE's 1×512): every lane of a t-slot belongs to the same head, so the edge
+    // coefficient is computed ONCE per (edge, head) instead of once per (edge, 32-column slot) — the exponentials, not the
+    // gather, dominated the first version of this kernel (20.9 → see profiles/r01_micro.json).
+    const int tper = F >> 5;
+    for (int64_t v = warp; v < n; v += nwarps) {
+      const int32_t s = rowptr[v], e = rowptr[v + 1];
+      float acc[MAXV];
+#pragma unroll
+      for (int t = 0; t < MAXV; ++t) acc[t] = 0.f;
+      for (int h = 0; h < nh; ++h) {
+        const float st = s_trg[v * nh + h];
+        float sh = gshift;
+        if (shift_mode == 1) {
+          float m = -CUDART_INF_F;
+          for (int32_t p = s + lane; p < e; p += 32) m = fmaxf(m, score_act_f(s_src[(int64_t)colidx[p] * nh + h] + st, act, slope));
+          m = warp_max(m);
+          sh = (e > s) ? m : 0.f;
+        }
+        float den = 0.f;
+        const int t0 = h * tper, t1 = t0 + tper;
+        for (int32_t p = s; p < e; ++p) {
+          const int32_t u = colidx[p];
+          const float pe = expf(score_act_f(s_src[(int64_t)u * nh + h] + st, act, slope) - sh);
+          den += pe;
+          const float* hu = H + (int64_t)u * ldh + lane;
+#pragma unroll
+          for (int t = 0; t < MAXV; ++t)
+            if (t >= t0 && t < t1) acc[t] = fmaf(pe, hu[32 * t], acc[t]);
+        }
+        const float inv = 1.f / (den + 1e-16f);
+#pragma unroll
+        for (int t = 0; t < MAXV; ++t)
+          if (t >= t0 && t < t1) out[v * ldo + lane + 32 * t] = acc[t] * inv;
+        if (alpha_out)
+          for (int32_t p = s + lane; p < e; p += 32)
+            alpha_out[(int64_t)p * nh + h] = expf(score_act_f(s_src[(int64_t)colidx[p] * nh + h] + st, act, slope) - sh) * inv;
+      }
+    }
+    return;
+  }
   for (int64_t v = warp; v < n; v += nwarps) {
     const int32_t s = rowptr[v], e = rowptr[v + 1];
     float acc[MAXV], den[MAXV], shift[MAXV];
@@ -168,16 +209,14 @@ gat_bwd_target_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restr
         if (H2)   // tied attention: the same α also weights a second layer's messages (stagate.py:197)
           for (int f = lane; f < F; f += 32) d = fmaf(dOut2[v * lddo2 + h * F + f], H2[(int64_t)u * ldh2 + h * F + f], d);
         d = warp_sum(d);
+        if (lane == 0) dpre_edge[(int64_t)p * nh + h] = d;          // kept for the second sweep (same lane reads it back)
         t = fmaf(alpha[(int64_t)p * nh + h], d, t);
       }
+      __syncwarp();
       float st = 0.f;
       for (int32_t p = s; p < e; ++p) {
         const int32_t u = colidx[p];
-        float d = 0.f;
-        for (int f = lane; f < F; f += 32) d = fmaf(dOut[v * lddo + h * F + f], H[(int64_t)u * ldh + h * F + f], d);
-        if (H2)   // tied attention: the same α also weights a second layer's messages (stagate.py:197)
-          for (int f = lane; f < F; f += 32) d = fmaf(dOut2[v * lddo2 + h * F + f], H2[(int64_t)u * ldh2 + h * F + f], d);
-        d = warp_sum(d);
+        const float d = dpre_edge[(int64_t)p * nh + h];      // the dot of the first sweep (written by lane 0, visible after __syncwarp)
         const float a = alpha[(int64_t)p * nh + h];
         const float pre = s_src[(int64_t)u * nh + h] + s_trg[v * nh + h];
         const float g = a * (d - t) * score_act_grad(pre, act, slope);
