@@ -152,7 +152,7 @@ template <int M>
 __global__ void __launch_bounds__(256)
 knn_refine_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ sqn,
                   const float* __restrict__ max_sqn, int32_t n, int32_t d, int32_t k, int32_t q_begin, int32_t n_q,
-                  int r0, const int32_t* __restrict__ cand_idx, const float* __restrict__ cand_thr,
+                  int r0, const int32_t* __restrict__ cand_idx, const float* __restrict__ cand_thr, float err_rel,
                   int32_t* __restrict__ idx_out, double* __restrict__ dist_out, int32_t* __restrict__ fail_list,
                   int32_t* __restrict__ fail_count) {
   constexpr int PER = M / 32;
@@ -199,7 +199,7 @@ knn_refine_kernel(const float* __restrict__ X, int64_t ldx, const float* __restr
       if (!proven) {
         // every non-candidate has fp32 estimate >= thr; |estimate - true d²| <= err
         const double qn = (double)sqn[q_begin + q], rmax = (double)max_sqn[0];
-        const double err = 1.1920928955078125e-07 * (double)(d + 8) * (qn + rmax + 2.0 * sqrt(qn * rmax));
+        const double err = (double)err_rel * (qn + rmax + 2.0 * sqrt(qn * rmax));   // err_rel: bound of the filter that produced thr
         const double thr = (double)cand_thr[q];
         proven = isfinite(worst) && (thr - err) > worst * worst * (1.0 + 1e-12);
       }
@@ -280,6 +280,14 @@ static size_t cand_smem_bytes(int M) {
 // `need` = number of sorted ranks that must be recovered (k, +1 when rank 0 is dropped); 8 spare candidates
 static int choose_M(int need) { return (need + 8 <= 32) ? 32 : 64; }
 
+namespace ktc {   // knn_tc.cu: tcgen05 candidate filter
+size_t workspace_bytes(int32_t n, int32_t d, int32_t n_q);
+bool eligible(int32_t n, int32_t d, int32_t n_q, int M);
+float tc_err_rel(int32_t d);
+int launch(const float* X, int64_t ldx, const float* sqn, int32_t n, int32_t d, int32_t q_begin, int32_t n_q, int32_t* cand_idx,
+           float* cand_thr, void* ws, size_t ws_bytes, cudaStream_t st);
+}  // namespace ktc
+
 }  // namespace b2
 
 using namespace b2;
@@ -287,7 +295,7 @@ using namespace b2;
 extern "C" size_t b2_knn_workspace_bytes(int32_t n, int32_t d, int32_t k, int32_t n_queries) {
   const int M = choose_M(k + 1);
   return align_up((size_t)n * 4, 256) + align_up((size_t)n_queries * M * 4, 256) +
-         2 * align_up((size_t)n_queries * 4, 256) + 1024;
+         2 * align_up((size_t)n_queries * 4, 256) + 1024 + (ktc::eligible(n, d, n_queries, M) ? ktc::workspace_bytes(n, d, n_queries) : 0);
 }
 
 extern "C" int b2_knn_l2_f32(const float* X, int64_t ldx, int32_t n, int32_t d, int32_t k, int32_t q_begin,
@@ -322,25 +330,33 @@ extern "C" int b2_knn_l2_f32(const float* X, int64_t ldx, int32_t n, int32_t d, 
     row_sqnorm_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, ldx, n, d, sqn, max_sqn);
     B2_CHECK_LAUNCH("row_sqnorm_kernel");
   }
+  float err_rel = 1.1920928955078125e-07f * (float)(d + 8);      // fp32 SIMT filter
+  bool tc_done = false;
+  if (ktc::eligible(n, d, n_q, M)) {
+    const int rc = ktc::launch(X, ldx, sqn, n, d, q_begin, n_q, cand, thr, ws + off + 1024, workspace_bytes - off - 1024, st);
+    if (rc == B2_OK) { tc_done = true; err_rel = ktc::tc_err_rel(d); }
+    else if (rc != B2_ERR_UNSUPPORTED) return rc;
+  }
   const unsigned grid = (unsigned)ceil_div(n_q, KQ);
   const size_t smem = cand_smem_bytes(M);
-  if (M == 32) {
+  if (tc_done) {
+  } else if (M == 32) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(knn_candidates_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     knn_candidates_kernel<32><<<grid, KTHREADS, smem, st>>>(X, ldx, sqn, n, d, q_begin, n_q, cand, thr);
   } else {
     B2_CHECK_CUDA(cudaFuncSetAttribute(knn_candidates_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     knn_candidates_kernel<64><<<grid, KTHREADS, smem, st>>>(X, ldx, sqn, n, d, q_begin, n_q, cand, thr);
   }
-  B2_CHECK_LAUNCH("knn_candidates_kernel");
+  if (!tc_done) B2_CHECK_LAUNCH("knn_candidates_kernel");
   {
     int64_t blocks = ceil_div<int64_t>(n_q, 8);
     const int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     if (M == 32)
-      knn_refine_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(X, ldx, sqn, max_sqn, n, d, k, q_begin, n_q, r0, cand, thr,
+      knn_refine_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(X, ldx, sqn, max_sqn, n, d, k, q_begin, n_q, r0, cand, thr, err_rel,
                                                                idx_out, dist_out, fail_list, fail_count);
     else
-      knn_refine_kernel<64><<<(unsigned)blocks, 256, 0, st>>>(X, ldx, sqn, max_sqn, n, d, k, q_begin, n_q, r0, cand, thr,
+      knn_refine_kernel<64><<<(unsigned)blocks, 256, 0, st>>>(X, ldx, sqn, max_sqn, n, d, k, q_begin, n_q, r0, cand, thr, err_rel,
                                                                idx_out, dist_out, fail_list, fail_count);
     B2_CHECK_LAUNCH("knn_refine_kernel");
   }

@@ -164,6 +164,31 @@ def test_knn_bit_exact_vs_oracle(cuda, n, d, k):
     assert np.array_equal(dist.cpu().numpy(), dist_ref)                         # fp64 distances: bit-exact
 
 
+@pytest.mark.parametrize("n,d,k", [(6000, 128, 15), (5000, 50, 15), (4500, 16, 10)])
+def test_knn_tensor_core_filter_bit_exact(cuda, n, d, k):
+    """n·n_q ≥ 2^24 routes the candidate filter through tcgen05 (fp16 hi/lo split); the fp64 refine + proof keep the result
+    bit-exact with the reference ranking; duplicates, a query range, and the SIMT filter (B2_KNN_NO_TC) agree."""
+    import os
+    from dance_b200 import ops
+    from oracle import port
+    X = port.synthetic_embedding(n, d=d, n_clusters=5, seed=n + d)
+    X[17] = X[4000]                                  # exact duplicate far apart in index
+    X[100:110] *= 40.0                               # a few large-norm rows: stresses the error bound / scale
+    idx_ref, dist_ref = port.knn_indices(X, k, return_dist=True)
+    Xc = torch.from_numpy(X).to(cuda)
+    idx, dist = ops.knn(Xc, k)
+    assert np.array_equal(idx.cpu().numpy().astype(np.int64), idx_ref)
+    assert np.array_equal(dist.cpu().numpy(), dist_ref)
+    os.environ["B2_KNN_NO_TC"] = "1"
+    try:
+        idx_s, _ = ops.knn(Xc, k)
+    finally:
+        del os.environ["B2_KNN_NO_TC"]
+    assert torch.equal(idx, idx_s)
+    part, _ = ops.knn(Xc, k, q_begin=300, q_end=n - 200)      # n·n_q still above the threshold: sharded queries on the TC path
+    assert torch.equal(part, idx[300:n - 200])
+
+
 def test_knn_golden_and_graph_build(cuda, golden):
     from dance_b200 import ops
     g = golden("knn_graph")
