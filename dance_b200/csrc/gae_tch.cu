@@ -49,7 +49,7 @@ struct Params {
   CUtensorMap mT_hi, mT_lo;      // ZT  [16,n'] halves box {64,16} SWIZZLE_128B  (B of the dZ product)
   const float* scale;            // scale[0] = 2^e applied to ZT, scale[2] = 2^-e
   const float* z; int64_t ldz;   // original embeddings (closed-form Σ_j x_ij in the epilogue)
-  const float* zsum;             // [j_splits, 16] column sums of z over each CTA column range
+  const double* zsum;            // [j_splits, 16] column sums of z over each CTA column range
   float* dz;                     // [n_rows, d]
   double* loss_acc;
   int n, d, row_begin, n_rows, j_chunk, j_splits;
@@ -103,19 +103,21 @@ split_kernel(const float* __restrict__ z, int64_t ldz, int32_t n, int32_t d, int
   }
 }
 
-// zsum[y, c] = Σ_{j in column range y} z[j, c]   (fp64 accumulation)
+// zsum[y, c] += Σ_{j in column range y, slice blockIdx.y} z[j, c]   (fp64; zsum zeroed by the caller)
 __global__ void __launch_bounds__(256)
-colrange_sum_kernel(const float* __restrict__ z, int64_t ldz, int32_t n, int32_t d, int32_t j_chunk, float* __restrict__ zsum) {
+colrange_sum_kernel(const float* __restrict__ z, int64_t ldz, int32_t n, int32_t d, int32_t j_chunk, double* __restrict__ zsum) {
   __shared__ double sh[256];
   const int y = blockIdx.x, c = threadIdx.x & 15, part = threadIdx.x >> 4;
   const int j0 = y * j_chunk, j1 = min(n, j0 + j_chunk);
+  const int per = (j1 - j0 + gridDim.y - 1) / gridDim.y;
+  const int a0 = j0 + blockIdx.y * per, a1 = min(j1, a0 + per);
   double a = 0.0;
-  if (c < d) for (int j = j0 + part; j < j1; j += 16) a += (double)z[(int64_t)j * ldz + c];
+  if (c < d) for (int j = a0 + part; j < a1; j += 16) a += (double)z[(int64_t)j * ldz + c];
   sh[threadIdx.x] = a;
   __syncthreads();
   if (part == 0) {
     for (int q = 1; q < 16; ++q) a += sh[q * 16 + c];
-    zsum[y * 16 + c] = (float)a;
+    atomicAdd(zsum + y * 16 + c, a);
   }
 }
 
@@ -344,10 +346,10 @@ gae_allpairs_tch_kernel(const __grid_constant__ Params p) {
     double lin = 0.0;
     if (live && part == 0 && n_tiles > 0) {
       const float* zi = p.z + (size_t)(p.row_begin + row_local) * p.ldz;
-      const float* zs = p.zsum + blockIdx.y * 16;
-      float dot = 0.f;
-      for (int c = 0; c < p.d; ++c) dot = fmaf(zi[c], zs[c], dot);
-      lin = (double)dot * (double)LOG2E;
+      const double* zs = p.zsum + blockIdx.y * 16;
+      double dot = 0.0;
+      for (int c = 0; c < p.d; ++c) dot += (double)zi[c] * zs[c];
+      lin = dot * (double)LOG2E;
     }
     double loss = live ? (double)LN2 * (0.5 * ((double)abs_sum + lin) + (double)lg_sum + 11.0 * EW_COLS * (double)tiles_done) : 0.0;
     loss = warp_sum(loss);
@@ -386,7 +388,7 @@ gae_allpairs_tch_kernel(const __grid_constant__ Params p) {
 static int64_t padded_n(int32_t n) { return ((int64_t)n + 63) / 64 * 64; }
 
 size_t workspace_bytes(int32_t n) {
-  return 256 + 16384 + 4 * align_up((size_t)n * DW * sizeof(__half), 256) + 2 * align_up((size_t)padded_n(n) * DW * sizeof(__half), 256);
+  return 256 + 32768 + 4 * align_up((size_t)n * DW * sizeof(__half), 256) + 2 * align_up((size_t)padded_n(n) * DW * sizeof(__half), 256);
 }
 
 bool eligible(int32_t n, int32_t d, int32_t n_rows) {
@@ -402,8 +404,8 @@ int launch(const float* z, int64_t ldz, int32_t n, int32_t d, int32_t row_begin,
   char* w = reinterpret_cast<char*>(ws);
   uint32_t* maxbits = reinterpret_cast<uint32_t*>(w);
   float* scale = reinterpret_cast<float*>(w + 16);
-  float* zsum = reinterpret_cast<float*>(w + 256);          // up to 256 column ranges × 16
-  w += 256 + 16384;
+  double* zsum = reinterpret_cast<double*>(w + 256);        // up to 256 column ranges × 16
+  w += 256 + 32768;
   const size_t a16 = align_up((size_t)n * DW * sizeof(__half), 256), at = align_up((size_t)npad * DW * sizeof(__half), 256);
   __half* z16h = reinterpret_cast<__half*>(w);
   __half* z16l = reinterpret_cast<__half*>(w + a16);
@@ -448,7 +450,14 @@ int launch(const float* z, int64_t ldz, int32_t n, int32_t d, int32_t row_begin,
   p.dz = dz; p.loss_acc = loss_acc; p.n = n; p.d = d; p.row_begin = row_begin; p.n_rows = n_rows;
   p.j_chunk = j_chunk; p.j_splits = j_splits; p.coef = coef;
   if (j_splits > 256) return B2_ERR_UNSUPPORTED;
-  colrange_sum_kernel<<<j_splits, 256, 0, st>>>(z, ldz, n, d, j_chunk, zsum);
+  B2_CHECK_CUDA(cudaMemsetAsync(zsum, 0, sizeof(double) * 16 * (size_t)j_splits, st));
+  {
+    int slices = ceil_div(sm_count() * 2, j_splits);
+    const int max_slices = ceil_div(j_chunk, 4096);
+    if (slices > max_slices) slices = max_slices;
+    if (slices < 1) slices = 1;
+    colrange_sum_kernel<<<dim3(j_splits, slices), 256, 0, st>>>(z, ldz, n, d, j_chunk, zsum);
+  }
   B2_CHECK_LAUNCH("colrange_sum_kernel");
   p.z = z; p.ldz = ldz; p.zsum = zsum;
   p.stagger = getenv("B2_GAE_STAGGER") ? atoi(getenv("B2_GAE_STAGGER")) : 800;

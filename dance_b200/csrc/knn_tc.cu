@@ -4,8 +4,10 @@
 //   S = Q · Rᵀ            tcgen05.mma kind::f16 on fp16 (hi, lo) pairs of 2^e·x (22 significant bits; hi·hi + hi·lo + lo·hi),
 //                         fp32 accumulation in TMEM, K = padded feature width (16 per instruction)
 //   d̂² = |q|² + |r|² − 2·S/4^e   four selection warps (TMEM lane = query row) read the 128 estimates of their query straight
-//                         from TMEM and keep the M smallest in a per-query sorted list (global memory: inserts are rare —
-//                         ≈ M·ln(n/M) per query over the whole sweep — so the list lives in L1/L2 and shared memory goes to the ring)
+//                         from TMEM and keep the M smallest in an UNSORTED per-query list held in registers (replace-the-maximum:
+//                         32 predicated moves + a 32-entry rescan per insertion; insertions are warp-divergent and some lane
+//                         hits in ≈ 95 % of the 32-estimate chunks, so their cost — not their count, ≈ M·ln(n/M) per query —
+//                         is what matters; the refine pass ranks the candidates anyway)
 // The estimates only FILTER: phase 2 (knn_refine_kernel) re-ranks the candidates in fp64 exactly like the reference and
 // proves with an error bound that no non-candidate can enter the top-k; unproven queries fall back to fp64 brute force.
 // The bound for this filter is documented at `tc_err_rel` below.  Replaces the 26 TFLOP/s SIMT filter (10 s at 1 M × 128).
@@ -37,9 +39,9 @@ struct Params {
   const float* sqn;              // |x|² (fp32, unscaled)
   const float* scale;            // scale[1] = 4^-e
   int32_t* cand_idx;             // [n_q, MC]
-  float* cand_key;               // [n_q, MC] sorted estimates (workspace)
   float* cand_thr;               // [n_q]
   int n, n_q, q_begin, atoms, stages;
+  int debug;   // timing experiments (B2_KNN_TC_DEBUG): 1 skip the MMAs, 2 skip the selection math, 4 skip insertions
 };
 
 // max |x| → 2^e with max·2^e ∈ [256, 512);  scale[0] = 2^e, scale[1] = 4^-e
@@ -146,7 +148,7 @@ knn_candidates_tc_kernel(const __grid_constant__ Params p) {
         const uint32_t st = s_ring + stage * 2 * op_bytes;
         const uint32_t d_t = tmem + (uint32_t)(b * BR);
         uint32_t acc = 0;
-        for (int a = 0; a < p.atoms; ++a) {
+        for (int a = 0; a < p.atoms && !(p.debug & 1); ++a) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {             // 64 halves per atom = 4 k-steps of 16
             const uint32_t off = (uint32_t)(a * ATOM_BYTES + kk * 32);
@@ -167,15 +169,19 @@ knn_candidates_tc_kernel(const __grid_constant__ Params p) {
   } else if (warp >= 4) {
     // ===================== selection warps: thread = query row =====================
     const int sub = warp & 3;
-    const int q = q0 + sub * 32 + lane;              // this thread's query
+    const int ql = sub * 32 + lane;                  // local query
+    const int q = q0 + ql;
     const uint32_t lane_off = (uint32_t)(sub * 32) << 16;
     const float inv_s2 = p.scale[1];
     const bool live = q < p.n_q;
     const float qn = live ? p.sqn[p.q_begin + q] : 0.f;
-    float* Lk = p.cand_key + (int64_t)(live ? q : 0) * MC;
-    int32_t* Li = p.cand_idx + (int64_t)(live ? q : 0) * MC;
-    if (live)
-      for (int c = 0; c < MC; ++c) { Lk[c] = CUDART_INF_F; Li[c] = -1; }
+    // the M kept candidates live in REGISTERS (static indexing only): replacing the maximum is 32 predicated moves and the
+    // rescan 32 compares — no memory traffic, one copy of the code (the hit loop below is not unrolled)
+    float key[MC];
+    int32_t kid[MC];
+#pragma unroll
+    for (int s2 = 0; s2 < MC; ++s2) { key[s2] = CUDART_INF_F; kid[s2] = -1; }
+    int maxslot = 0;                                  // slot currently holding the largest kept estimate (= thr)
     float thr = CUDART_INF_F;
     const float m2 = -2.f * inv_s2;
     for (int t = 0; t < n_tiles; ++t) {
@@ -183,28 +189,62 @@ knn_candidates_tc_kernel(const __grid_constant__ Params p) {
       mbar_wait(d_full + 8 * b, (t >> 1) & 1);
       tc_fence_after();
       const int r0 = t * BR;
-#pragma unroll 1
+      // |r|² of the tile: four coalesced loads per lane issued up front, then broadcast by shuffle (a per-element load of the
+      // warp-uniform address serialised ~300 cycles of L2 latency per estimate in the first version of this loop)
+      float rn_l[BR / 32];
+#pragma unroll
+      for (int u = 0; u < BR / 32; ++u) {
+        const int r = r0 + u * 32 + lane;
+        rn_l[u] = r < p.n ? __ldg(p.sqn + r) : CUDART_INF_F;
+      }
+#pragma unroll
       for (int chunk = 0; chunk < BR / 32; ++chunk) {
+        if (p.debug & 2) break;
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem + lane_off + (uint32_t)(b * BR + chunk * 32), v);
+        float est[32];
+        float mn = CUDART_INF_F;
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          const int r = r0 + chunk * 32 + c;
-          const float rn = r < p.n ? __ldg(p.sqn + r) : CUDART_INF_F;       // warp-uniform address: one broadcast load
-          const float est = fmaf(m2, __uint_as_float(v[c]), qn + rn);
-          if (live && est < thr) {
-            int pos = MC - 1;
-            while (pos > 0 && Lk[pos - 1] > est) { Lk[pos] = Lk[pos - 1]; Li[pos] = Li[pos - 1]; --pos; }
-            Lk[pos] = est;
-            Li[pos] = r;
-            thr = Lk[MC - 1];
+          const float rn = __shfl_sync(0xffffffffu, rn_l[chunk], c);
+          est[c] = fmaf(m2, __uint_as_float(v[c]), qn + rn);
+          mn = fminf(mn, est[c]);
+        }
+        uint32_t mask = 0;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) mask |= (est[c] < thr ? 1u : 0u) << c;
+        if (live && mask && !(p.debug & 4)) {
+          // Per lane ≈ 9 % of the chunks contain a hit, per WARP ≈ 95 % do: the path must be short and exist once.
+          float es[32];                               // dynamic indexing below → local memory, touched only on this path
+#pragma unroll
+          for (int c = 0; c < 32; ++c) es[c] = est[c];
+          while (mask) {
+            const int c = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float e = es[c];
+            if (e < thr) {                            // thr may have dropped since the mask was built
+              const int32_t rid = r0 + chunk * 32 + c;
+#pragma unroll
+              for (int s2 = 0; s2 < MC; ++s2)
+                if (s2 == maxslot) { key[s2] = e; kid[s2] = rid; }
+              float mx = key[0];
+              maxslot = 0;
+#pragma unroll
+              for (int s2 = 1; s2 < MC; ++s2)
+                if (key[s2] > mx) { mx = key[s2]; maxslot = s2; }
+              thr = mx;
+            }
           }
         }
       }
       tc_fence_before();
       if (lane == 0) mbar_arrive(d_empty + 8 * b);
     }
-    if (live) p.cand_thr[q] = thr;
+    if (live) {
+#pragma unroll
+      for (int c = 0; c < MC; ++c) p.cand_idx[(int64_t)q * MC + c] = kid[c];
+      p.cand_thr[q] = thr;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -217,7 +257,8 @@ knn_candidates_tc_kernel(const __grid_constant__ Params p) {
 static int padded_d(int32_t d) { return (d + 63) / 64 * 64; }
 
 size_t workspace_bytes(int32_t n, int32_t d, int32_t n_q) {
-  return 256 + 2 * align_up((size_t)n * padded_d(d) * sizeof(__half), 256) + align_up((size_t)n_q * MC * sizeof(float), 256);
+  (void)n_q;
+  return 256 + 2 * align_up((size_t)n * padded_d(d) * sizeof(__half), 256);
 }
 
 bool eligible(int32_t n, int32_t d, int32_t n_q, int M) {
@@ -241,7 +282,6 @@ int launch(const float* X, int64_t ldx, const float* sqn, int32_t n, int32_t d, 
   float* scale = reinterpret_cast<float*>(w + 16);
   __half* xh = reinterpret_cast<__half*>(w + 256);
   __half* xl = reinterpret_cast<__half*>(w + 256 + align_up((size_t)n * dp * sizeof(__half), 256));
-  float* keys = reinterpret_cast<float*>(w + 256 + 2 * align_up((size_t)n * dp * sizeof(__half), 256));
   B2_CHECK_CUDA(cudaMemsetAsync(maxbits, 0, 4, st));
   int64_t blocks = ceil_div<int64_t>((int64_t)n * d, 256 * 8);
   const int64_t cap = (int64_t)sm_count() * 8;
@@ -263,14 +303,15 @@ int launch(const float* X, int64_t ldx, const float* sqn, int32_t n, int32_t d, 
   if (!make_tensor_map_f16_ex(&p.m_hi, xh, (uint64_t)dp, (uint64_t)n, (uint64_t)dp, 64, BR, SW128) ||
       !make_tensor_map_f16_ex(&p.m_lo, xl, (uint64_t)dp, (uint64_t)n, (uint64_t)dp, 64, BR, SW128))
     return B2_ERR_UNSUPPORTED;
-  p.sqn = sqn; p.scale = scale; p.cand_idx = cand_idx; p.cand_key = keys; p.cand_thr = cand_thr;
+  p.sqn = sqn; p.scale = scale; p.cand_idx = cand_idx; p.cand_thr = cand_thr;
   p.n = n; p.n_q = n_q; p.q_begin = q_begin; p.atoms = dp / 64;
   const int op_bytes = p.atoms * ATOM_BYTES;
   const size_t fixed = 2 * (size_t)op_bytes + 256 + 1024;
-  int stages = (int)((220 * 1024 - fixed) / (2 * (size_t)op_bytes));
+  int stages = (int)((232448 - fixed) / (2 * (size_t)op_bytes));
   if (stages > 4) stages = 4;
   if (stages < 2) return B2_ERR_UNSUPPORTED;
   p.stages = stages;
+  p.debug = getenv("B2_KNN_TC_DEBUG") ? atoi(getenv("B2_KNN_TC_DEBUG")) : 0;
   const size_t smem = fixed + (size_t)stages * 2 * op_bytes;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {

@@ -139,18 +139,47 @@ extern "C" int b2_sym_eig_jacobi_f32(float* W, float* V, int32_t g, int32_t max_
     eye_kernel<<<(unsigned)blocks, 256, 0, st>>>(V, g);
     B2_CHECK_LAUNCH("eye_kernel");
   }
+  // One sweep = memset + (m-1) tiny launches (a few µs of work each): at g = 2000 the solver is launch-bound, so the sweep
+  // is captured once into a CUDA graph and replayed; the convergence flag is read back after every replay.
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  bool use_graph = m - 1 >= 64;
+  if (use_graph) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) use_graph = false;   // caller is capturing
+  }
+  if (use_graph) {
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      cudaMemsetAsync(off_max, 0, sizeof(float), st);
+      for (int r = 0; r < m - 1; ++r) jacobi_round_kernel<<<m / 2, 256, 0, st>>>(W, V, g, m, r, tol, off_max);
+      if (cudaStreamEndCapture(st, &graph) != cudaSuccess || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+        use_graph = false;
+        (void)cudaGetLastError();
+      }
+    } else {
+      use_graph = false;
+      (void)cudaGetLastError();
+    }
+  }
   int sweep = 0;
   for (; sweep < max_sweeps; ++sweep) {
-    B2_CHECK_CUDA(cudaMemsetAsync(off_max, 0, sizeof(float), st));
-    for (int r = 0; r < m - 1; ++r) {
-      jacobi_round_kernel<<<m / 2, 256, 0, st>>>(W, V, g, m, r, tol, off_max);
-      B2_CHECK_LAUNCH("jacobi_round_kernel");
+    if (use_graph) {
+      B2_CHECK_CUDA(cudaGraphLaunch(exec, st));
+      g_launch_count += (long long)(m - 1);
+    } else {
+      B2_CHECK_CUDA(cudaMemsetAsync(off_max, 0, sizeof(float), st));
+      for (int r = 0; r < m - 1; ++r) {
+        jacobi_round_kernel<<<m / 2, 256, 0, st>>>(W, V, g, m, r, tol, off_max);
+        B2_CHECK_LAUNCH("jacobi_round_kernel");
+      }
     }
     float h = 0.f;
     B2_CHECK_CUDA(cudaMemcpyAsync(&h, off_max, sizeof(float), cudaMemcpyDeviceToHost, st));
     B2_CHECK_CUDA(cudaStreamSynchronize(st));
     if (!(h > tol)) { ++sweep; break; }
   }
+  if (exec) cudaGraphExecDestroy(exec);
+  if (graph) cudaGraphDestroy(graph);
   if (sweeps_done_host) *sweeps_done_host = sweep;
   float* max_norm = off_max + 4;
   B2_CHECK_CUDA(cudaMemsetAsync(max_norm, 0, sizeof(float), st));
