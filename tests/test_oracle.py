@@ -207,3 +207,72 @@ def test_spagcn_golden(golden):
     assert np.allclose(Wc, g["C_W"], rtol=1e-4, atol=1e-6) and np.allclose(bc, g["C_b"], rtol=1e-4, atol=1e-6)
     Wd, bd, mud, _ = port.spagcn_fit(X, adj, g["W0"], g["b0"], g["init_y"], 0.01, 8, update_interval=1, opt="sgd", train_mu=True)
     assert np.allclose(Wd, g["D_W"], rtol=1e-4, atol=1e-6) and np.allclose(mud, g["D_mu"], rtol=1e-4, atol=1e-6)
+
+
+def test_pyg_lite_primitives_against_dense_formulas():
+    """The restated torch_geometric pieces (oracle/pyg_lite.py) against dense per-target formulas."""
+    from oracle import pyg_lite
+    rng = np.random.default_rng(0)
+    n, e = 23, 140
+    src, dst = torch.from_numpy(rng.integers(0, n, e)), torch.from_numpy(rng.integers(0, n, e))
+    ei = torch.stack([src, dst])
+    sc = torch.from_numpy(rng.normal(size=(e, 1)).astype(np.float32))
+    a = pyg_lite.softmax(sc, dst, None, n)
+    for v in range(n):
+        m = dst == v
+        if m.any():
+            ref = torch.softmax(sc[m, 0], 0)
+            assert torch.allclose(a[m, 0], ref, atol=1e-6)
+    x = torch.from_numpy(rng.normal(size=(n, 5)).astype(np.float32))
+
+    class Sum(pyg_lite.MessagePassing):
+
+        def message(self, x_j, w_i):
+            return x_j * w_i
+
+    w = torch.from_numpy(rng.normal(size=(n, 1)).astype(np.float32))
+    out = Sum().propagate(ei, x=x, w=(None, w))
+    dense = torch.zeros(n, n)
+    dense.index_put_((dst, src), torch.ones(e), accumulate=True)          # row = target, column = source
+    assert torch.allclose(out, (dense @ x) * w, atol=1e-5)
+    ei2, _ = pyg_lite.remove_self_loops(torch.tensor([[0, 1, 2], [0, 2, 2]]))
+    assert ei2.tolist() == [[1], [2]]
+    ei3, _ = pyg_lite.add_self_loops(ei2, num_nodes=3)
+    assert ei3.tolist() == [[1, 0, 1, 2], [2, 0, 1, 2]]
+
+
+def test_dgl_lite_graphconv_against_dense_formula():
+    """oracle/dgl_lite.GraphConv(norm="both") = D_in^-1/2 A D_out^-1/2 applied on the side dgl chooses."""
+    from oracle import dgl_lite
+    rng = np.random.default_rng(1)
+    n = 17
+    A = (rng.random((n, n)) < 0.25)
+    np.fill_diagonal(A, True)
+    src, dst = np.nonzero(A)                                             # edge u → v for A[u, v]
+    g = dgl_lite.Graph(src, dst, n)
+    Ad = torch.from_numpy(A.T.astype(np.float32))                        # aggregation matrix: row = destination
+    din = Ad.sum(1).clamp(min=1).pow(-0.5)
+    dout = Ad.sum(0).clamp(min=1).pow(-0.5)
+    for fin, fout in ((9, 4), (4, 9)):
+        conv = dgl_lite.GraphConv(fin, fout, activation=torch.tanh)
+        x = torch.from_numpy(rng.normal(size=(n, fin)).astype(np.float32))
+        if fin <= fout:      # aggregate first, then W
+            ref = torch.tanh(din[:, None] * (Ad @ (dout[:, None] * x)) @ conv.weight + conv.bias)
+        else:                # W first
+            ref = torch.tanh(din[:, None] * (Ad @ ((dout[:, None] * x) @ conv.weight)) + conv.bias)
+        assert torch.allclose(conv(g, x), ref, atol=1e-5)
+    with pytest.raises(RuntimeError):
+        dgl_lite.GraphConv(3, 3)(dgl_lite.Graph([0], [1], 3), torch.zeros(3, 3))
+
+
+def test_stagate_and_graphsci_fixtures_are_self_consistent(golden):
+    """Cheap invariants of the committed fixtures: tied / aliased STAGATE weights, GraphSCI loss bookkeeping."""
+    g = golden("stagate")
+    assert np.array_equal(g["fit.conv3.lin_src"], g["fit.conv2.lin_src"].T) and np.array_equal(g["fit.conv4.lin_src"], g["fit.conv1.lin_src"].T)
+    assert np.array_equal(g["fit.conv2.att_src"], g["init.conv2.att_src"])          # never receives a gradient
+    gn = np.sqrt(sum((g[k].astype(np.float64)**2).sum() for k in g.files if k.startswith("grad.")))
+    assert abs(gn - float(g["grad_norm"])) < 1e-4 * gn
+    s = golden("graphsci")
+    la, le, kl, tr, va = s["e1.losses"]
+    assert abs((la + le - kl) - tr) < 1e-6 * abs(tr)                                # loss = log_lik − kl  (graphsci.py:482-483)
+    assert "grad.gnnmodel.dec_log_std.weight" not in s.files                        # dec_log_std never runs (:129)
