@@ -24,6 +24,40 @@ def test_repr_and_hexdigest():
     assert repr(PCACellFeatureGraph(n_components=100, split_name="train")) == "PCACellFeatureGraph(n_components=100, split_name='train')"
     with pytest.raises(TypeError):
         Compose(t, "not a transform")
+    # the remaining graph / filter transforms of the hot path: repr strings are cache keys (datasets/base.py:129-133)
+    from dance_b200.transforms import (FeatureFeatureGraph, FilterGenesMatch, NeighborGraph, SpaGCNGraph, SpaGCNGraph2D,
+                                       StagateGraph)
+    assert repr(NeighborGraph(n_neighbors=10, n_pcs=None, knn=True, random_state=0, method="umap", metric="euclidean")) == (
+        "NeighborGraph(n_neighbors=10, n_pcs=None, knn=True, random_state=0, method='umap', metric='euclidean')")   # test_basics.py:17-20
+    assert repr(SpaGCNGraph(alpha=1, beta=2)) == "SpaGCNGraph(alpha=1, beta=2)"                                     # test_basics.py:30-32
+    assert repr(SpaGCNGraph2D()) == "SpaGCNGraph2D()"
+    assert repr(StagateGraph("radius", radius=150)) == "StagateGraph(model_name='radius', radius=150, n_neighbors=5)"
+    assert repr(FeatureFeatureGraph(threshold=0.3)) == (
+        "FeatureFeatureGraph(threshold=0.3, positive_only=False, normalize_edges=True, score_func='pearson', score_func_kwargs={})")
+    assert repr(FilterGenesMatch(prefixes=["ERCC", "MT-"])) == "FilterGenesMatch(prefixes=['ERCC', 'MT-'], suffixes=[])"
+    with pytest.raises(ValueError):
+        StagateGraph("delaunay")
+
+
+def test_model_shells_expose_the_reference_surface():
+    """Constructor / method names of the reference models — importable and inspectable without a GPU."""
+    import inspect
+    from dance_b200.modules import graphsci, scdeepsort, scgnn2, spagcn, stagate
+    assert list(inspect.signature(spagcn.SpaGCN.fit).parameters)[:3] == ["self", "x", "y"]
+    for name in ("search_l", "set_l", "calc_adj_exp", "fit", "predict_proba", "predict", "fit_predict", "score", "preprocessing_pipeline"):
+        assert hasattr(spagcn.SpaGCN, name), name
+    for name in ("forward", "pretrain", "save_pretrained", "load_pretrained", "fit", "predict", "fit_score", "preprocessing_pipeline"):
+        assert hasattr(stagate.Stagate, name), name
+    assert list(inspect.signature(graphsci.GraphSCI.__init__).parameters)[1:7] == ["num_cells", "num_genes", "dataset", "dropout", "gpu", "seed"]
+    assert list(inspect.signature(graphsci.GraphSCI.fit).parameters)[1:12] == [
+        "train_data", "train_data_raw", "graph", "mask", "le", "la", "ke", "ka", "n_epochs", "lr", "weight_decay"]
+    assert list(inspect.signature(scdeepsort.ScDeepSort.__init__).parameters)[1:6] == ["dim_in", "dim_hid", "num_layers", "species", "tissue"]
+    assert hasattr(scgnn2, "feature_AE_handler") and hasattr(scgnn2, "graph_AE_handler") and hasattr(scgnn2.ScGNN2, "fit")
+    # no CPU path: constructing a model on a machine without CUDA fails loudly instead of falling back
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):
+            stagate.Stagate([10, 8, 4])
 
 
 def test_data_standin_splits_and_config():
