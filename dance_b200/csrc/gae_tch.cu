@@ -41,7 +41,7 @@ constexpr int STAGE_BYTES = 2 * ZJ_BYTES + 2 * ZT_BYTES;   // 8 KB
 constexpr int GCOLS = BJ / 2;                    // TMEM columns of one packed G tile
 constexpr uint32_t TM_S = 0, TM_GHI = 128, TM_GLO = 192, TM_D = 256, TM_COLS = 512;
 constexpr float G_SCALE = 2048.f;                // σ·2^11 keeps the hi/lo halves of small σ out of the fp16 subnormals
-// dZ accumulators at TM_D + 16·{0: big A, 1: small A, 2: big B, 3: small B}
+// dZ accumulators at TM_D + 16·{0: big A, 1: small A, 2: big B, 3: small B}   (packed variant: 48 columns per parity)
 
 struct Params {
   CUtensorMap mI_hi, mI_lo;      // Z16 [n,16] halves box {16,128} SWIZZLE_32B   (A of the S product)
@@ -55,6 +55,8 @@ struct Params {
   int n, d, row_begin, n_rows, j_chunk, j_splits;
   float coef;
   int stagger; // initial delay (cycles) of the second elementwise group
+  int packed;  // experimental (B2_GAE_PACKED=1, default off: passes the parity test on a B200, not yet timed): dZ with B = [Z_hi | Z_lo] as one
+               // N = 32 operand → 8 instead of 12 tcgen05.mma per tile (hi·hi and hi·lo come out of one instruction)
   int debug;   // timing experiments only (B2_GAE_TC_DEBUG): 1 = skip SFU math, 2 = skip dZ MMAs, 4 = skip S MMAs
 };
 
@@ -197,6 +199,7 @@ gae_allpairs_tch_kernel(const __grid_constant__ Params p) {
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_f16(BI, BJ, 0, 0);   // S  = Z_I (K-major, K = 16) · Z_J (K-major)
       const uint32_t idesc_d = umma_idesc_f16(BI, DW, 0, 0);   // dZ = G (TMEM, K = j) · Z_Jᵀ tile (K-major, N = 16)
+      const uint32_t idesc_d2 = umma_idesc_f16(BI, 2 * DW, 0, 0);   // packed variant: N = 32 over the adjacent hi | lo ZT tiles
       mbar_wait(zi_bar, 0);
       tc_fence_after();
       auto issue_s = [&](int t, int stage, uint32_t phase) {
@@ -236,11 +239,19 @@ gae_allpairs_tch_kernel(const __grid_constant__ Params p) {
           const uint64_t b_hi = umma_desc(zt + (uint32_t)k * 32u, 16, 1024, 2);
           const uint64_t b_lo = umma_desc(zt + ZT_BYTES + (uint32_t)k * 32u, 16, 1024, 2);
           // even / odd k-steps feed independent accumulator pairs (A / B) so consecutive MMAs never wait on each other
-          const uint32_t dbase = tmem + TM_D + (uint32_t)((k & 1) * 32);
           const uint32_t acc = (t > 0 || k > 1) ? 1u : 0u;
-          umma_f16_ts(dbase + 16, g_lo + k * 8, b_hi, idesc_d, acc);   // small: lo·hi
-          umma_f16_ts(dbase, g_hi + k * 8, b_hi, idesc_d, acc);        // big:   hi·hi
-          umma_f16_ts(dbase + 16, g_hi + k * 8, b_lo, idesc_d, 1);     // small: hi·lo
+          if (p.packed) {
+            // the hi and lo ZT tiles are adjacent 16-row K-major tiles (2 KB each, 8-row groups 1 KB apart), i.e. ONE 32-row
+            // operand: G_hi·[Z_hi | Z_lo] yields hi·hi (columns 0-15) and hi·lo (16-31) together; lo·hi stays a N = 16 product
+            const uint32_t dbase = tmem + TM_D + (uint32_t)((k & 1) * 48);
+            umma_f16_ts(dbase, g_hi + k * 8, b_hi, idesc_d2, acc);       // [big | small hi·lo]
+            umma_f16_ts(dbase + 32, g_lo + k * 8, b_hi, idesc_d, acc);   // small lo·hi
+          } else {
+            const uint32_t dbase = tmem + TM_D + (uint32_t)((k & 1) * 32);
+            umma_f16_ts(dbase + 16, g_lo + k * 8, b_hi, idesc_d, acc);   // small: lo·hi
+            umma_f16_ts(dbase, g_hi + k * 8, b_hi, idesc_d, acc);        // big:   hi·hi
+            umma_f16_ts(dbase + 16, g_hi + k * 8, b_lo, idesc_d, 1);     // small: hi·lo
+          }
         }
         umma_commit(g_empty + 8 * b);
         umma_commit(stage_free + 8 * stage_d);
@@ -362,6 +373,19 @@ gae_allpairs_tch_kernel(const __grid_constant__ Params p) {
       tmem_ld_32x32b_x16(tmem + lane_off + TM_D + 16, a1);
       tmem_ld_32x32b_x16(tmem + lane_off + TM_D + 32, a2);
       tmem_ld_32x32b_x16(tmem + lane_off + TM_D + 48, a3);
+      if (p.packed) {
+        // packed layout: parity 0 = [big 0-15 | small 16-31 | small 32-47], parity 1 = the same at +48
+        uint32_t b4[16], b5[16];
+        tmem_ld_32x32b_x16(tmem + lane_off + TM_D + 64, b4);
+        tmem_ld_32x32b_x16(tmem + lane_off + TM_D + 80, b5);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const float big = __uint_as_float(a0[c]) + __uint_as_float(a3[c]);                                          // +0, +48
+          const float small = (__uint_as_float(a1[c]) + __uint_as_float(a2[c])) + (__uint_as_float(b4[c]) + __uint_as_float(b5[c]));   // +16, +32, +64, +80
+          a0[c] = __float_as_uint(big); a2[c] = 0u;
+          a1[c] = __float_as_uint(small); a3[c] = 0u;
+        }
+      }
       if (live && n_tiles > 0) {
         const float c2 = 2.f * p.coef * p.scale[2] * (1.f / G_SCALE);   // undo the ZT and G scales
         float* dst = p.dz + (size_t)row_local * p.d;
@@ -461,6 +485,7 @@ int launch(const float* z, int64_t ldz, int32_t n, int32_t d, int32_t row_begin,
   B2_CHECK_LAUNCH("colrange_sum_kernel");
   p.z = z; p.ldz = ldz; p.zsum = zsum;
   p.stagger = getenv("B2_GAE_STAGGER") ? atoi(getenv("B2_GAE_STAGGER")) : 800;
+  p.packed = getenv("B2_GAE_PACKED") ? atoi(getenv("B2_GAE_PACKED")) : 0;
   p.debug = getenv("B2_GAE_TC_DEBUG") ? atoi(getenv("B2_GAE_TC_DEBUG")) : 0;
   const size_t smem = 2 * ZI_BYTES + STAGES * STAGE_BYTES + 1024 + 256;
   static bool attr_set = false;
