@@ -429,6 +429,8 @@ class GraphSCI:
         if mask is not None:
             mk = torch.as_tensor(np.asarray(mask)[np.asarray(list(test_idx))], device=self.device)
             p = torch.where(mk, t.to(p.dtype), p)
+        else:
+            mk = torch.zeros_like(t, dtype=torch.bool)       # the reference indexes `~mask[...]` and fails for mask=None; score everything
         if metric == "RMSE":
             return float(np.sqrt(torch.mean((t - p)**2).item()))
         tt, pp = t[~mk].cpu(), p[~mk].cpu()
