@@ -160,7 +160,8 @@ int b2_clip_grad_norm_f32(float* grad, int64_t n, float pre_scale, float max_nor
 /* ------------------------------------------------------------------------
  * Elementwise helpers on the GCN path
  * ---------------------------------------------------------------------- */
-/* out = grad ⊙ (y > 0)   (ReLU backward; in-place allowed) */
+/* out = grad ⊙ (y > 0)   (backward of F.relu in GraphConvolution / Graph_AE, scgnn2.py:388,497-502, and of nn.ReLU in
+ * graphsci.py:37-45,85-87; in-place allowed) */
 int b2_relu_bwd_f32(const float* grad, const float* y, float* out, int64_t n, void* stream);
 /* z = mu + eps ⊙ exp(logvar)  (Graph_AE.reparameterize, scgnn2.py:394-400); [n,d] with leading dims */
 int b2_reparam_fwd_f32(const float* mu, const float* logvar, int64_t ldm, const float* eps, int64_t lde,
