@@ -13,12 +13,83 @@ import torch
 import torch.nn as nn
 
 
-class Graph:
+class _EdgeBatch:
+    """What a dgl message UDF receives: ``edges.src[k]`` / ``edges.dst[k]`` (node data gathered per edge), ``edges.data[k]``."""
 
-    def __init__(self, src, dst, num_nodes):
+    def __init__(self, g):
+        self.src = {k: v[g.src] for k, v in g.srcdata.items()}
+        self.dst = {k: v[g.dst] for k, v in g.dstdata.items()}
+        self.data = dict(g.edata)
+
+
+class _Mean:
+    """``dgl.function.mean(msg, out)``: out[v] = mean of the messages on v's in-edges, 0 for in-degree 0."""
+
+    def __init__(self, msg, out):
+        self.msg, self.out = msg, out
+
+
+class function:   # noqa: N801  (mirrors the ``dgl.function`` namespace)
+    mean = _Mean
+
+
+class Graph:
+    """COO multigraph; edge id = position (``dgl.graph((src, dst))``).  Used as a full-graph "block" too: source and destination
+    node sets are both all nodes, so ``srcdata`` / ``dstdata`` alias ``ndata`` and ``number_of_dst_nodes() == num_nodes()``."""
+
+    def __init__(self, src, dst, num_nodes=None):
         self.src, self.dst = torch.as_tensor(src).long(), torch.as_tensor(dst).long()
-        self.n = int(num_nodes)
+        self.n = int(num_nodes) if num_nodes is not None else int(max(self.src.max(), self.dst.max())) + 1
         self.ndata, self.edata = {}, {}
+
+    # --- the extra surface cell_feature_graph.py:53-69 and models/nn/gnn.py:84-96 touch ---
+    @property
+    def srcdata(self):
+        return self.ndata
+
+    @property
+    def dstdata(self):
+        return self.ndata
+
+    def number_of_nodes(self):
+        return self.n
+
+    def number_of_dst_nodes(self):
+        return self.n
+
+    def nodes(self):
+        return torch.arange(self.n)
+
+    def in_edges(self, i, form="uv"):
+        eid = torch.nonzero(self.dst == int(i)).flatten()            # ascending edge id, like dgl
+        return (self.src[eid], self.dst[eid], eid) if form == "all" else (self.src[eid], self.dst[eid])
+
+    def add_edges(self, u, v, data=None):
+        u, v = torch.as_tensor(u).long(), torch.as_tensor(v).long()
+        for k, val in self.edata.items():                               # missing keys are zero-filled by dgl
+            add = data[k].to(val.dtype) if data and k in data else torch.zeros((u.numel(), ) + tuple(val.shape[1:]), dtype=val.dtype)
+            self.edata[k] = torch.cat([val, add])
+        self.src, self.dst = torch.cat([self.src, u]), torch.cat([self.dst, v])
+
+    def local_scope(self):
+        import contextlib
+
+        @contextlib.contextmanager
+        def scope():
+            saved_n, saved_e = dict(self.ndata), dict(self.edata)
+            try:
+                yield
+            finally:
+                self.ndata, self.edata = saved_n, saved_e
+
+        return scope()
+
+    def update_all(self, message_func, reduce_func):
+        msgs = message_func(_EdgeBatch(self))
+        m = msgs[reduce_func.msg]
+        out = torch.zeros((self.n, ) + tuple(m.shape[1:]), dtype=m.dtype).index_add(0, self.dst, m)
+        deg = torch.bincount(self.dst, minlength=self.n).clamp(min=1).to(m.dtype)
+        self.ndata[reduce_func.out] = out / deg.view(-1, *([1] * (m.dim() - 1)))
 
     def edges(self):
         return self.src.int(), self.dst.int()

@@ -366,15 +366,51 @@ def _graphsci_fixture():
     np.savez_compressed(OUT / "graphsci.npz", **out)
 
 
+def _cellgene_fixture():
+    """scDeepSort front end: the reference's own CellFeatureGraph.__call__ (cell_feature_graph.py:34-79) and
+    AdaptiveSAGE.message_func / forward (models/nn/gnn.py:62-96) running on oracle/dgl_lite.py (dgl itself is absent)."""
+    from dance_b200.data import AnnDataLite, Data       # host-side stand-ins for AnnData / dance.data.Data (no kernels involved)
+    from . import dgl_lite
+    cfg = ref_loader.cell_feature_graph()
+    gnn = ref_loader.gnn()
+    rng = np.random.default_rng(31)
+    n, g, c = 37, 19, 6
+    X = (rng.random((n, g)) < 0.3) * rng.gamma(2.0, 1.5, size=(n, g))
+    X[5] = 0            # a cell without expressed genes
+    X[:, 7] = 0         # a gene nobody expresses
+    X = X.astype(np.float32)
+    gene_feat = rng.normal(size=(g, c)).astype(np.float32)
+    cell_feat = rng.normal(size=(n, c)).astype(np.float32)
+    out = dict(X=X, gene_feat=gene_feat, cell_feat=cell_feat)
+    for norm, tag in ((True, "norm"), (False, "raw")):
+        data = Data(AnnDataLite(X.copy(), obsm={"f": cell_feat}, varm={"f": gene_feat}))
+        cfg.CellFeatureGraph(cell_feature_channel="f", normalize_edges=norm)(data)
+        gr = data.data.uns["CellFeatureGraph"]
+        out.update({f"{tag}.src": gr.src.numpy(), f"{tag}.dst": gr.dst.numpy(), f"{tag}.w": gr.edata["weight"].numpy()})
+        if norm:
+            out.update(cell_id=gr.ndata["cell_id"].numpy(), feat_id=gr.ndata["feat_id"].numpy(), features=gr.ndata["features"].numpy())
+            graph = gr
+    # AdaptiveSAGE on the full graph (every node is a destination): message_func + fn.mean, then the layer output
+    torch.manual_seed(3)
+    alpha = torch.nn.Parameter(torch.rand(g + 2, 1) + 0.5)
+    layer = gnn.AdaptiveSAGE(c, 5, alpha, torch.nn.Dropout(0.0), torch.nn.ReLU(), torch.nn.Identity())
+    h = graph.ndata["features"]
+    graph.ndata["h"] = h
+    graph.update_all(layer.message_func, dgl_lite.function.mean("m", "neigh"))
+    out.update(alpha=alpha.detach().numpy(), neigh=graph.ndata["neigh"].detach().numpy(), sage_weight=layer.layers[1].weight.detach().numpy(),
+               sage_bias=layer.layers[1].bias.detach().numpy(), sage_out=layer(graph, h).detach().numpy())
+    np.savez_compressed(OUT / "cellgene.npz", **out)
+
+
 def main():
     import sys
     OUT.mkdir(parents=True, exist_ok=True)
-    only = [a for a in sys.argv[1:] if a in ("spagcn", "stagate", "graphsci")]
+    only = [a for a in sys.argv[1:] if a in ("spagcn", "stagate", "graphsci", "cellgene")]
     if only:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             for a in only:
-                {"spagcn": _spagcn_fixture, "stagate": _stagate_fixture, "graphsci": _graphsci_fixture}[a]()
+                {"spagcn": _spagcn_fixture, "stagate": _stagate_fixture, "graphsci": _graphsci_fixture, "cellgene": _cellgene_fixture}[a]()
         return
     ref = ref_loader.scgnn2()
     with warnings.catch_warnings():
@@ -387,6 +423,7 @@ def main():
         _spagcn_fixture()
         _stagate_fixture()
         _graphsci_fixture()
+        _cellgene_fixture()
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)
 

@@ -145,3 +145,42 @@ def graphsci():
     _stub("dance.transforms.graph", FeatureFeatureGraph=dummy, StagateGraph=dummy, SpaGCNGraph=dummy, SpaGCNGraph2D=dummy)
     _stub("dance.transforms.misc", UpdateRaw=dummy)
     return _load("dance_ref_graphsci", "dance/modules/single_modality/imputation/graphsci.py")
+
+
+def _dgl_stub():
+    from . import dgl_lite
+    _stub("dgl", graph=lambda data, num_nodes=None: dgl_lite.Graph(data[0], data[1], num_nodes), function=dgl_lite.function)
+    _stub("dgl.nn", GraphConv=dgl_lite.GraphConv)
+    _stub("dgl.function", mean=dgl_lite.function.mean)
+
+
+def cell_feature_graph():
+    """The reference's ``dance/transforms/graph/cell_feature_graph.py`` (CellFeatureGraph.__call__) on ``oracle/dgl_lite.Graph``.
+    ``dance.transforms.base`` is stubbed with a minimal BaseTransform (the real one imports anndata)."""
+    if "dance_ref_cell_feature_graph" in sys.modules:
+        return sys.modules["dance_ref_cell_feature_graph"]
+    _install_stubs()
+    _dgl_stub()
+
+    class BaseTransform:
+        _DISPLAY_ATTRS = ()
+
+        def __init__(self, out=None, log_level="WARNING"):
+            self.out = out or type(self).__name__
+            self.logger = logging.getLogger("dance-ref-stub")
+            self.log_level = log_level
+
+    _stub("dance.registry", register_preprocessor=lambda *a, **k: (lambda cls: cls))
+    _stub("dance.transforms")
+    _stub("dance.transforms.base", BaseTransform=BaseTransform)
+    _stub("dance.transforms.cell_feature", WeightedFeaturePCA=type("WeightedFeaturePCA", (), {}))
+    return _load("dance_ref_cell_feature_graph", "dance/transforms/graph/cell_feature_graph.py")
+
+
+def gnn():
+    """The reference's ``dance/models/nn/gnn.py`` (AdaptiveSAGE) with ``dgl.function.mean`` / ``update_all`` from dgl_lite."""
+    if "dance_ref_gnn" in sys.modules:
+        return sys.modules["dance_ref_gnn"]
+    _install_stubs()
+    _dgl_stub()
+    return _load("dance_ref_gnn", "dance/models/nn/gnn.py")

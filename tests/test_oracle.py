@@ -276,3 +276,24 @@ def test_stagate_and_graphsci_fixtures_are_self_consistent(golden):
     la, le, kl, tr, va = s["e1.losses"]
     assert abs((la + le - kl) - tr) < 1e-6 * abs(tr)                                # loss = log_lik − kl  (graphsci.py:482-483)
     assert "grad.gnnmodel.dec_log_std.weight" not in s.files                        # dec_log_std never runs (:129)
+
+
+def test_cellgene_and_adaptive_sage_golden(golden):
+    """port.cell_feature_graph / adaptive_sage_neighbour_mean / ScDeepSortNet against the reference's own CellFeatureGraph
+    and AdaptiveSAGE code (run on oracle/dgl_lite.py by make_golden) — the restatements the GPU tests compare with."""
+    g = golden("cellgene")
+    X = g["X"]
+    n, G = X.shape
+    for norm, tag in ((True, "norm"), (False, "raw")):
+        src, dst, w = port.cell_feature_graph(X, normalize_edges=norm)
+        assert np.array_equal(src.numpy(), g[f"{tag}.src"]) and np.array_equal(dst.numpy(), g[f"{tag}.dst"])      # edge list + order
+        assert np.allclose(w.numpy(), g[f"{tag}.w"], rtol=1e-6, atol=0)
+    assert np.array_equal(g["cell_id"], np.concatenate([np.arange(G), -np.ones(n)]).astype(np.int32))          # the naming quirk (:56-59)
+    assert np.array_equal(g["feat_id"], np.concatenate([-np.ones(G), np.arange(n)]).astype(np.int32))
+    assert np.array_equal(g["features"], np.vstack([g["gene_feat"], g["cell_feat"]]))
+    src, dst, w = (torch.from_numpy(g[f"norm.{k}"]) for k in ("src", "dst", "w"))
+    neigh = port.adaptive_sage_neighbour_mean(src, dst, w, torch.from_numpy(g["features"]), torch.from_numpy(g["alpha"]), G)
+    assert np.allclose(neigh.numpy(), g["neigh"], rtol=1e-5, atol=1e-6)
+    # the layer output ignores the aggregate (SURVEY App. B): Linear → ReLU on the destination features only
+    z = torch.relu(torch.from_numpy(g["features"]) @ torch.from_numpy(g["sage_weight"]).T + torch.from_numpy(g["sage_bias"]))
+    assert np.allclose(z.numpy(), g["sage_out"], rtol=1e-5, atol=1e-6)
