@@ -427,7 +427,8 @@ def main():
         ach = dec_flops / (dec_total * 1e-3) / 1e12 if dec_total else 0.0
         roofline = {"kernel": "gae_allpairs_tch_kernel (matrix-free z·zᵀ BCE decoder: tcgen05 kind::f16 hi/lo split, S and G in TMEM)",
                     "bound": "tensor", "achieved": ach,
-                    "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": None,
+                    "peak": peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": ach / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]), "traffic": None,
                     "launches": dec_n, "ms_total": dec_total, "peak_source": peaks["source"],
                     "note": "dominant kernel of the step; algorithmic flops = the two K=16 products per logit (S and G·Z). Its real ceiling is "
                             "the per-logit elementwise work (2 MUFU + 9 ALU instructions on 16 warps, ncu: issue 58 %, XU 58 %), not the tensor "
