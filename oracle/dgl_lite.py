@@ -25,12 +25,26 @@ class _EdgeBatch:
 class _Mean:
     """``dgl.function.mean(msg, out)``: out[v] = mean of the messages on v's in-edges, 0 for in-degree 0."""
 
-    def __init__(self, msg, out):
+    def __init__(self, msg, out):          # called as fn.mean("m", "neigh") and fn.sum(msg="m", out="h")
         self.msg, self.out = msg, out
+
+
+class _Sum(_Mean):
+    """``dgl.function.sum(msg, out)``."""
 
 
 class function:   # noqa: N801  (mirrors the ``dgl.function`` namespace)
     mean = _Mean
+    sum = _Sum
+
+
+class DGLError(Exception):
+    pass
+
+
+def expand_as_pair(feat, graph=None):
+    """dgl.utils.expand_as_pair for homogeneous graphs / full-graph blocks: the same tensor on both sides."""
+    return (feat, feat) if not isinstance(feat, tuple) else feat
 
 
 class Graph:
@@ -53,6 +67,9 @@ class Graph:
 
     def number_of_nodes(self):
         return self.n
+
+    def to(self, device):
+        return self
 
     def number_of_dst_nodes(self):
         return self.n
@@ -88,8 +105,10 @@ class Graph:
         msgs = message_func(_EdgeBatch(self))
         m = msgs[reduce_func.msg]
         out = torch.zeros((self.n, ) + tuple(m.shape[1:]), dtype=m.dtype).index_add(0, self.dst, m)
-        deg = torch.bincount(self.dst, minlength=self.n).clamp(min=1).to(m.dtype)
-        self.ndata[reduce_func.out] = out / deg.view(-1, *([1] * (m.dim() - 1)))
+        if not isinstance(reduce_func, _Sum):
+            deg = torch.bincount(self.dst, minlength=self.n).clamp(min=1).to(m.dtype)
+            out = out / deg.view(-1, *([1] * (m.dim() - 1)))
+        self.ndata[reduce_func.out] = out
 
     def edges(self):
         return self.src.int(), self.dst.int()
@@ -111,8 +130,10 @@ class GraphConv(nn.Module):
 
     def __init__(self, in_feats, out_feats, norm="both", weight=True, bias=True, activation=None, allow_zero_in_degree=False):
         super().__init__()
-        assert norm == "both" and weight and bias
+        assert norm in ("both", "right", "none") and weight and bias
         self._in, self._out, self._act, self._allow = in_feats, out_feats, activation, allow_zero_in_degree
+        # attribute names of dgl.nn.pytorch.GraphConv that the in-tree WeightedGraphConv subclass reads (graphsc.py:428-484)
+        self._norm, self._allow_zero_in_degree, self._activation = norm, allow_zero_in_degree, activation
         self.weight = nn.Parameter(torch.Tensor(in_feats, out_feats))
         self.bias = nn.Parameter(torch.Tensor(out_feats))
         nn.init.xavier_uniform_(self.weight)
@@ -131,3 +152,92 @@ class GraphConv(nn.Module):
         rst = rst * graph.in_degrees().to(feat).clamp(min=1).pow(-0.5)[:, None]
         rst = rst + self.bias
         return self._act(rst) if self._act is not None else rst
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# dgl.dataloading surface used by scdeepsort.py:183,233-236,270-272,321-322: full-neighbourhood blocks over "in" edges
+# ---------------------------------------------------------------------------------------------------------------
+class Block:
+    """Message-flow block of ``NeighborSampler(fanouts=[-1], edge_dir="in")`` for the seed nodes ``dst_nodes``: all their
+    in-edges; source nodes = the seeds first (dgl's convention, AdaptiveSAGE relies on it at gnn.py:87), then the remaining
+    neighbours; node / edge data are sliced from the parent graph."""
+
+    def __init__(self, g: Graph, dst_nodes):
+        dst_nodes = torch.as_tensor(dst_nodes).long()
+        pos = torch.full((g.n, ), -1, dtype=torch.long)
+        pos[dst_nodes] = torch.arange(dst_nodes.numel())
+        eid = torch.nonzero(pos[g.dst] >= 0).flatten()
+        extra = torch.unique(g.src[eid])
+        extra = extra[pos[extra] < 0]
+        self.src_nodes = torch.cat([dst_nodes, extra])
+        spos = torch.full((g.n, ), -1, dtype=torch.long)
+        spos[self.src_nodes] = torch.arange(self.src_nodes.numel())
+        self.dst_nodes = dst_nodes
+        self.src, self.dst = spos[g.src[eid]], pos[g.dst[eid]]
+        self.srcdata = {k: v[self.src_nodes] for k, v in g.ndata.items()}
+        self.dstdata = {k: v[dst_nodes] for k, v in g.ndata.items()}
+        self.edata = {k: v[eid] for k, v in g.edata.items()}
+        self.n_dst = dst_nodes.numel()
+
+    def to(self, device):
+        return self
+
+    def number_of_dst_nodes(self):
+        return self.n_dst
+
+    num_dst_nodes = number_of_dst_nodes
+
+    def local_scope(self):
+        import contextlib
+
+        @contextlib.contextmanager
+        def scope():
+            saved = dict(self.srcdata), dict(self.dstdata), dict(self.edata)
+            try:
+                yield
+            finally:
+                self.srcdata, self.dstdata, self.edata = saved
+
+        return scope()
+
+    def update_all(self, message_func, reduce_func):
+        msgs = message_func(_EdgeBatch(self))
+        m = msgs[reduce_func.msg]
+        out = torch.zeros((self.n_dst, ) + tuple(m.shape[1:]), dtype=m.dtype).index_add(0, self.dst, m)
+        if not isinstance(reduce_func, _Sum):
+            deg = torch.bincount(self.dst, minlength=self.n_dst).clamp(min=1).to(m.dtype)
+            out = out / deg.view(-1, *([1] * (m.dim() - 1)))
+        self.dstdata[reduce_func.out] = out
+
+
+class NeighborSampler:
+
+    def __init__(self, fanouts, edge_dir="in"):
+        assert all(f == -1 for f in fanouts) and edge_dir == "in", "only full in-neighbourhoods are restated"
+        self.n_layers = len(fanouts)
+
+
+class DataLoader:
+    """Seeds are visited in ``torch.randperm`` order when ``shuffle`` (global torch RNG) and recorded in ``DataLoader.history``
+    so that a fixture can replay exactly the batches the reference saw.  Yields (input_nodes, output_nodes, blocks)."""
+
+    history = []
+
+    def __init__(self, graph, indices, graph_sampler, batch_size=1, shuffle=False, num_workers=0, **kwargs):
+        self.g, self.idx, self.sampler, self.bs, self.shuffle = graph, torch.as_tensor(indices).long(), graph_sampler, batch_size, shuffle
+
+    def enable_cpu_affinity(self):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def __iter__(self):
+        order = self.idx[torch.randperm(self.idx.numel())] if self.shuffle else self.idx
+        for i in range(0, order.numel(), self.bs):
+            seeds = order[i:i + self.bs]
+            DataLoader.history.append(seeds.clone())
+            blocks, cur = [], seeds
+            for _ in range(self.sampler.n_layers):          # outermost layer last in the list, like dgl
+                b = Block(self.g, cur)
+                blocks.insert(0, b)
+                cur = b.src_nodes
+            yield cur, seeds, blocks

@@ -402,15 +402,112 @@ def _cellgene_fixture():
     np.savez_compressed(OUT / "cellgene.npz", **out)
 
 
+def _scdeepsort_fixture():
+    """scDeepSort training: the reference's own ScDeepSort.fit / cal_loss / evaluate / predict_proba (scdeepsort.py:142-349) with
+    its GNN + AdaptiveSAGE, running on oracle/dgl_lite.py (graph, full-neighbourhood blocks, dataloader).  The batches the
+    reference saw are recorded so that the restatement / the GPU module can replay them."""
+    import contextlib
+    import io
+    import os
+    import tempfile
+    from . import dgl_lite
+    ref = ref_loader.scdeepsort()
+    rng = np.random.default_rng(41)
+    n, g, c, hid, n_lab, bs = 90, 30, 8, 7, 4, 16
+    lab = rng.integers(0, n_lab, n)
+    X = ((rng.random((n, g)) < 0.3) * rng.gamma(2.0, 1.5, size=(n, g))).astype(np.float32)
+    X[np.arange(n), lab * 5] += 3.0                                   # a label-specific marker gene: something to learn
+    src, dst, w = port.cell_feature_graph(X, True)
+    feats = rng.normal(size=(n + g, c)).astype(np.float32)
+    feats[g:] += np.eye(n_lab, c, dtype=np.float32)[lab] * 2.0
+    out = dict(X=X, feats=feats, labels=lab, src=src.numpy(), dst=dst.numpy(), w=w.numpy(), hid=hid, batch_size=bs)
+
+    def graph():
+        gr = dgl_lite.Graph(src, dst, n + g)
+        gr.edata["weight"] = w.clone()
+        gr.ndata["cell_id"] = torch.cat([torch.arange(g, dtype=torch.int32), -torch.ones(n, dtype=torch.int32)])
+        gr.ndata["features"] = torch.from_numpy(feats)
+        return gr
+
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                torch.manual_seed(9)
+                m0 = ref.ScDeepSort(c, hid, 1, "sp", "ti", batch_size=bs)
+                try:
+                    m0.fit(graph(), torch.from_numpy(lab), epochs=0, lr=1e-2)         # builds the model: initial weights …
+                except UnboundLocalError:
+                    pass                                                              # … then trips over its own summary print (:204-207)
+                for k, v in m0.model.state_dict().items():
+                    out["init." + k] = v.numpy().copy()
+                torch.manual_seed(9)
+                dgl_lite.DataLoader.history = []
+                m = ref.ScDeepSort(c, hid, 1, "sp", "ti", batch_size=bs)
+                snaps, losses = [], []
+                orig = m.cal_loss
+
+                def cal_loss(graph_, idx):
+                    start = len(dgl_lite.DataLoader.history)
+                    loss = orig(graph_, idx)
+                    snaps.append(([b.numpy().copy() for b in dgl_lite.DataLoader.history[start:]],
+                                  {k: v.numpy().copy() for k, v in m.model.state_dict().items()}))
+                    losses.append(loss)
+                    return loss
+
+                m.cal_loss = cal_loss
+                m.fit(graph(), torch.from_numpy(lab), epochs=3, lr=1e-2, weight_decay=1e-4, val_ratio=0.2)
+                prob = m.predict_proba(graph())
+                pred, unsure = m.predict(graph(), unsure_rate=1.2, return_unsure=True)
+        finally:
+            os.chdir(cwd)
+    out["losses"] = np.array(losses)
+    for e, (batches, sd) in enumerate(snaps):
+        out[f"e{e}.n_batches"] = len(batches)
+        for b, idx in enumerate(batches):
+            out[f"e{e}.batch{b}"] = idx
+        for k, v in sd.items():
+            out[f"e{e}.{k}"] = v
+    for k, v in m.model.state_dict().items():
+        out["best." + k] = v.numpy().copy()
+    out.update(prob=prob, pred=pred, unsure=unsure)
+    np.savez_compressed(OUT / "scdeepsort.npz", **out)
+
+
+def _graphsc_conv_fixture():
+    """graph-sc's in-tree WeightedGraphConv (graphsc.py:414-484) — the reference class itself, on oracle/dgl_lite.py."""
+    from . import dgl_lite
+    ref = ref_loader.graphsc()
+    rng = np.random.default_rng(51)
+    n, fin, fout = 40, 9, 5
+    src = np.concatenate([rng.integers(0, n, 150), np.arange(n)])
+    dst = np.concatenate([rng.integers(0, n, 150), np.arange(n)])
+    w_e = rng.uniform(0.1, 2.0, size=(len(src), 1)).astype(np.float32)
+    x = rng.normal(size=(n, fin)).astype(np.float32)
+    out = dict(src=src, dst=dst, w_e=w_e, x=x)
+    for norm in ("both", "right", "none"):
+        torch.manual_seed(1)
+        conv = ref.WeightedGraphConv(fin, fout, norm=norm, activation=torch.relu)
+        with torch.no_grad():
+            conv.bias.copy_(torch.linspace(-0.2, 0.2, fout))
+        gr = dgl_lite.Graph(src, dst, n)
+        gr.edata["weight"] = torch.from_numpy(w_e)
+        out[f"{norm}.W"], out[f"{norm}.b"] = conv.weight.detach().numpy().copy(), conv.bias.detach().numpy().copy()
+        for agg in ("sum", "mean"):
+            out[f"{norm}.{agg}"] = conv(gr, torch.from_numpy(x), agg=agg).detach().numpy()
+    np.savez_compressed(OUT / "graphsc_conv.npz", **out)
+
+
 def main():
     import sys
     OUT.mkdir(parents=True, exist_ok=True)
-    only = [a for a in sys.argv[1:] if a in ("spagcn", "stagate", "graphsci", "cellgene")]
+    only = [a for a in sys.argv[1:] if a in ("spagcn", "stagate", "graphsci", "cellgene", "scdeepsort", "graphsc_conv")]
     if only:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             for a in only:
-                {"spagcn": _spagcn_fixture, "stagate": _stagate_fixture, "graphsci": _graphsci_fixture, "cellgene": _cellgene_fixture}[a]()
+                {"spagcn": _spagcn_fixture, "stagate": _stagate_fixture, "graphsci": _graphsci_fixture, "cellgene": _cellgene_fixture, "scdeepsort": _scdeepsort_fixture, "graphsc_conv": _graphsc_conv_fixture}[a]()
         return
     ref = ref_loader.scgnn2()
     with warnings.catch_warnings():
@@ -424,6 +521,8 @@ def main():
         _stagate_fixture()
         _graphsci_fixture()
         _cellgene_fixture()
+        _scdeepsort_fixture()
+        _graphsc_conv_fixture()
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)
 

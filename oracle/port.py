@@ -483,6 +483,27 @@ def feature_feature_graph(feat: np.ndarray, threshold: float = 0.3, positive_onl
     return src, dst, w.numpy(), adj
 
 
+def weighted_graphconv(x, src, dst, w_e, W, b, norm: str = "both", agg: str = "sum", act=None):
+    """graph-sc's in-tree WeightedGraphConv.forward (modules/single_modality/clustering/graphsc.py:428-484): out-degree^-1/2 on
+    the sources (norm="both"), W first, messages h_src·w_e, sum | mean over in-edges, in-degree scaling, bias, activation.
+    Degrees are structural (edge counts, clamped to 1).  torch tensors; src/dst int64, w_e [E] or [E,1]."""
+    n = x.shape[0]
+    indeg = torch.bincount(dst, minlength=n).float().clamp(min=1)
+    outdeg = torch.bincount(src, minlength=n).float().clamp(min=1)
+    h = x
+    if norm == "both":
+        h = h * outdeg.pow(-0.5)[:, None]
+    h = h @ W
+    m = h[src] * w_e.reshape(-1, 1)
+    rst = torch.zeros(n, W.shape[1], dtype=h.dtype).index_add(0, dst, m)
+    if agg == "mean":
+        rst = rst / indeg[:, None]
+    if norm != "none":
+        rst = rst * (indeg.pow(-0.5) if norm == "both" else 1.0 / indeg)[:, None]
+    rst = rst + b
+    return act(rst) if act is not None else rst
+
+
 def umap_connectivities(knn_idx: np.ndarray, knn_dist: np.ndarray) -> sp.csr_matrix:
     """scanpy 1.10.1 ``_connectivity.umap`` → umap-learn 0.5 ``fuzzy_simplicial_set(set_op_mix_ratio=1,
     local_connectivity=1)`` restated loop by loop (smooth_knn_dist, compute_membership_strengths, fuzzy union);

@@ -152,6 +152,12 @@ def _dgl_stub():
     _stub("dgl", graph=lambda data, num_nodes=None: dgl_lite.Graph(data[0], data[1], num_nodes), function=dgl_lite.function)
     _stub("dgl.nn", GraphConv=dgl_lite.GraphConv)
     _stub("dgl.function", mean=dgl_lite.function.mean)
+    _stub("dgl.dataloading", DataLoader=dgl_lite.DataLoader, NeighborSampler=dgl_lite.NeighborSampler)
+    _stub("dgl.nn.pytorch", GraphConv=dgl_lite.GraphConv)
+    _stub("dgl.utils", expand_as_pair=dgl_lite.expand_as_pair)
+    sys.modules["dgl"].DGLGraph = dgl_lite.Graph
+    sys.modules["dgl"].DGLError = dgl_lite.DGLError
+    sys.modules["dgl.function"].sum = dgl_lite.function.sum
 
 
 def cell_feature_graph():
@@ -184,3 +190,43 @@ def gnn():
     _install_stubs()
     _dgl_stub()
     return _load("dance_ref_gnn", "dance/models/nn/gnn.py")
+
+
+def scdeepsort():
+    """The reference's ``dance/modules/single_modality/cell_type_annotation/scdeepsort.py`` (GNN, ScDeepSort.fit / cal_loss /
+    evaluate / predict_proba) with its own AdaptiveSAGE, on the dgl_lite graph / block / dataloader surface."""
+    if "dance_ref_scdeepsort" in sys.modules:
+        return sys.modules["dance_ref_scdeepsort"]
+    _install_stubs()
+    _dgl_stub()
+    _stub("dance.models")
+    _stub("dance.models.nn", AdaptiveSAGE=gnn().AdaptiveSAGE)
+    _stub("dance.modules")
+    _stub("dance.modules.base", BaseClassificationMethod=type("BaseClassificationMethod", (), {}),
+          BaseRegressionMethod=type("BaseRegressionMethod", (), {}), BaseClusteringMethod=type("B", (), {}), BasePretrain=type("P", (), {}))
+    dummy = type("Dummy", (), {"__init__": lambda self, *a, **k: None})
+    _stub("dance.transforms", Compose=dummy, SetConfig=dummy, AnnDataTransform=dummy, CellPCA=dummy, FilterGenesMatch=dummy)
+    _stub("dance.transforms.graph", PCACellFeatureGraph=dummy, StagateGraph=dummy, SpaGCNGraph=dummy, SpaGCNGraph2D=dummy,
+          FeatureFeatureGraph=dummy)
+    return _load("dance_ref_scdeepsort", "dance/modules/single_modality/cell_type_annotation/scdeepsort.py")
+
+
+def graphsc():
+    """The reference's ``dance/modules/single_modality/clustering/graphsc.py`` — used for its in-tree ``WeightedGraphConv``
+    (:414-484, a subclass of dgl's GraphConv) and ``InnerProductDecoder`` (:386-411)."""
+    if "dance_ref_graphsc" in sys.modules:
+        return sys.modules["dance_ref_graphsc"]
+    _install_stubs()
+    _dgl_stub()
+    _stub("scanpy", pp=types.SimpleNamespace(), tl=types.SimpleNamespace(), AnnData=object)
+    _stub("dance.modules")
+    _stub("dance.modules.base", BaseClusteringMethod=type("BaseClusteringMethod", (), {}), BaseClassificationMethod=type("C", (), {}),
+          BaseRegressionMethod=type("R", (), {}), BasePretrain=type("P", (), {}))
+    dummy = type("Dummy", (), {"__init__": lambda self, *a, **k: None})
+    _stub("dance.transforms", Compose=dummy, SetConfig=dummy, AnnDataTransform=dummy, CellPCA=dummy, FilterGenesMatch=dummy)
+    _stub("dance.transforms.graph", PCACellFeatureGraph=dummy, StagateGraph=dummy, SpaGCNGraph=dummy, SpaGCNGraph2D=dummy,
+          FeatureFeatureGraph=dummy)
+    typing_mod = sys.modules["dance.typing"]
+    if not hasattr(typing_mod, "Literal"):
+        typing_mod.Literal = typing.Literal
+    return _load("dance_ref_graphsc", "dance/modules/single_modality/clustering/graphsc.py")

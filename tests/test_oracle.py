@@ -297,3 +297,50 @@ def test_cellgene_and_adaptive_sage_golden(golden):
     # the layer output ignores the aggregate: Linear → ReLU on the destination features only
     z = torch.relu(torch.from_numpy(g["features"]) @ torch.from_numpy(g["sage_weight"]).T + torch.from_numpy(g["sage_bias"]))
     assert np.allclose(z.numpy(), g["sage_out"], rtol=1e-5, atol=1e-6)
+
+
+def test_scdeepsort_training_golden(golden):
+    """port.ScDeepSortNet / scdeepsort_epoch replaying the batches the reference's own ScDeepSort.fit saw (run on
+    oracle/dgl_lite.py by make_golden): per-epoch loss and weights, the alpha that never trains, final probabilities."""
+    g = golden("scdeepsort")
+    feats, lab = torch.from_numpy(g["feats"]), g["labels"]
+    n, G = g["X"].shape
+    c, hid, n_lab = feats.shape[1], int(g["hid"]), int(lab.max()) + 1
+    net = port.ScDeepSortNet(c, hid, n_lab, G)
+    with torch.no_grad():
+        net.sage_linear.weight.copy_(torch.from_numpy(g["init.layers.0.layers.1.weight"]))
+        net.sage_linear.bias.copy_(torch.from_numpy(g["init.layers.0.layers.1.bias"]))
+        net.linear.weight.copy_(torch.from_numpy(g["init.linear.weight"]))
+        net.linear.bias.copy_(torch.from_numpy(g["init.linear.bias"]))
+    assert np.array_equal(g["init.alpha"], np.ones((G + 2, 1), np.float32))
+    full_labels = torch.cat([-torch.ones(G, dtype=torch.long), torch.from_numpy(lab).long()])
+    # Adam over the parameters that receive gradients (alpha has none: torch skips it; weight decay never touches it either)
+    opt = torch.optim.Adam([net.sage_linear.weight, net.sage_linear.bias, net.linear.weight, net.linear.bias], lr=1e-2, weight_decay=1e-4)
+    for e in range(3):
+        batches = [g[f"e{e}.batch{b}"] for b in range(int(g[f"e{e}.n_batches"]))]
+        loss = port.scdeepsort_epoch(net, opt, feats, full_labels, batches)
+        assert abs(loss - float(g["losses"][e])) < 1e-5 * abs(float(g["losses"][e]))
+        assert np.allclose(net.sage_linear.weight.detach().numpy(), g[f"e{e}.layers.0.layers.1.weight"], rtol=1e-4, atol=1e-6)
+        assert np.allclose(net.linear.weight.detach().numpy(), g[f"e{e}.linear.weight"], rtol=1e-4, atol=1e-6)
+        assert np.array_equal(g[f"e{e}.alpha"], g["init.alpha"])                     # the aggregate is discarded → no gradient
+    # the reference reloads its best-validation state; with the restatement's weights at that epoch the probabilities agree
+    best = [e for e in range(3) if np.array_equal(g[f"e{e}.linear.weight"], g["best.linear.weight"])]
+    assert best, "best state must be one of the epoch snapshots"
+    with torch.no_grad():
+        w1, b1 = torch.from_numpy(g["best.layers.0.layers.1.weight"]), torch.from_numpy(g["best.layers.0.layers.1.bias"])
+        w2, b2 = torch.from_numpy(g["best.linear.weight"]), torch.from_numpy(g["best.linear.bias"])
+        logits = torch.relu(feats[G:] @ w1.T + b1) @ w2.T + b2
+        prob = torch.softmax(logits, -1).numpy()
+    assert np.allclose(prob, g["prob"], rtol=1e-5, atol=1e-6) and np.array_equal(prob.argmax(1), g["pred"])
+
+
+def test_weighted_graphconv_golden(golden):
+    """port.weighted_graphconv against the reference's own WeightedGraphConv class (graph-sc) for every norm / agg mode."""
+    g = golden("graphsc_conv")
+    src, dst = torch.from_numpy(g["src"]).long(), torch.from_numpy(g["dst"]).long()
+    x, w_e = torch.from_numpy(g["x"]), torch.from_numpy(g["w_e"])
+    for norm in ("both", "right", "none"):
+        for agg in ("sum", "mean"):
+            out = port.weighted_graphconv(x, src, dst, w_e, torch.from_numpy(g[f"{norm}.W"]), torch.from_numpy(g[f"{norm}.b"]), norm=norm,
+                                          agg=agg, act=torch.relu)
+            assert np.allclose(out.numpy(), g[f"{norm}.{agg}"], rtol=1e-5, atol=1e-6), (norm, agg)
