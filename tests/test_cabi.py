@@ -60,3 +60,23 @@ def test_sass_is_sm100a():
     out = subprocess.run([cuobjdump, "-lelf", str(_lib.lib_path())], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_(\d+a?)", out))
     assert archs == {"100a"}, archs
+
+
+def test_library_contains_blackwell_tensor_core_and_tma_code():
+    """The shipped .so is sm_100a code that really uses the 5th-gen tensor cores, tensor memory and TMA: the SASS of the
+    GEMM, decoder and kNN-filter kernels must contain UTCHMMA (tcgen05.mma), LDTM/STTM (tcgen05.ld/st) and UTMALDG
+    (cp.async.bulk.tensor).  Needs cuobjdump (CUDA toolkit); skipped where it is not installed."""
+    import shutil
+    import subprocess
+    from dance_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(cuobjdump).exists():
+        pytest.skip("cuobjdump not available")
+    lib_path = Path(_lib.__file__).resolve().parent / "lib" / "libdance_b200.so"
+    elf = subprocess.run([cuobjdump, "-lelf", str(lib_path)], capture_output=True, text=True, timeout=120).stdout
+    assert "sm_100a" in elf
+    sass = subprocess.run([cuobjdump, "-sass", str(lib_path)], capture_output=True, text=True, timeout=300).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UTMALDG"):
+        assert mnemonic in sass, mnemonic
+    for kernel in ("gemm_tc_kernel", "gae_allpairs_tch_kernel", "knn_candidates_tc_kernel"):
+        assert kernel in sass, kernel
