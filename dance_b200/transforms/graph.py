@@ -155,11 +155,55 @@ class StagateGraph(BaseTransform):
         return data
 
 
+def _average_ranks(X: torch.Tensor, chunk: int = 64) -> torch.Tensor:
+    """Column-wise ranks with ties averaged (scipy.stats.rankdata(method="average") along axis 0, as used by
+    ``scipy.stats.spearmanr``): a value whose equals occupy sorted positions lb … ub-1 gets rank (lb + ub + 1) / 2.
+    Sort / searchsorted are library plumbing (like the CUB sorts elsewhere); ranks ≤ 2²⁴ are exact in fp32."""
+    n, g = X.shape
+    out = torch.empty((n, g), dtype=torch.float32, device=X.device)
+    for c0 in range(0, g, chunk):
+        xt = X[:, c0:c0 + chunk].t().contiguous()
+        sv = torch.sort(xt, dim=1).values
+        lb = torch.searchsorted(sv, xt, right=False)
+        ub = torch.searchsorted(sv, xt, right=True)
+        out[:, c0:c0 + chunk] = ((lb + ub + 1).to(torch.float32) * 0.5).t()
+    return out
+
+
+def _median_np(v: torch.Tensor, dim=None):
+    """numpy.median semantics (mean of the two middle order statistics for an even count)."""
+    if dim is None:
+        sv = torch.sort(v.flatten()).values
+        m = sv.numel()
+        return (sv[(m - 1) // 2] + sv[m // 2]) * 0.5
+    sv = torch.sort(v, dim=dim).values
+    m = v.shape[dim]
+    return (sv.select(dim, (m - 1) // 2) + sv.select(dim, m // 2)).unsqueeze(dim) * 0.5
+
+
+def _rbf_from_gram(gram: torch.Tensor, denom_scale: float = 1.0, scale_mode: str = "med_dist") -> torch.Tensor:
+    """feature_feature_graph.py:53-57 + utils/matrix.py:70-97 from the Gram matrix ``featᵀ·feat``: euclidean distances between
+    gene columns (negative round-off clipped), then ``exp(-d / denom)`` with the reference's three scaling modes."""
+    nv = torch.diagonal(gram).unsqueeze(0)
+    dist = torch.sqrt(torch.clamp(nv + nv.t() - 2 * gram, min=0))
+    if scale_mode == "med_dist":
+        denom = _median_np(dist) * denom_scale
+    elif scale_mode == "ind_med_dist":
+        denom = _median_np(dist, dim=1) * denom_scale
+    elif scale_mode == "scale":
+        denom = denom_scale
+    else:
+        raise ValueError(f"Uknwon rbf scaling mode {scale_mode}")
+    return torch.exp(-dist / denom)
+
+
 class FeatureFeatureGraph(BaseTransform):
-    """Gene–gene similarity graph (feature_feature_graph.py:14-87): Pearson correlation of the gene columns, entries
-    with |r| below ``threshold`` dropped, edges in row-major order, unit weights optionally normalised like
-    ``dgl.nn.EdgeWeightNorm("both")``.  Result: ``uns[out]`` = graph with ``ndata["feat"] = Xᵀ`` and ``edata["weight"]``.
-    ``score_func`` "spearman" / "rbf" are not built."""
+    """Gene–gene similarity graph (feature_feature_graph.py:14-87): similarity of the gene columns — ``pearson`` (np.corrcoef),
+    ``spearman`` (Pearson of the tie-averaged ranks, scipy.stats.spearmanr) or ``rbf`` (Gaussian kernel of the euclidean
+    distance, utils/matrix.py:70-97) — entries with |score| below ``threshold`` dropped, edges in row-major order, unit weights
+    optionally normalised like ``dgl.nn.EdgeWeightNorm("both")``.  Result: ``uns[out]`` = graph with ``ndata["feat"] = Xᵀ`` and
+    ``edata["weight"]``.  The correlations run through the fp64 Gram kernel; the rbf Gram through the tcgen05 GEMM (the
+    reference uses an fp32 BLAS product there, so entries within round-off of the threshold may differ)."""
 
     _DISPLAY_ATTRS = ("threshold", "positive_only", "normalize_edges", "score_func", "score_func_kwargs")
 
@@ -171,12 +215,15 @@ class FeatureFeatureGraph(BaseTransform):
 
     def __call__(self, data):
         feat = data.get_feature(return_type="numpy")
-        if self.score_func != "pearson":
-            if self.score_func in ("spearman", "rbf"):
-                raise NotImplementedError(f"score_func={self.score_func!r} is not built (pearson is the GraphSCI default)")
+        if self.score_func not in ("pearson", "spearman", "rbf"):
             raise ValueError(f"Unknown similarity score function {self.score_func!r}, supported options are: 'pearson', 'spearman', 'rbf'")
         X = torch.as_tensor(np.ascontiguousarray(feat, dtype=np.float32)).cuda()
-        adj = ops.pearson_corr(X)
+        if self.score_func == "pearson":
+            adj = ops.pearson_corr(X)
+        elif self.score_func == "spearman":
+            adj = ops.pearson_corr(_average_ranks(X))
+        else:
+            adj = _rbf_from_gram(ops.gemm(X, X, transA=True), **self.score_func_kwargs).contiguous()
         src, dst, w, _ = ops.threshold_graph(adj, self.threshold, self.positive_only, self.normalize_edges)
         g = GraphLite(src.cpu(), dst.cpu(), adj.shape[0])
         g.ndata["feat"] = torch.from_numpy(np.ascontiguousarray(feat.astype(np.float32).T))

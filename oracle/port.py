@@ -464,11 +464,27 @@ def spagcn_fit(X, adj, W, b, init_y, lr, epochs, update_interval=3, weight_decay
     return W.detach().numpy(), b.detach().numpy(), mu_t.detach().numpy(), done
 
 
-def feature_feature_graph(feat: np.ndarray, threshold: float = 0.3, positive_only: bool = False, normalize_edges: bool = True):
-    """FeatureFeatureGraph with the pearson score (feature_feature_graph.py:45-87); dgl.graph + EdgeWeightNorm("both")
+def feature_feature_graph(feat: np.ndarray, threshold: float = 0.3, positive_only: bool = False, normalize_edges: bool = True,
+                          score_func: str = "pearson", score_func_kwargs=None):
+    """FeatureFeatureGraph (feature_feature_graph.py:45-87) with the pearson / spearman / rbf score; dgl.graph + EdgeWeightNorm("both")
     restated (dgl 1.1.3, un-vendored): weight_e = outdeg_w(src)^-0.5 · indeg_w(dst)^-0.5 · w_e on unit weights.
     Returns (src int32, dst int32, w fp32, adj fp32 after thresholding)."""
-    adj = np.corrcoef(feat.T).astype(np.float32)
+    if score_func == "pearson":
+        adj = np.corrcoef(feat.T)
+    elif score_func == "spearman":
+        from scipy.stats import spearmanr
+        adj = spearmanr(feat, axis=0)[0]
+    elif score_func == "rbf":
+        norm_vec = np.power(feat, 2).sum(0, keepdims=True)
+        dist_mat = np.sqrt((norm_vec + norm_vec.T - 2 * feat.T @ feat).clip(0))
+        kw = dict(score_func_kwargs or {})
+        mode, scale = kw.get("scale_mode", "med_dist"), kw.get("denom_scale", 1.0)          # dist_to_rbf, utils/matrix.py:70-97
+        denom = {"med_dist": lambda: np.median(dist_mat) * scale, "ind_med_dist": lambda: np.median(dist_mat, axis=1, keepdims=True) * scale,
+                 "scale": lambda: scale}[mode]()
+        adj = np.exp(-dist_mat / denom)
+    else:
+        raise ValueError(score_func)
+    adj = adj.astype(np.float32)
     adj[np.logical_and(adj > -threshold, adj < threshold)] = 0
     if positive_only:
         adj[adj < 0] = 0

@@ -5,7 +5,12 @@ import numpy as np
 import pytest
 import torch
 
+import os
+
 pytestmark = pytest.mark.gpu
+# Added after the round-1 GPU budget was spent: the device-agnostic helpers are verified on the CPU (tests/test_transforms_api.py),
+# the device glue below has not run on a B200 yet — enabled with B2_RUN_UNVERIFIED=1 until it has.
+unverified = pytest.mark.skipif(os.environ.get("B2_RUN_UNVERIFIED") != "1", reason="not yet run on a B200 (see comment)")
 
 
 @pytest.mark.parametrize("mode", ["normalize", "standardize", "minmax", "l2"])
@@ -78,3 +83,28 @@ def test_pearson_corr_split_k_and_values(cuda):
     assert np.array_equal(out, out.T)
     assert repr(__import__("dance_b200").transforms.FeatureFeatureGraph()) == \
         "FeatureFeatureGraph(threshold=0.3, positive_only=False, normalize_edges=True, score_func='pearson', score_func_kwargs={})"
+
+
+@unverified
+@pytest.mark.parametrize("score_func,kw", [("spearman", None), ("rbf", {"scale_mode": "med_dist"}), ("rbf", {"scale_mode": "ind_med_dist", "denom_scale": 2.0})])
+def test_feature_feature_graph_spearman_and_rbf(cuda, score_func, kw):
+    from dance_b200.data import AnnDataLite, Data
+    from dance_b200.transforms import FeatureFeatureGraph
+    from oracle import port
+    rng = np.random.default_rng(13)
+    n, g = 600, 90
+    lat = rng.gamma(2.0, 1.0, size=(n, 4))
+    X = rng.poisson(lat @ rng.gamma(1.0, 0.7, size=(4, g))).astype(np.float32)
+    thr = 0.3 if score_func == "spearman" else 0.5
+    src_r, dst_r, w_r, adj_r = port.feature_feature_graph(X, thr, False, True, score_func=score_func, score_func_kwargs=kw)
+    data = Data(AnnDataLite(X))
+    FeatureFeatureGraph(threshold=thr, score_func=score_func, score_func_kwargs=kw)(data)
+    gph = data.data.uns["FeatureFeatureGraph"]
+    src, dst = gph.edges()
+    if score_func == "spearman":      # fp64 correlations on both sides → the thresholded structure is exact
+        assert np.array_equal(src.numpy(), src_r) and np.array_equal(dst.numpy(), dst_r)
+        assert np.allclose(gph.edata["weight"].numpy(), w_r, rtol=1e-6)
+    else:                             # fp32 Gram on both sides (BLAS vs tcgen05 tf32x3): entries within round-off of the threshold may flip
+        mine = set(zip(src.numpy().tolist(), dst.numpy().tolist()))
+        ref = set(zip(src_r.tolist(), dst_r.tolist()))
+        assert len(mine ^ ref) <= max(2, len(ref) // 500)

@@ -103,3 +103,30 @@ def test_log1p_and_fused_pipeline_on_gpu(cuda, assert_ary_isclose):
     NormalizeTotalLog1P(target_sum=1e4, max_fraction=1.0)(b)
     ref = port.log1p(port.normalize_total(X, target_sum=1e4))
     assert np.allclose(a.data.X, ref, rtol=2e-6, atol=1e-7) and np.allclose(b.data.X, ref, rtol=2e-6, atol=1e-7)
+
+
+def test_feature_graph_score_helpers_on_cpu():
+    """The device-agnostic pieces of FeatureFeatureGraph's spearman / rbf scores against scipy / the reference formulas
+    (transforms/graph/feature_feature_graph.py:50-57, utils/matrix.py:70-97); the Gram / correlation kernels are GPU-tested."""
+    import torch
+    from scipy.stats import rankdata, spearmanr
+    from dance_b200.transforms.graph import _average_ranks, _rbf_from_gram
+    rng = np.random.default_rng(0)
+    X = rng.poisson(0.8, size=(300, 70)).astype(np.float32)           # count data: heavy ties
+    X[:, 3] = rng.normal(size=300).astype(np.float32)                 # a tie-free column
+    ranks = _average_ranks(torch.from_numpy(X), chunk=16).numpy()
+    assert np.array_equal(ranks, rankdata(X, method="average", axis=0).astype(np.float32))
+    rho = np.corrcoef(ranks.astype(np.float64), rowvar=False)
+    assert np.allclose(rho, spearmanr(X, axis=0)[0], atol=1e-12, equal_nan=True)
+    feat = rng.normal(size=(200, 40)).astype(np.float32)
+    gram = feat.T.astype(np.float64) @ feat.astype(np.float64)
+    nv = np.power(feat.astype(np.float64), 2).sum(0, keepdims=True)
+    dist = np.sqrt((nv + nv.T - 2 * gram).clip(0))
+    for mode, kw in (("med_dist", {}), ("ind_med_dist", {"denom_scale": 2.0}), ("scale", {"denom_scale": 3.0})):
+        denom = {"med_dist": np.median(dist) * kw.get("denom_scale", 1.0), "ind_med_dist": np.median(dist, axis=1, keepdims=True) * kw.get("denom_scale", 1.0),
+                 "scale": kw.get("denom_scale", 1.0)}[mode]
+        ref = np.exp(-dist / denom)
+        out = _rbf_from_gram(torch.from_numpy(gram), scale_mode=mode, **kw).numpy()
+        assert np.allclose(out, ref, rtol=1e-9, atol=1e-9), mode
+    with pytest.raises(ValueError):
+        _rbf_from_gram(torch.eye(3), scale_mode="nope")
