@@ -66,6 +66,35 @@ def search_l(p: float, adj, start: float = 0.01, end: float = 1000, tol: float =
     return None
 
 
+def _refine_labels(pred: torch.Tensor, dis: torch.Tensor, num_nbs: int) -> torch.Tensor:
+    """Majority vote over each spot's ``num_nbs`` + 1 nearest spots (itself included), device-agnostic torch:
+    relabel when the spot's own label holds fewer than num_nbs/2 of those votes and some label holds more than num_nbs/2
+    (spagcn.py:322-333).  ``pred`` int64 labels in 0..K-1; ties in distance go to the lower index (the reference's quicksort
+    leaves them unspecified)."""
+    idx = torch.sort(dis, dim=1, stable=True).indices[:, :num_nbs + 1]
+    votes = torch.nn.functional.one_hot(pred[idx], int(pred.max().item()) + 1).sum(1)
+    self_cnt = votes.gather(1, pred.view(-1, 1)).squeeze(1)
+    max_cnt, major = votes.max(1)
+    flip = (self_cnt < num_nbs / 2) & (max_cnt > num_nbs / 2)
+    return torch.where(flip, major, pred)
+
+
+def refine(sample_id, pred, dis, shape: str = "hexagon"):
+    """Optional post-processing of the domain labels (module-level ``refine`` of the reference, spagcn.py:290-334): returns the
+    refined labels as a list in ``sample_id`` order.  ``dis`` is the spot-to-spot distance matrix (numpy or tensor)."""
+    if shape == "hexagon":
+        num_nbs = 6
+    elif shape == "square":
+        num_nbs = 4
+    else:
+        raise ValueError("Shape not recognized, shape='hexagon' for Visium data, 'square' for ST data.")   # the reference logs and then fails on an unbound name
+    labels, inv = np.unique(np.asarray(pred), return_inverse=True)
+    dev = dis.device if isinstance(dis, torch.Tensor) else torch.device("cuda")
+    dis_t = dis if isinstance(dis, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(dis)).to(dev)
+    out = _refine_labels(torch.as_tensor(inv, dtype=torch.int64, device=dis_t.device), dis_t, num_nbs)
+    return labels[out.cpu().numpy()].tolist()
+
+
 class SimpleGCDEC:
     """One graph convolution + DEC clustering head; explicit forward/backward on the C-ABI kernels."""
 

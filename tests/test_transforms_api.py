@@ -130,3 +130,38 @@ def test_feature_graph_score_helpers_on_cpu():
         assert np.allclose(out, ref, rtol=1e-9, atol=1e-9), mode
     with pytest.raises(ValueError):
         _rbf_from_gram(torch.eye(3), scale_mode="nope")
+
+
+def test_spagcn_refine_matches_reference_logic():
+    """``refine`` (spagcn.py:290-334): the torch implementation (run here on CPU tensors) against a restatement of the
+    reference's pandas loop, on a jittered hexagonal layout with noisy domain labels."""
+    import pandas as pd
+    import torch
+    from dance_b200.modules.spagcn import _refine_labels, refine
+    rng = np.random.default_rng(2)
+    side = 18
+    gx, gy = np.meshgrid(np.arange(side), np.arange(side), indexing="ij")
+    xy = np.stack([gx.ravel() + 0.5 * (gy.ravel() % 2), gy.ravel() * 0.866], 1) + rng.normal(scale=0.01, size=(side * side, 2))
+    n = len(xy)
+    pred = (xy[:, 0] > side / 2).astype(int) + 2 * (xy[:, 1] > side * 0.433).astype(int)
+    noisy = pred.copy()
+    flip = rng.random(n) < 0.15
+    noisy[flip] = rng.integers(0, 4, flip.sum())
+    dis = np.sqrt(((xy[:, None, :] - xy[None, :, :])**2).sum(-1)).astype(np.float32)
+    for shape, num_nbs in (("hexagon", 6), ("square", 4)):
+        ids = [f"s{i}" for i in range(n)]
+        p_df = pd.DataFrame({"pred": noisy}, index=ids)
+        d_df = pd.DataFrame(dis, index=ids, columns=ids)
+        ref = []
+        for i in range(n):                                    # the reference loop, with a stable sort
+            nbs = d_df.loc[ids[i], :].sort_values(kind="stable")[0:num_nbs + 1]
+            v_c = p_df.loc[nbs.index, "pred"].value_counts()
+            self_pred = p_df.loc[ids[i], "pred"]
+            ref.append(v_c.idxmax() if (v_c.loc[self_pred] < num_nbs / 2) and (np.max(v_c) > num_nbs / 2) else self_pred)
+        got = refine(ids, noisy, torch.from_numpy(dis), shape=shape)        # CPU tensor in → runs on the CPU
+        assert got == [int(v) for v in ref]
+        assert (np.array(got) == pred).mean() > (noisy == pred).mean()       # the vote removes most of the label noise
+    out = _refine_labels(torch.tensor([0, 0, 1]), torch.tensor([[0., 1, 2], [1, 0, 1], [2, 1, 0]]), 6)
+    assert out.tolist() == [0, 0, 1]                                         # three spots: nobody reaches more than 3 votes
+    with pytest.raises(ValueError):
+        refine(["a"], [0], np.zeros((1, 1), np.float32), shape="triangle")
