@@ -315,6 +315,32 @@ class SpaGCN:
     def set_l(self, l):
         self.l = l
 
+    def search_set_res(self, x, l, target_num, start=0.4, step=0.1, tol=5e-3, lr=0.05, epochs=10, max_run=10):
+        """Search the leiden resolution that yields ``target_num`` domains (spagcn.py:771-805; same control flow).  Needs the
+        ``init="louvain"`` initialisation, i.e. scanpy — raises NotImplementedError from ``fit`` where scanpy is absent."""
+        res = start
+        clf = SpaGCN(l, device=self.device, precision=self.precision, seed=self.seed)
+        old_num = len(set(clf.fit_predict(x, init_spa=True, init="louvain", res=res, tol=tol, lr=lr, epochs=epochs)))
+        run = 0
+        while old_num != target_num:
+            old_sign = 1 if (old_num < target_num) else -1
+            clf = SpaGCN(l, device=self.device, precision=self.precision, seed=self.seed)
+            new_num = len(set(clf.fit_predict(x, init_spa=True, init="louvain", res=res + step * old_sign, tol=tol, lr=lr, epochs=epochs)))
+            if new_num == target_num:
+                res = res + step * old_sign
+                return res
+            new_sign = 1 if (new_num < target_num) else -1
+            if new_sign == old_sign:
+                res = res + step * old_sign
+                old_num = new_num
+            else:
+                step = step / 2
+            if run > max_run:
+                return res
+            run += 1
+        self.res = res
+        return res
+
     def calc_adj_exp(self, adj) -> torch.Tensor:
         """``exp(-adj²/(2 l²))`` on the device (spagcn.py:807-809); returns a CUDA tensor (the reference returns numpy)."""
         out, _ = ops.exp_adj(_dev(adj, self.device), self.l, want_matrix=True, want_sum=False)
