@@ -15,7 +15,7 @@ loss, dz, _, _ = ops.gae_loss_grad(z, L, 0.5, 100.0)
 print("MS", med, "loss", loss.item(), "dz", dz.double().norm().item())
 '''
 for nn in (100000, 200000):
-    for name, env in (("f16", {}), ("tf32", {"B2_GAE_NO_F16": "1"}), ("cuda-core", {"B2_GAE_NO_TC": "1"}),
+    for name, env in (("f16", {}), ("f16 packed-B dZ (8 MMAs)", {"B2_GAE_PACKED": "1"}), ("tf32", {"B2_GAE_NO_F16": "1"}), ("cuda-core", {"B2_GAE_NO_TC": "1"}),
                       ("f16 no-SFU", {"B2_GAE_TC_DEBUG": "1"}), ("f16 no-dZ", {"B2_GAE_TC_DEBUG": "2"}), ("f16 no-S", {"B2_GAE_TC_DEBUG": "4"}),
                       ("f16 none", {"B2_GAE_TC_DEBUG": "7"})):
         if nn > 100000 and "no-" in name or (nn > 100000 and name == "f16 none"):
