@@ -60,14 +60,17 @@ class WeightedFeaturePCA(BaseTransform):
 
     def __call__(self, data):
         feat = data.get_x(self.split_name)                      # cells × genes
-        if self.feat_norm_mode is not None:
-            raise NotImplementedError("feat_norm_mode is not built (the scDeepSort pipeline uses None, scdeepsort.py:134-140)")
+        feat_dev = None
+        if self.feat_norm_mode is not None:      # normalize(feat, mode, axis) before the decomposition (cell_feature.py:51-54)
+            feat_dev = ops.matrix_normalize(_to_cuda(feat), self.feat_norm_mode, self.feat_norm_axis % 2)
         if self.n_components > min(feat.shape):
             self.logger.warning(f"n_components={self.n_components} must be between 0 and min(n_samples, n_features)={min(feat.shape)}")
             self.n_components = min(feat.shape)
         k = int(self.n_components)
-        Xt = _to_cuda(np.asarray(feat).T)                       # genes × cells: genes are the PCA samples (cell_feature.py:61)
-        gene_feat = ops.pca(Xt, k)["scores"]                    # genes × components
+        # genes × cells: genes are the PCA samples (cell_feature.py:61)
+        Xt = _to_cuda(np.asarray(feat).T) if feat_dev is None else feat_dev.t().contiguous()
+        res = ops.pca(Xt, k)
+        gene_feat = res["scores"]                               # genes × components
         x = _to_cuda(data.get_x())
         # normalize(x, mode="normalize", axis=1) @ gene_feat   (cell_feature.py:66-67); zero row sums → divide by 1
         rs = x.sum(1, keepdim=True)
@@ -75,4 +78,11 @@ class WeightedFeaturePCA(BaseTransform):
         cell_feat = ops.gemm((x / rs).contiguous(), gene_feat.contiguous())
         data.data.obsm[self.out] = cell_feat.cpu().numpy().astype(np.float32)
         data.data.varm[self.out] = gene_feat.cpu().numpy().astype(np.float32)
+        if self.save_info:
+            ev = res["explained_variance"].cpu().numpy()
+            total_var = float(Xt.double().var(dim=0, unbiased=True).sum().item())
+            data.data.uns["pca_components"] = res["components"].cpu().numpy()
+            data.data.uns["pca_mean"] = res["mean"].cpu().numpy()
+            data.data.uns["pca_explained_variance"] = ev
+            data.data.uns["pca_explained_variance_ratio"] = ev / total_var
         return data
