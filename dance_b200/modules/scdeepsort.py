@@ -27,14 +27,16 @@ class ScDeepSort:
                  batch_size: int = 500, device: str = "cuda", precision: Optional[str] = None, seed: Optional[int] = None):
         if num_layers != 1:
             raise NotImplementedError("only num_layers=1 (the example default, scdeepsort.py(ex):25) is built")
-        if dropout:
-            raise NotImplementedError("dropout > 0 is not built")
+        if not 0.0 <= float(dropout) < 1.0:
+            raise ValueError("dropout must be in [0, 1)")
         self.dense_dim, self.hidden_dim, self.n_layers = dim_in, dim_hid, num_layers
         self.species, self.tissue, self.batch_size = species, tissue, batch_size
         self.device = torch.device(device if device != "auto" else "cuda")
         if self.device.type != "cuda":
             raise RuntimeError("dance_b200 runs on CUDA devices only")
         self.precision, self.seed = precision, seed
+        self.dropout = float(dropout)
+        self._drop_gen = None                  # device generator for the dropout masks (created on first use)
         self.params: Optional[FlatParams] = None
 
     # ---- model ------------------------------------------------------------------------------
@@ -70,6 +72,14 @@ class ScDeepSort:
 
     def _train_batch(self, x: torch.Tensor, y: torch.Tensor, lr: float, weight_decay: float, loss_acc: torch.Tensor):
         P, G = self.params.p, self.params.g
+        if self.dropout > 0.0:
+            # nn.Dropout in front of the AdaptiveSAGE linear (gnn.py:56,92-94): the layer sees only the destination features,
+            # so the mask acts on x; the backward below uses the same dropped-out input.  Masks come from a device generator.
+            if self._drop_gen is None:
+                self._drop_gen = torch.Generator(device=self.device)
+                self._drop_gen.manual_seed(int(self.seed) if self.seed is not None else torch.seed() % (2**31))
+            keep = (torch.rand(x.shape, device=self.device, generator=self._drop_gen) >= self.dropout).to(torch.float32)
+            x = x * (keep / (1.0 - self.dropout))
         h, logits = self._forward(x)
         _, dlogits = ops.softmax_ce_sum(logits, y, loss_out=loss_acc)                                       # CrossEntropyLoss(sum)
         ops.gemm(dlogits, h, transA=True, out=G["linear.weight"], precision=self.precision)
