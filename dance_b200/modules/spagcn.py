@@ -89,8 +89,7 @@ def refine(sample_id, pred, dis, shape: str = "hexagon"):
     else:
         raise ValueError("Shape not recognized, shape='hexagon' for Visium data, 'square' for ST data.")   # the reference logs and then fails on an unbound name
     labels, inv = np.unique(np.asarray(pred), return_inverse=True)
-    dev = dis.device if isinstance(dis, torch.Tensor) else torch.device("cuda")
-    dis_t = dis if isinstance(dis, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(dis)).to(dev)
+    dis_t = (dis if isinstance(dis, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(dis))).to("cuda")   # no CPU path
     out = _refine_labels(torch.as_tensor(inv, dtype=torch.int64, device=dis_t.device), dis_t, num_nbs)
     return labels[out.cpu().numpy()].tolist()
 
