@@ -344,3 +344,49 @@ def test_weighted_graphconv_golden(golden):
             out = port.weighted_graphconv(x, src, dst, w_e, torch.from_numpy(g[f"{norm}.W"]), torch.from_numpy(g[f"{norm}.b"]), norm=norm,
                                           agg=agg, act=torch.relu)
             assert np.allclose(out.numpy(), g[f"{norm}.{agg}"], rtol=1e-5, atol=1e-6), (norm, agg)
+
+
+def test_umap_connectivities_against_closed_forms():
+    """Independent checks of the loop-level UMAP restatement (scanpy/umap are absent, so there is no fixture): a vectorised
+    re-derivation of the smooth-kNN bisection, the fuzzy-union identity on the dense matrices, and analytically known cases."""
+    rng = np.random.default_rng(4)
+    n, d, k = 120, 6, 10
+    X = rng.normal(size=(n, d)).astype(np.float32)
+    X[9] = X[2]                                                  # a zero distance to a non-self neighbour
+    d2 = ((X[:, None, :].astype(np.float64) - X[None, :, :])**2).sum(-1)
+    idx = np.argsort(d2, axis=1, kind="stable")[:, :k].astype(np.int32)
+    dist = np.sqrt(np.take_along_axis(d2, idx, 1)).astype(np.float32)
+    C = port.umap_connectivities(idx, dist)
+    # (1) vectorised smooth_knn_dist: rho = first positive distance, sigma solves Σ_{j>=1} exp(-max(d-rho,0)/sigma) = log2(k)
+    pos = np.where(dist > 0, dist, np.inf)
+    rho = pos.min(1).astype(np.float32)
+    lo, hi, mid = np.zeros(n), np.full(n, np.inf), np.ones(n)
+    done = np.zeros(n, bool)
+    target = np.log2(k)
+    for _ in range(64):
+        dd = (dist[:, 1:] - rho[:, None]).astype(np.float32).astype(np.float64)
+        psum = np.where(dd > 0, np.exp(-dd / mid[:, None]), 1.0).sum(1)
+        done |= np.abs(psum - target) < 1e-5
+        up = (psum > target) & ~done
+        dn = (psum <= target) & ~done
+        hi = np.where(up, mid, hi)
+        lo = np.where(dn, mid, lo)
+        mid = np.where(up, (lo + hi) / 2, np.where(dn, np.where(np.isinf(hi), mid * 2, (lo + hi) / 2), mid))
+    sigma = np.maximum(mid.astype(np.float32), (1e-3 * dist.mean(1)).astype(np.float32))
+    # (2) membership strengths and the fuzzy union A + Aᵀ - A∘Aᵀ on dense matrices
+    val = np.where(idx == np.arange(n)[:, None], 0.0, np.where((dist - rho[:, None] <= 0) | (sigma[:, None] == 0), 1.0,
+                                                                np.exp(-((dist - rho[:, None]) / sigma[:, None])))).astype(np.float32)
+    A = np.zeros((n, n), np.float32)
+    np.add.at(A, (np.repeat(np.arange(n), k), idx.reshape(-1)), val.reshape(-1))
+    dense = A + A.T - A * A.T
+    assert np.allclose(C.toarray(), dense, rtol=1e-5, atol=1e-7)
+    assert np.array_equal(C.toarray() != 0, dense != 0)
+    # (3) analytic cases: every non-self neighbour at the SAME distance → d - rho = 0 → strength 1 for all of them
+    idx2 = np.stack([np.arange(6), (np.arange(6) + 1) % 6, (np.arange(6) + 2) % 6], 1).astype(np.int32)
+    dist2 = np.tile(np.array([0.0, 2.0, 2.0], np.float32), (6, 1))
+    C2 = port.umap_connectivities(idx2, dist2).toarray()
+    expect = np.zeros((6, 6), np.float32)
+    for i in range(6):
+        for j in ((i + 1) % 6, (i + 2) % 6):
+            expect[i, j] = expect[j, i] = 1.0                   # 1 + 1 - 1·1 = 1 when both directions exist, 1 + 0 - 0 otherwise
+    assert np.array_equal(C2, expect)
