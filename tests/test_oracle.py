@@ -390,3 +390,46 @@ def test_umap_connectivities_against_closed_forms():
         for j in ((i + 1) % 6, (i + 2) % 6):
             expect[i, j] = expect[j, i] = 1.0                   # 1 + 1 - 1·1 = 1 when both directions exist, 1 + 0 - 0 otherwise
     assert np.array_equal(C2, expect)
+
+
+def _trunc32(x):
+    """Round a float64 array toward zero to fp32 precision (the accumulate behaviour measured for tcgen05 + TMEM)."""
+    y = x.astype(np.float32)
+    over = np.abs(y.astype(np.float64)) > np.abs(x)
+    return np.where(over, np.nextafter(y, np.float32(0)), y).astype(np.float32)
+
+
+@pytest.mark.parametrize("d,scale", [(128, 1.0), (50, 1.0), (128, 300.0), (16, 1e-3)])
+def test_knn_tensor_core_filter_error_bound_is_sound(d, scale):
+    """Host emulation of the fp16 hi/lo-split filter estimate of knn_tc.cu (operands 2^e·x split into fp16 pairs, the three
+    products per 16-feature step accumulated in fp32 with TRUNCATING adds, fp32 norms and final fma) against the exact fp64
+    squared distance: the bound `tc_err_rel` used by the refine proof (csrc/knn_tc.cu) must dominate the error — this is
+    what makes the tensor-core kNN exact.  Includes vectors of very different norms."""
+    rng = np.random.default_rng(d)
+    n = 400
+    X = (rng.normal(size=(n, d)) * scale + rng.normal(size=(1, d)) * 3 * scale).astype(np.float32)
+    X[:7] *= 40.0
+    dp = (d + 63) // 64 * 64
+    e = 9 - int(np.frexp(np.abs(X).max())[1])
+    s = np.float32(2.0**e)
+    Xs = np.zeros((n, dp), np.float32)
+    Xs[:, :d] = X * s
+    hi = Xs.astype(np.float16)
+    lo = (Xs - hi.astype(np.float32)).astype(np.float16)
+    hi64, lo64 = hi.astype(np.float64), lo.astype(np.float64)
+    q = slice(0, 60)
+    acc = np.zeros((60, n), np.float32)
+    for k0 in range(0, dp, 16):                                  # one tcgen05.mma per product and 16-feature step
+        ks = slice(k0, k0 + 16)
+        for a, b in ((lo64, hi64), (hi64, lo64), (hi64, hi64)):
+            acc = _trunc32(acc.astype(np.float64) + a[q, ks] @ b[:, ks].T)
+    sqn = np.array([np.float32(np.sum(np.float32(r) * np.float32(r), dtype=np.float32)) for r in X], np.float32)   # row_sqnorm_kernel (fp32)
+    inv_s2 = np.float32(2.0**(-2 * e))
+    est = (np.float32(-2.0) * inv_s2 * acc + (sqn[q, None] + sqn[None, :])).astype(np.float32)
+    true = ((X[q, None, :].astype(np.float64) - X[None, :, :].astype(np.float64))**2).sum(-1)
+    err_rel = 7.62939453125e-06 + 1.1920928955078125e-07 * (d + 8)           # ktc::tc_err_rel
+    rmax = float(sqn.max())
+    bound = err_rel * (sqn[q, None].astype(np.float64) + rmax + 2.0 * np.sqrt(sqn[q, None].astype(np.float64) * rmax))
+    worst = np.abs(est.astype(np.float64) - true) / bound
+    assert worst.max() < 1.0, worst.max()
+    assert worst.max() < 0.5                                                 # comfortable margin, not a knife edge
