@@ -80,3 +80,20 @@ def test_library_contains_blackwell_tensor_core_and_tma_code():
         assert mnemonic in sass, mnemonic
     for kernel in ("gemm_tc_kernel", "gae_allpairs_tch_kernel", "knn_candidates_tc_kernel"):
         assert kernel in sass, kernel
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/dance_b200.h must compile as C99 (no C++ constructs, no torch / CUDA types)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "probe.c"
+    hdr = Path(__file__).resolve().parent.parent / "include"
+    src.write_text('#include "dance_b200.h"\nint main(void) { return b2_version() < 0; }\n')
+    res = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", f"-I{hdr}", str(src)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    code = re.sub(r"/\*.*?\*/", "", (hdr / "dance_b200.h").read_text(), flags=re.S)      # declarations only, comments stripped
+    for banned in ("std::", "template", "class ", "Tensor", "cudaStream_t", "torch"):
+        assert banned not in code, banned
