@@ -478,3 +478,30 @@ def test_decoder_fp16_split_scheme_precision_on_host():
     sig = 1.0 / (1.0 + np.exp(-x_true))
     dz_true = sig @ z.astype(np.float64)
     assert np.linalg.norm(dz - dz_true) / np.linalg.norm(dz_true) < 2e-6
+
+
+def test_plain_c_restatements_agree_with_the_port(golden):
+    """oracle/c (plain C, built by oracle/Makefile) as an independent checker: CSR aggregate, fp64 kNN ranking and the
+    Graph-AE decoder loss + gradient against oracle/port.py and the reference fixtures."""
+    from oracle import c_oracle
+    g = golden("knn_graph")
+    X, k = g["X"], int(g["k"])
+    for qi in (0, 17, len(X) - 1):
+        idx, dist = c_oracle.knn_rank(X, qi, k)
+        assert np.array_equal(idx, g["knn_idx"][qi]) and np.array_equal(1 / (dist + 1e-16), g["knn_w"][qi])       # bit-exact vs the reference
+    rng = np.random.default_rng(0)
+    S = rng.normal(size=(len(X), 12)).astype(np.float32)
+    A = sp.csr_matrix((g["norm_data"], g["norm_indices"], g["norm_indptr"]), shape=(len(X), len(X)))
+    assert np.allclose(c_oracle.csr_spmm(A.indptr, A.indices, A.data, S), A @ S, rtol=1e-5, atol=1e-6)
+    # decoder: dense torch formula of the port (scgnn2.py:603-609) vs the C loops
+    n, d = 150, 16
+    z = torch.tensor((rng.normal(size=(n, d)) * 0.4).astype(np.float32), requires_grad=True)
+    adj, _ = port.feature2adj(port.synthetic_embedding(n, d=8, seed=2), 5)
+    L = (adj + sp.eye(n)).tocsr()
+    L.sort_indices()
+    pw, norm = port.gae_norm_constants(adj)
+    loss = port.gae_loss(torch.mm(z, z.t()), torch.from_numpy(L.toarray()).float(), None, None, n, norm, pw)
+    loss.backward()
+    c_loss, c_dz = c_oracle.gae_loss_grad(z.detach().numpy(), L.indptr, L.indices, norm, pw)
+    assert abs(c_loss - loss.item()) < 1e-5 * abs(loss.item())
+    assert np.linalg.norm(c_dz - z.grad.numpy()) / np.linalg.norm(z.grad.numpy()) < 1e-4      # torch side is fp32
