@@ -49,7 +49,6 @@ struct Params {
   double* loss_acc;
   int n, d, row_begin, n_rows, j_chunk, j_splits;
   float coef;
-  int debug;   // timing experiments only (B2_GAE_TC_DEBUG): 1 = skip SFU math, 2 = skip dZ MMAs, 4 = skip S MMAs
 };
 
 // z [n,d] → hi/lo tf32 split, as Z16 (row-major, padded to 16) and ZT (transposed, row pitch npad)
@@ -155,7 +154,6 @@ gae_allpairs_tc_kernel(const __grid_constant__ Params p) {
         const uint32_t d_s = tmem + TM_S + (uint32_t)(b * BJ);
 #pragma unroll
         for (int k = 0; k < DW / 8; ++k) {
-          if (p.debug & 4) break;
           // SWIZZLE_64B K-major: 64-byte rows, 8-row groups 512 B apart
           const uint64_t a_hi = umma_desc(s_zi_hi + k * 32, 16, 512, 4), a_lo = umma_desc(s_zi_lo + k * 32, 16, 512, 4);
           const uint64_t b_hi = umma_desc(st + k * 32, 16, 512, 4), b_lo = umma_desc(st + ZJ_BYTES + k * 32, 16, 512, 4);
@@ -177,7 +175,6 @@ gae_allpairs_tc_kernel(const __grid_constant__ Params p) {
         const uint32_t g_hi = tmem + TM_GHI + (uint32_t)(b * BJ), g_lo = tmem + TM_GLO + (uint32_t)(b * BJ);
 #pragma unroll
         for (int k = 0; k < BJ / 8; ++k) {
-          if (p.debug & 2) break;
           // ZT tile: two boxes of [16 rows(d) x 128 B (32 j)], SWIZZLE_128B K-major; k-step = 8 j = 32 B
           const uint32_t boff = (uint32_t)(k >> 2) * 2048u + (uint32_t)(k & 3) * 32u;
           const uint64_t b_hi = umma_desc(zt + boff, 16, 1024, 2);
@@ -220,9 +217,9 @@ gae_allpairs_tc_kernel(const __grid_constant__ Params p) {
       // staged so that the 16 independent SFU chains are issued back to back (ILP instead of one long dependent chain)
       float e[EW_COLS], sg[EW_COLS];
 #pragma unroll
-      for (int c = 0; c < EW_COLS; ++c) e[c] = (p.debug & 1) ? __uint_as_float(v[c]) : ex2a(-fabsf(__uint_as_float(v[c])) * LOG2E);
+      for (int c = 0; c < EW_COLS; ++c) e[c] = ex2a(-fabsf(__uint_as_float(v[c])) * LOG2E);
 #pragma unroll
-      for (int c = 0; c < EW_COLS; ++c) sg[c] = (p.debug & 1) ? e[c] : rcpa(1.f + e[c]);
+      for (int c = 0; c < EW_COLS; ++c) sg[c] = rcpa(1.f + e[c]);
       float prod0 = 1.f, prod1 = 1.f;
       uint32_t hi[EW_COLS], lo[EW_COLS];
 #pragma unroll
@@ -289,7 +286,8 @@ size_t workspace_bytes(int32_t n) {
 }
 
 bool eligible(int32_t n, int32_t d, int32_t n_rows) {
-  if (getenv("B2_GAE_NO_TC")) return false;
+  static const bool no_tc = getenv("B2_GAE_NO_TC") != nullptr;   // A/B path selector (both paths are exact), read once
+  if (no_tc) return false;
   return d >= 1 && d <= DW && (int64_t)n * n_rows >= (1ll << 22);
 }
 
@@ -330,7 +328,6 @@ int launch(const float* z, int64_t ldz, int32_t n, int32_t d, int32_t row_begin,
   j_splits = ceil_div(n, j_chunk);
   p.dz = dz; p.loss_acc = loss_acc; p.n = n; p.d = d; p.row_begin = row_begin; p.n_rows = n_rows;
   p.j_chunk = j_chunk; p.j_splits = j_splits; p.coef = coef;
-  p.debug = getenv("B2_GAE_TC_DEBUG") ? atoi(getenv("B2_GAE_TC_DEBUG")) : 0;
   const size_t smem = 2 * ZI_BYTES + STAGES * STAGE_BYTES + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {

@@ -54,11 +54,8 @@ struct Params {
   double* loss_acc;
   int n, d, row_begin, n_rows, j_chunk, j_splits;
   float coef;
-  int stagger; // initial delay (cycles) of the second elementwise group
-  int packed;  // experimental (B2_GAE_PACKED=1, default off: passes the parity test on a B200, not yet timed): dZ with B = [Z_hi | Z_lo] as one
-               // N = 32 operand → 8 instead of 12 tcgen05.mma per tile (hi·hi and hi·lo come out of one instruction)
-  int debug;   // timing experiments only (B2_GAE_TC_DEBUG): 1 = skip SFU math, 2 = skip dZ MMAs, 4 = skip S MMAs
 };
+constexpr int STAGGER_CYCLES = 800;   // initial delay of the second elementwise group (half a tile period)
 
 // max |z| → power-of-two scale (scale[0] = 2^e, scale[1] = 2^-2e, scale[2] = 2^-e)
 __global__ void __launch_bounds__(256)
@@ -127,8 +124,6 @@ __device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f3
 __device__ __forceinline__ float lg2a(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcpa(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// MODE (timing experiments, B2_GAE_MUFU_MODE): 0 production, 1 RCP replaced by a second EX2, 2 no MUFU at all
-template <int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 gae_allpairs_tch_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -199,7 +194,6 @@ gae_allpairs_tch_kernel(const __grid_constant__ Params p) {
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_f16(BI, BJ, 0, 0);   // S  = Z_I (K-major, K = 16) · Z_J (K-major)
       const uint32_t idesc_d = umma_idesc_f16(BI, DW, 0, 0);   // dZ = G (TMEM, K = j) · Z_Jᵀ tile (K-major, N = 16)
-      const uint32_t idesc_d2 = umma_idesc_f16(BI, 2 * DW, 0, 0);   // packed variant: N = 32 over the adjacent hi | lo ZT tiles
       mbar_wait(zi_bar, 0);
       tc_fence_after();
       auto issue_s = [&](int t, int stage, uint32_t phase) {
@@ -209,14 +203,12 @@ gae_allpairs_tch_kernel(const __grid_constant__ Params p) {
         tc_fence_after();
         const uint32_t st = s_ring + stage * STAGE_BYTES;
         const uint32_t d_s = tmem + TM_S + (uint32_t)(b * BJ);
-        if (!(p.debug & 4)) {
-          // SWIZZLE_32B K-major: 32-byte rows (the whole K = 16), 8-row groups 256 B apart — one k-step
-          const uint64_t a_hi = umma_desc(s_zi_hi, 16, 256, 6), a_lo = umma_desc(s_zi_lo, 16, 256, 6);
-          const uint64_t b_hi = umma_desc(st, 16, 256, 6), b_lo = umma_desc(st + ZJ_BYTES, 16, 256, 6);
-          umma_f16(d_s, a_lo, b_hi, idesc_s, 0);
-          umma_f16(d_s, a_hi, b_lo, idesc_s, 1);
-          umma_f16(d_s, a_hi, b_hi, idesc_s, 1);
-        }
+        // SWIZZLE_32B K-major: 32-byte rows (the whole K = 16), 8-row groups 256 B apart — one k-step
+        const uint64_t a_hi = umma_desc(s_zi_hi, 16, 256, 6), a_lo = umma_desc(s_zi_lo, 16, 256, 6);
+        const uint64_t b_hi = umma_desc(st, 16, 256, 6), b_lo = umma_desc(st + ZJ_BYTES, 16, 256, 6);
+        umma_f16(d_s, a_lo, b_hi, idesc_s, 0);
+        umma_f16(d_s, a_hi, b_lo, idesc_s, 1);
+        umma_f16(d_s, a_hi, b_hi, idesc_s, 1);
         umma_commit(s_full + 8 * b);
       };
       int stage_s = 0, stage_d = 0;
@@ -234,24 +226,15 @@ gae_allpairs_tch_kernel(const __grid_constant__ Params p) {
         const uint32_t g_hi = tmem + TM_GHI + (uint32_t)(b * GCOLS), g_lo = tmem + TM_GLO + (uint32_t)(b * GCOLS);
 #pragma unroll
         for (int k = 0; k < BJ / 16; ++k) {
-          if (p.debug & 2) break;
           // ZT tile: [16 rows(d) x 128 B (64 j)], SWIZZLE_128B K-major; k-step = 16 j = 32 B; G: 8 packed columns per k-step
           const uint64_t b_hi = umma_desc(zt + (uint32_t)k * 32u, 16, 1024, 2);
           const uint64_t b_lo = umma_desc(zt + ZT_BYTES + (uint32_t)k * 32u, 16, 1024, 2);
           // even / odd k-steps feed independent accumulator pairs (A / B) so consecutive MMAs never wait on each other
           const uint32_t acc = (t > 0 || k > 1) ? 1u : 0u;
-          if (p.packed) {
-            // the hi and lo ZT tiles are adjacent 16-row K-major tiles (2 KB each, 8-row groups 1 KB apart), i.e. ONE 32-row
-            // operand: G_hi·[Z_hi | Z_lo] yields hi·hi (columns 0-15) and hi·lo (16-31) together; lo·hi stays a N = 16 product
-            const uint32_t dbase = tmem + TM_D + (uint32_t)((k & 1) * 48);
-            umma_f16_ts(dbase, g_hi + k * 8, b_hi, idesc_d2, acc);       // [big | small hi·lo]
-            umma_f16_ts(dbase + 32, g_lo + k * 8, b_hi, idesc_d, acc);   // small lo·hi
-          } else {
-            const uint32_t dbase = tmem + TM_D + (uint32_t)((k & 1) * 32);
-            umma_f16_ts(dbase + 16, g_lo + k * 8, b_hi, idesc_d, acc);   // small: lo·hi
-            umma_f16_ts(dbase, g_hi + k * 8, b_hi, idesc_d, acc);        // big:   hi·hi
-            umma_f16_ts(dbase + 16, g_hi + k * 8, b_lo, idesc_d, 1);     // small: hi·lo
-          }
+          const uint32_t dbase = tmem + TM_D + (uint32_t)((k & 1) * 32);
+          umma_f16_ts(dbase + 16, g_lo + k * 8, b_hi, idesc_d, acc);   // small: lo·hi
+          umma_f16_ts(dbase, g_hi + k * 8, b_hi, idesc_d, acc);        // big:   hi·hi
+          umma_f16_ts(dbase + 16, g_hi + k * 8, b_lo, idesc_d, 1);     // small: hi·lo
         }
         umma_commit(g_empty + 8 * b);
         umma_commit(stage_free + 8 * stage_d);
@@ -276,7 +259,7 @@ gae_allpairs_tch_kernel(const __grid_constant__ Params p) {
     // idle in turn (ncu: XU 58 %, issue 58 %); two groups half a period apart keep both busy.
     const int group = part >> 1;                          // tile parity handled (= buffer index)
     const int half = part & 1;                            // 32-column half of the tile
-    if (group == 1) { const long long t0 = clock64(); while (clock64() - t0 < p.stagger) { } }
+    if (group == 1) { const long long t0 = clock64(); while (clock64() - t0 < STAGGER_CYCLES) { } }
     for (int t = group; t < n_tiles; t += 2) {
       const int b = group;
       const uint32_t par = (t >> 1) & 1;
@@ -306,9 +289,9 @@ gae_allpairs_tch_kernel(const __grid_constant__ Params p) {
 #pragma unroll
         for (int c = 0; c < EW_COLS; ++c) {
           const float x = __uint_as_float(v[c]);
-          const float e = MODE == 2 ? fabsf(x) * 0.001f : ex2a(-fabsf(x));
+          const float e = ex2a(-fabsf(x));
           const float q = fmaf(e, 1.f / G_SCALE, 1.f / G_SCALE);
-          const float r = MODE == 0 ? rcpa(q) : (MODE == 1 ? ex2a(q) : q * 3.f);
+          const float r = rcpa(q);
           const float er = e * r;
           float gc = x >= 0.f ? r : er;
           if (FULL) {
@@ -373,19 +356,6 @@ gae_allpairs_tch_kernel(const __grid_constant__ Params p) {
       tmem_ld_32x32b_x16(tmem + lane_off + TM_D + 16, a1);
       tmem_ld_32x32b_x16(tmem + lane_off + TM_D + 32, a2);
       tmem_ld_32x32b_x16(tmem + lane_off + TM_D + 48, a3);
-      if (p.packed) {
-        // packed layout: parity 0 = [big 0-15 | small 16-31 | small 32-47], parity 1 = the same at +48
-        uint32_t b4[16], b5[16];
-        tmem_ld_32x32b_x16(tmem + lane_off + TM_D + 64, b4);
-        tmem_ld_32x32b_x16(tmem + lane_off + TM_D + 80, b5);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const float big = __uint_as_float(a0[c]) + __uint_as_float(a3[c]);                                          // +0, +48
-          const float small = (__uint_as_float(a1[c]) + __uint_as_float(a2[c])) + (__uint_as_float(b4[c]) + __uint_as_float(b5[c]));   // +16, +32, +64, +80
-          a0[c] = __float_as_uint(big); a2[c] = 0u;
-          a1[c] = __float_as_uint(small); a3[c] = 0u;
-        }
-      }
       if (live && n_tiles > 0) {
         const float c2 = 2.f * p.coef * p.scale[2] * (1.f / G_SCALE);   // undo the ZT and G scales
         float* dst = p.dz + (size_t)row_local * p.d;
@@ -416,7 +386,8 @@ size_t workspace_bytes(int32_t n) {
 }
 
 bool eligible(int32_t n, int32_t d, int32_t n_rows) {
-  if (getenv("B2_GAE_NO_TC") || getenv("B2_GAE_NO_F16")) return false;
+  static const bool off = getenv("B2_GAE_NO_TC") || getenv("B2_GAE_NO_F16");   // A/B path selectors (exact fallbacks), read once
+  if (off) return false;
   return d >= 1 && d <= DW && (int64_t)n * n_rows >= (1ll << 22);
 }
 
@@ -484,22 +455,14 @@ int launch(const float* z, int64_t ldz, int32_t n, int32_t d, int32_t row_begin,
   }
   B2_CHECK_LAUNCH("colrange_sum_kernel");
   p.z = z; p.ldz = ldz; p.zsum = zsum;
-  p.stagger = getenv("B2_GAE_STAGGER") ? atoi(getenv("B2_GAE_STAGGER")) : 800;
-  p.packed = getenv("B2_GAE_PACKED") ? atoi(getenv("B2_GAE_PACKED")) : 0;
-  p.debug = getenv("B2_GAE_TC_DEBUG") ? atoi(getenv("B2_GAE_TC_DEBUG")) : 0;
   const size_t smem = 2 * ZI_BYTES + STAGES * STAGE_BYTES + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(gae_allpairs_tch_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B2_CHECK_CUDA(cudaFuncSetAttribute(gae_allpairs_tch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B2_CHECK_CUDA(cudaFuncSetAttribute(gae_allpairs_tch_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2_CHECK_CUDA(cudaFuncSetAttribute(gae_allpairs_tch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   dim3 grid(row_blocks, j_splits);
-  const int mode = getenv("B2_GAE_MUFU_MODE") ? atoi(getenv("B2_GAE_MUFU_MODE")) : 0;
-  if (mode == 1) gae_allpairs_tch_kernel<1><<<grid, THREADS, smem, st>>>(p);
-  else if (mode == 2) gae_allpairs_tch_kernel<2><<<grid, THREADS, smem, st>>>(p);
-  else gae_allpairs_tch_kernel<0><<<grid, THREADS, smem, st>>>(p);
+  gae_allpairs_tch_kernel<<<grid, THREADS, smem, st>>>(p);
   B2_CHECK_LAUNCH("gae_allpairs_tch_kernel");
   return B2_OK;
 }

@@ -381,8 +381,7 @@ bool make_tensor_map_f16_ex(CUtensorMap* map, const void* ptr, uint64_t inner, u
 
 bool make_tensor_map_f32(CUtensorMap* map, const float* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer,
                          bool mn_major) {
-  int mn_swz = (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-  if (const char* e = getenv("B2_TC_MN_SWZ")) mn_swz = atoi(e);   // bring-up probe only
+  const int mn_swz = (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   return make_tensor_map_f32_ex(map, ptr, inner, outer, ld, 32, box_outer, mn_major ? mn_swz : (int)CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
@@ -455,9 +454,6 @@ int gemm_tc(const float* A, int64_t lda, int transA, const float* B, int64_t ldb
   p.tiles_m = pl.tiles_m; p.tiles_n = pl.tiles_n; p.splits = pl.splits; p.kb_per_split = pl.kb_per_split;
   p.kb_total = pl.kb_total; p.stages = pl.stages;
   p.mn_lbo = ATOM_BYTES; p.mn_sbo = 512; p.mn_layout = 1;
-  if (const char* e = getenv("B2_TC_MN_LBO")) p.mn_lbo = (unsigned)atoi(e);            // bring-up probes only
-  if (const char* e = getenv("B2_TC_MN_SBO")) p.mn_sbo = (unsigned)atoi(e);
-  if (const char* e = getenv("B2_TC_MN_LAYOUT")) p.mn_layout = (unsigned)atoi(e);
   p.partial = nullptr;
   if (pl.splits > 1) {
     const size_t need = (size_t)pl.splits * M * N * sizeof(float);

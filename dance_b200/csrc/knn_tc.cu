@@ -41,7 +41,6 @@ struct Params {
   int32_t* cand_idx;             // [n_q, MC]
   float* cand_thr;               // [n_q]
   int n, n_q, q_begin, atoms, stages;
-  int debug;   // timing experiments (B2_KNN_TC_DEBUG): 1 skip the MMAs, 2 skip the selection math, 4 skip insertions
 };
 
 // max |x| → 2^e with max·2^e ∈ [256, 512);  scale[0] = 2^e, scale[1] = 4^-e
@@ -148,7 +147,7 @@ knn_candidates_tc_kernel(const __grid_constant__ Params p) {
         const uint32_t st = s_ring + stage * 2 * op_bytes;
         const uint32_t d_t = tmem + (uint32_t)(b * BR);
         uint32_t acc = 0;
-        for (int a = 0; a < p.atoms && !(p.debug & 1); ++a) {
+        for (int a = 0; a < p.atoms; ++a) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {             // 64 halves per atom = 4 k-steps of 16
             const uint32_t off = (uint32_t)(a * ATOM_BYTES + kk * 32);
@@ -199,7 +198,6 @@ knn_candidates_tc_kernel(const __grid_constant__ Params p) {
       }
 #pragma unroll
       for (int chunk = 0; chunk < BR / 32; ++chunk) {
-        if (p.debug & 2) break;
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem + lane_off + (uint32_t)(b * BR + chunk * 32), v);
         float est[32];
@@ -213,7 +211,7 @@ knn_candidates_tc_kernel(const __grid_constant__ Params p) {
         uint32_t mask = 0;
 #pragma unroll
         for (int c = 0; c < 32; ++c) mask |= (est[c] < thr ? 1u : 0u) << c;
-        if (live && mask && !(p.debug & 4)) {
+        if (live && mask) {
           // Per lane ≈ 9 % of the chunks contain a hit, per WARP ≈ 95 % do: the path must be short and exist once.
           float es[32];                               // dynamic indexing below → local memory, touched only on this path
 #pragma unroll
@@ -262,7 +260,8 @@ size_t workspace_bytes(int32_t n, int32_t d, int32_t n_q) {
 }
 
 bool eligible(int32_t n, int32_t d, int32_t n_q, int M) {
-  if (getenv("B2_KNN_NO_TC")) return false;
+  static const bool no_tc = getenv("B2_KNN_NO_TC") != nullptr;   // A/B path selector (both paths are bit-exact), read once
+  if (no_tc) return false;
   return M == MC && d >= 8 && padded_d(d) <= 64 * MAX_ATOMS && (int64_t)n * n_q >= (1ll << 24);
 }
 
@@ -311,7 +310,6 @@ int launch(const float* X, int64_t ldx, const float* sqn, int32_t n, int32_t d, 
   if (stages > 4) stages = 4;
   if (stages < 2) return B2_ERR_UNSUPPORTED;
   p.stages = stages;
-  p.debug = getenv("B2_KNN_TC_DEBUG") ? atoi(getenv("B2_KNN_TC_DEBUG")) : 0;
   const size_t smem = fixed + (size_t)stages * 2 * op_bytes;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {

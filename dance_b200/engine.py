@@ -150,21 +150,34 @@ class FeatureAEEngine:
         self.params.adam_step(self.lr)
         return z, r
 
+    def idle_step(self):
+        """Optimiser step of a rank whose shard has no rows left in this epoch (uneven shards under data parallelism): it
+        contributes a zero gradient to the all-reduce and applies the same reduced gradient, so the replicas stay identical and
+        every rank issues the same number of collectives."""
+        self.params.grad.zero_()
+        if self.grad_hook is not None:
+            self.grad_hook(self.params.grad)
+        self.params.adam_step(self.lr)
+
     def train_epoch(self, X: torch.Tensor, batch_size: int, regularizer_type: str = "noregu", regu_strength: float = 0.9,
                     ltmg: Optional[torch.Tensor] = None, z_out: Optional[torch.Tensor] = None,
-                    recon_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    recon_out: Optional[torch.Tensor] = None, n_steps: Optional[int] = None) -> torch.Tensor:
         """One epoch over device-resident X in order (DataLoader without shuffle, scgnn2.py:299).
         Optionally gathers the per-batch embeddings / reconstructions (the reference's ``torch.cat``
-        of all batches, scgnn2.py:1284-1291).  Returns the device scalar of summed batch losses."""
+        of all batches, scgnn2.py:1284-1291).  Returns the device scalar of summed batch losses.
+        ``n_steps`` (data parallelism): optimiser steps of the epoch = ``parallel.epoch_steps(bounds, batch_size)``."""
+        from .parallel import batch_schedule
         self.loss_acc.zero_()
-        n = X.shape[0]
-        for b0 in range(0, n, batch_size):
-            xb = X[b0:b0 + batch_size]
-            z, r = self.train_step(xb, None if ltmg is None else ltmg[b0:b0 + batch_size], regu_strength, regularizer_type)
+        for rng in batch_schedule(X.shape[0], batch_size, n_steps):
+            if rng is None:
+                self.idle_step()
+                continue
+            b0, b1 = rng
+            z, r = self.train_step(X[b0:b1], None if ltmg is None else ltmg[b0:b1], regu_strength, regularizer_type)
             if z_out is not None:
-                z_out[b0:b0 + xb.shape[0]].copy_(z)
+                z_out[b0:b1].copy_(z)
             if recon_out is not None:
-                recon_out[b0:b0 + xb.shape[0]].copy_(r)
+                recon_out[b0:b1].copy_(r)
         return self.loss_acc
 
 

@@ -271,8 +271,14 @@ def gae_loss_grad(z, labels: CSR, norm: float, pos_weight: float, mu=None, logva
     _chk(z, torch.float32, "z", 2)
     n, d = z.shape
     n_rows = n if n_rows is None else n_rows
+    if labels.shape[0] != n_rows or labels.shape[1] != n:
+        raise B2Error(f"gae_loss_grad: labels must be [{n_rows}, {n}] (rows of this shard x all columns), got {tuple(labels.shape)}")
     if dz is None:
         dz = torch.empty((n_rows, d), dtype=torch.float32, device=z.device)
+    else:
+        _chk(dz, torch.float32, "dz", 2)
+        if tuple(dz.shape) != (n_rows, d) or not dz.is_contiguous():
+            raise B2Error(f"gae_loss_grad: dz must be a contiguous [{n_rows}, {d}] buffer, got {tuple(dz.shape)} strides {dz.stride()}")
     ldm = ldd = 0
     if mu is not None:
         _chk(mu, torch.float32, "mu", 2)

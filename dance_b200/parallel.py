@@ -31,6 +31,23 @@ def shard_bounds(n: int, world: int) -> List[Tuple[int, int]]:
     return out
 
 
+def epoch_steps(bounds: List[Tuple[int, int]], batch_size: int) -> int:
+    """Optimiser steps per data-parallel epoch = mini-batches of the LARGEST shard.  Every rank must issue this many gradient
+    all-reduces per epoch: with uneven shards (e.g. 100 001 cells on 2 ranks, batch 12 500 → 5 and 4 local batches) a rank that
+    stopped after its own batches would leave the others waiting in the collective."""
+    return max((b - a + batch_size - 1) // batch_size for a, b in bounds)
+
+
+def batch_schedule(n_local: int, batch_size: int, n_steps: Optional[int] = None) -> List[Optional[Tuple[int, int]]]:
+    """Row ranges of one epoch over ``n_local`` rows; padded with ``None`` (= contribute a zero gradient) up to ``n_steps``."""
+    sched: List[Optional[Tuple[int, int]]] = [(b0, min(n_local, b0 + batch_size)) for b0 in range(0, n_local, batch_size)]
+    if n_steps is not None:
+        if n_steps < len(sched):
+            raise ValueError(f"n_steps={n_steps} is smaller than this rank's {len(sched)} local batches")
+        sched += [None] * (n_steps - len(sched))
+    return sched
+
+
 class Comm:
     """Thin wrapper over a torch.distributed process group (or a no-op for world size 1)."""
 

@@ -302,6 +302,62 @@ def _dense_gae_reference(z, L_dense, norm, pw, mu=None, lv=None):
     return cost.item(), z.grad
 
 
+def gae_reference_rows(z, rowptr, colidx, norm, pw, rows, chunk=512):
+    """fp64 closed form of gae_loss_function (scgnn2.py:603-612) restricted to `rows` × all columns, evaluated on the device with
+    torch in row chunks: returns (Σ over those rows of the per-logit cost · norm / n², the gradient rows).  With labels y (pattern
+    of the CSR, unit values) and pos_weight = y·pw:  cost = y·pw·softplus(−x) + (1−y)·softplus(x);  ∂/∂z_i = 2·Σ_j c_ij z_j with
+    c = σ(x) off the pattern and −pw·σ(−x) on it (labels symmetric)."""
+    import torch.nn.functional as F
+    zd = z.double()
+    n = zd.shape[0]
+    rp = rowptr.long()
+    loss = 0.0
+    out = torch.empty(len(rows), zd.shape[1], dtype=torch.float64, device=z.device)
+    for a in range(0, len(rows), chunk):
+        r = rows[a:a + chunk]
+        x = zd[r] @ zd.t()
+        c = torch.sigmoid(x)
+        cost = F.softplus(x)
+        # label pattern of these rows
+        cnt = rp[r + 1] - rp[r]
+        loc = torch.repeat_interleave(torch.arange(len(r), device=z.device), cnt)
+        start = torch.repeat_interleave(rp[r], cnt)
+        within = torch.arange(int(cnt.sum()), device=z.device) - torch.repeat_interleave(torch.cumsum(cnt, 0) - cnt, cnt)
+        cols = colidx.long()[start + within]
+        xe = x[loc, cols]
+        cost[loc, cols] = pw * F.softplus(-xe)
+        c[loc, cols] = -pw * torch.sigmoid(-xe)
+        loss += float(cost.sum())
+        out[a:a + chunk] = 2.0 * (c @ zd)
+    return norm * loss / (float(n) * n), out * (norm / (float(n) * n))
+
+
+def test_gae_loss_tensor_core_single_column_range(cuda):
+    """The branch bench.py times: n_rows ≥ 148·128 ⇒ j_splits == 1, every CTA sweeps ALL columns and the epilogue adds into dz without
+    atomics (gae_tch.cu).  Checked against the fp64 closed form evaluated in row chunks, full and row-sharded."""
+    from dance_b200 import ops
+    n, d, k = 19_200, 16, 7
+    gen = torch.Generator(device=cuda).manual_seed(11)
+    z = (torch.randn(n, d, device=cuda, generator=gen) * 0.45).contiguous()
+    idx = torch.randint(0, n, (n, k), device=cuda, dtype=torch.int32, generator=gen)
+    A = ops.knn_graph_build(idx.contiguous())
+    L = ops.CSR(A.rowptr, A.colidx, None, A.shape)
+    norm, pw = 0.5003, 1234.5
+    ref_loss, ref_dz = gae_reference_rows(z, A.rowptr, A.colidx, norm, pw, torch.arange(n, device=cuda))
+    loss, dz, _, _ = ops.gae_loss_grad(z, L, norm, pw)
+    assert abs(loss.item() - ref_loss) < 2e-6 * abs(ref_loss), (loss.item(), ref_loss)
+    assert rel_err(dz, ref_dz) < 2e-5
+    # one shard with ≥ 148·128 rows (still j_splits == 1) + a short one (j_splits > 1)
+    h = 148 * 128 + 3
+    rp = A.rowptr.long()
+    top = ops.CSR(A.rowptr[:h + 1].contiguous(), A.colidx[:rp[h]].contiguous(), None, (h, n))
+    bot = ops.CSR((A.rowptr[h:] - A.rowptr[h]).contiguous(), A.colidx[rp[h]:].contiguous(), None, (n - h, n))
+    la, dza, _, _ = ops.gae_loss_grad(z, top, norm, pw, row_begin=0, n_rows=h)
+    lb, dzb, _, _ = ops.gae_loss_grad(z, bot, norm, pw, row_begin=h, n_rows=n - h)
+    assert abs(la.item() + lb.item() - ref_loss) < 2e-6 * abs(ref_loss)
+    assert rel_err(torch.cat([dza, dzb]), ref_dz) < 2e-5
+
+
 @pytest.mark.parametrize("n,d", [(3000, 16), (2500, 16), (4133, 8), (2304, 32)])
 def test_gae_loss_tensor_core_path(cuda, n, d):
     """tcgen05 decoder (S in TMEM → SFU → G in TMEM → dZ) vs the dense fp64 formula and vs the CUDA-core kernel."""

@@ -5,12 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-import os
-
 pytestmark = pytest.mark.gpu
-# Added after the round-1 GPU budget was spent: the device-agnostic helpers are verified on the CPU (tests/test_transforms_api.py),
-# the device glue below has not run on a B200 yet — enabled with B2_RUN_UNVERIFIED=1 until it has.
-unverified = pytest.mark.skipif(os.environ.get("B2_RUN_UNVERIFIED") != "1", reason="not yet run on a B200 (see comment)")
 
 
 @pytest.mark.parametrize("mode", ["normalize", "standardize", "minmax", "l2"])
@@ -85,7 +80,6 @@ def test_pearson_corr_split_k_and_values(cuda):
         "FeatureFeatureGraph(threshold=0.3, positive_only=False, normalize_edges=True, score_func='pearson', score_func_kwargs={})"
 
 
-@unverified
 @pytest.mark.parametrize("score_func,kw", [("spearman", None), ("rbf", {"scale_mode": "med_dist"}), ("rbf", {"scale_mode": "ind_med_dist", "denom_scale": 2.0})])
 def test_feature_feature_graph_spearman_and_rbf(cuda, score_func, kw):
     from dance_b200.data import AnnDataLite, Data

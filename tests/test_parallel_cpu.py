@@ -160,5 +160,64 @@ def _dp_feature_ae_case(rank, world):
     return (torch.norm(flat - flat_ref) / torch.norm(flat_ref)).item()
 
 
+def _uneven_epoch_case(rank, world):
+    """Feature-AE data parallelism with uneven shards: 21 cells on 2 ranks, batch 5 → 11 / 10 rows = 3 / 2 local
+    batches.  Driving FeatureAEEngine.train_epoch's schedule (parallel.batch_schedule + idle steps) with the oracle's torch-CPU
+    model in place of the CUDA kernels: every rank issues epoch_steps() all-reduces (no hang) and the replicas stay identical
+    and equal to single-process training on the union batches."""
+    from dance_b200.parallel import Comm, batch_schedule, epoch_steps, shard_bounds
+    from oracle import port
+    comm = Comm()
+    n, g, bs = 21, 12, 5
+    X = torch.from_numpy(port.synthetic_expression(n, g, density=0.4, seed=3))
+    bounds = shard_bounds(n, world)
+    steps = epoch_steps(bounds, bs)
+    a, b = bounds[rank]
+    torch.manual_seed(0)
+    model = port.FeatureAE(g)
+    ref = port.FeatureAE(g)
+    ref.load_state_dict(model.state_dict())
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    ropt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    sched = batch_schedule(b - a, bs, steps)
+    n_coll = 0
+    for rng in sched:
+        opt.zero_grad()
+        if rng is not None:
+            xb = X[a:b][rng[0]:rng[1]]
+            _, r = model(xb)
+            port.feature_ae_loss(r, xb, "LTMG", 0.9, torch.zeros_like(xb)).backward()
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in model.parameters()])
+        comm.allreduce_sum_(flat)
+        n_coll += 1
+        o = 0
+        for p in model.parameters():
+            p.grad = flat[o:o + p.numel()].view_as(p).clone()
+            o += p.numel()
+        opt.step()
+    # single-process reference: step s trains on the union of every rank's s-th batch
+    for s in range(steps):
+        rows = []
+        for ra, rb in bounds:
+            sc = batch_schedule(rb - ra, bs, steps)[s]
+            if sc is not None:
+                rows += list(range(ra + sc[0], ra + sc[1]))
+        ropt.zero_grad()
+        xb = X[rows]
+        _, r = ref(xb)
+        port.feature_ae_loss(r, xb, "LTMG", 0.9, torch.zeros_like(xb)).backward()
+        ropt.step()
+    pf = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    rf = torch.cat([p.detach().reshape(-1) for p in ref.parameters()])
+    return n_coll, steps, len([s for s in sched if s is None]), (torch.norm(pf - rf) / torch.norm(rf)).item()
+
+
+def test_uneven_shards_issue_equal_collectives_gloo():
+    out = _run("_uneven_epoch_case")
+    assert out[0][0] == out[1][0] == out[0][1] == 3
+    assert out[0][2] == 0 and out[1][2] == 1          # rank 1 pads one idle step
+    assert max(v[3] for v in out.values()) < 1e-5
+
+
 def test_data_parallel_feature_ae_gradients_gloo():
     assert max(_run("_dp_feature_ae_case").values()) < 1e-5
