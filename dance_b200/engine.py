@@ -93,13 +93,15 @@ class FeatureAEEngine:
             self.params.p[k].copy_(torch.as_tensor(v, dtype=torch.float32))
 
     # -- buffers ----------------------------------------------------------------
-    def _buffers(self, B: int):
-        bufs = self._bufs.get(B)
+    def _buffers(self, B: int, slot: int = 0):
+        """Activation / gradient buffers of a batch of B rows.  ``slot`` selects one of several independent sets, so that a
+        caller can still be reading batch b's outputs (device→host copy on a side stream) while batch b+1 trains."""
+        bufs = self._bufs.get((B, slot))
         if bufs is None:
             H, E, D = self.HID, self.EMB, self.dim
             mk = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
             bufs = dict(h1=mk(B, H), z=mk(B, E), h3=mk(B, H), r=mk(B, D), dr=mk(B, D), dh3=mk(B, H), dz=mk(B, E), dh1=mk(B, H))
-            self._bufs[B] = bufs
+            self._bufs[(B, slot)] = bufs
         return bufs
 
     # -- forward ----------------------------------------------------------------
@@ -115,19 +117,24 @@ class FeatureAEEngine:
 
     # -- one optimiser step -------------------------------------------------------
     def train_step(self, x: torch.Tensor, ltmg: Optional[torch.Tensor] = None, regu_strength: float = 0.9,
-                   regularizer_type: str = "noregu"):
+                   regularizer_type: str = "noregu", slot: int = 0, row_weight: Optional[torch.Tensor] = None,
+                   x_dropout: Optional[torch.Tensor] = None):
         """One mini-batch of train_handler (scgnn2.py:1256-1281): forward, loss_function_graph
         ('noregu' | 'LTMG'), backward, Adam.  The batch loss is accumulated into ``self.loss_acc``.
         Returns (z, recon) views into the engine's buffers (valid until the next call with the same batch size)."""
         P, G, pr = self.params.p, self.params.g, self.precision
         B = x.shape[0]
-        b = self._buffers(B)
+        b = self._buffers(B, slot)
         z, r = self.forward(x, b)
         if regularizer_type == "noregu":
             ops.mse_sum_loss_grad(r, x, None, 0.0, relu_mask=True, grad=b["dr"], loss_out=self.loss_acc)
         elif regularizer_type == "LTMG":
             # ltmg=None ⇔ the all-zero TRS matrix of the reference driver (scgnn2.py:40)
             ops.mse_sum_loss_grad(r, x, ltmg, regu_strength, relu_mask=True, grad=b["dr"], loss_out=self.loss_acc)
+        elif regularizer_type == "Celltype":
+            # Cluster-AE inside the EM loop (scgnn2.py:1316-1326): 0.3·BCE + ‖(x_dropout − r)[x_dropout≠0]‖ + 0.3·(adj_cc @ mse).sum()
+            # + 0.1·(celltype_cc @ mse).sum(); the two dense products are per-row weights here (row_weight, see ops.graph_regu_weights)
+            ops.celltype_loss_grad(r, x, x_dropout, row_weight, relu_mask=True, grad=b["dr"], loss_out=self.loss_acc)
         else:
             raise ValueError(f"unsupported regularizer_type {regularizer_type!r}")
         # layer 4:  r = relu(h3 W4ᵀ + b4)
@@ -145,6 +152,9 @@ class FeatureAEEngine:
         # layer 1
         ops.gemm(b["dh1"], x, transA=True, out=G["fc1.weight"], precision=pr)
         ops.colsum(b["dh1"], out=G["fc1.bias"])
+        if regularizer_type == "Celltype":
+            # `loss = loss + 1 * l1 + 0 * l2` over all parameters (train_handler, scgnn2.py:1268-1274)
+            ops.l1_grad_add(self.params.flat, self.params.grad, 1.0, self.loss_acc)
         if self.grad_hook is not None:
             self.grad_hook(self.params.grad)
         self.params.adam_step(self.lr)

@@ -7,14 +7,18 @@ Same names, argument meaning and return types as the reference:
   * ``graph_AE_handler(X_embed, CCC_graph, args, param)``               scgnn2.py:530-600
 numpy in / numpy out at this boundary, everything in between stays in HBM.
 
+  * ``clustering_handler`` / ``graph_celltype_regu_handler`` / ``cluster_AE_handler``       scgnn2.py:138-216, 716-752, 821-880
+numpy in / numpy out at this boundary, everything in between stays in HBM.
+
 Differences that are deliberate and documented in DESIGN.md:
   * the N×N decoder logits, the dense label matrix (scgnn2.py:557) and ``recon_graph`` are never
     materialised; ``graph_AE_handler`` returns the ``edgeList`` as an [N·k, 2] index array plus a
     weight array instead of a Python list of tuples, and ``CCC_graph_hat`` as None above
     ``dense_recon_max_cells`` cells;
-  * the EM iterations (clustering_handler / cluster_AE_handler, scgnn2.py:138-216, 821-880) are
-    SURVEY §8(f) "next" rows and are not built yet: ``fit`` runs the pre-EM stage (the two
-    handlers above) and raises for ``total_epoch > 0``.
+  * the EM iterations never form the two dense N×N regulariser matrices of ``graph_celltype_regu_handler``: the Cluster-AE
+    loss only needs their column sums inside each cluster (``ops.graph_regu_weights``); Louvain runs in host C++ on the
+    sparse graph (the reference densifies it for igraph), KMeans as Lloyd iterations on the device seeded by sklearn's
+    k-means++ (same ``random_state=0``; above ``kmeans_init_max_cells`` cells on a fixed-seed subsample).
 """
 from __future__ import annotations
 
@@ -25,7 +29,7 @@ from typing import Any, Optional
 import numpy as np
 import torch
 
-from .. import ops
+from .. import hostio, ops
 from ..engine import FeatureAEEngine, GATEngine, GraphAEEngine
 
 logger = logging.getLogger("dance_b200.scgnn2")
@@ -52,32 +56,70 @@ def feature_AE_handler(X, TRS, args, param, model_state=None):
         raise NotImplementedError("feature_AE_dropout_prob > 0 (input masking, scgnn2.py:1260) is not built")
     if getattr(args, "feature_AE_concat_prev_embed", None) and param["epoch_num"] > 0:
         raise NotImplementedError("feature_AE_concat_prev_embed is not built")
-    Xd = torch.as_tensor(X, dtype=torch.float32).to(dev, non_blocking=True)
+    pool = param.get("io_pool")
+    resident = isinstance(X, torch.Tensor) and X.is_cuda
+    if resident:                                   # already in HBM (EM iterations hand device tensors from stage to stage)
+        Xd, host = X.float().contiguous(), None
+    else:
+        host = hostio.as_host_tensor(X)
+        Xd = torch.empty(host.shape, dtype=torch.float32, device=dev)
+    n, dim = Xd.shape
     ltmg = None
     if TRS is not None and np.any(TRS):
         ltmg = torch.as_tensor(TRS, dtype=torch.float32).to(dev)
-    eng = FeatureAEEngine(Xd.shape[1], device=dev, lr=args.feature_AE_learning_rate, precision=param.get("precision"),
-                          seed=param.get("seed"))
+    eng = FeatureAEEngine(dim, device=dev, lr=args.feature_AE_learning_rate, precision=param.get("precision"), seed=param.get("seed"))
     if param["epoch_num"] > 0 and model_state is not None:
         eng.load_state_dict(model_state["model"])
     # regu_type=["LTMG", "noregu"][epoch_num > 0]   (scgnn2.py:314)
     regu = "noregu" if param["epoch_num"] > 0 else "LTMG"
-    n = Xd.shape[0]
+    batches = [(b0, min(n, b0 + batch_size)) for b0 in range(0, n, batch_size)]
     z_all = torch.empty(n, eng.EMB, dtype=torch.float32, device=dev)
-    r_all = torch.empty(n, Xd.shape[1], dtype=torch.float32, device=dev)
+    keep_dev = bool(param.get("keep_on_device"))          # EM loop: outputs stay in HBM, nothing is copied back
+    recon_dev = torch.empty(n, dim, dtype=torch.float32, device=dev) if keep_dev else None
+    recon_host = None if keep_dev else hostio.pinned_empty(pool, "feature_recon", (n, dim))
+    up = hostio.Uploader(host, dev, pool, max_rows=batch_size) if host is not None else None
+    down = None if keep_dev else hostio.Downloader(dev)
+    main = torch.cuda.current_stream(dev)
+    if total_epoch == 0:
+        raise ValueError("feature_AE_epoch must be >= 1 (the reference's train_handler returns the last epoch's outputs)")
     for epoch in range(total_epoch):
-        last = epoch == total_epoch - 1
-        loss = eng.train_epoch(Xd, batch_size, regu, args.feature_AE_regu_strength, ltmg, z_all if last else None,
-                               r_all if last else None)
+        first, last = epoch == 0 and up is not None, epoch == total_epoch - 1
+        eng.loss_acc.zero_()
+        ready, queued = {}, 0
+        lookahead = len(batches) if (up is not None and up.pinned) else 2
+        slot_busy = [None, None]
+        for b, (b0, b1) in enumerate(batches):
+            if first:                                     # epoch 0 streams X in: batch b trains while b+1.. are in flight
+                while queued < min(len(batches), b + 1 + lookahead):
+                    q0, q1 = batches[queued]
+                    ready[queued] = up.copy_rows(q0, q1, Xd[q0:q1])
+                    queued += 1
+                main.wait_event(ready.pop(b))
+            slot = b & 1
+            if slot_busy[slot] is not None:               # the download of batch b-2's reconstruction has left this buffer set
+                main.wait_event(slot_busy[slot])
+                slot_busy[slot] = None
+            z, r = eng.train_step(Xd[b0:b1], None if ltmg is None else ltmg[b0:b1], args.feature_AE_regu_strength, regu, slot=slot)
+            if last:
+                z_all[b0:b1].copy_(z)
+                if keep_dev:
+                    recon_dev[b0:b1].copy_(r)
+                else:
+                    slot_busy[slot] = down.copy(r, recon_host[b0:b1])
         if logger.isEnabledFor(logging.INFO):
-            logger.info(f"Epoch: {epoch+1}/{total_epoch}, Average loss: {loss.item() / n:.4f}")
+            logger.info(f"Epoch: {epoch+1}/{total_epoch}, Average loss: {eng.loss_acc.item() / n:.4f}")
     checkpoint = {"model": eng.state_dict(),
                   "optimizer": {"step": eng.params.step, "exp_avg": eng.params.exp_avg.clone(),
                                 "exp_avg_sq": eng.params.exp_avg_sq.clone()}}
     param["_feature_AE_engine"] = eng
-    X_embed_out = z_all.cpu().numpy()
-    X_recon_out = r_all.cpu().numpy()[:, :param["n_feature_orig"]]
-    return X_embed_out, X_recon_out, checkpoint
+    nf = param["n_feature_orig"]
+    if keep_dev:
+        return z_all, recon_dev[:, :nf], checkpoint
+    embed_host = hostio.pinned_empty(pool, "feature_embed", (n, eng.EMB))
+    embed_host.copy_(z_all, non_blocking=True)
+    down.synchronize()
+    torch.cuda.current_stream(dev).synchronize()
+    return embed_host.numpy(), recon_host.numpy()[:, :nf], checkpoint
 
 
 def build_knn_graph(x_embed: torch.Tensor, neighborhood_factor):
@@ -100,21 +142,36 @@ def graph_AE_handler(X_embed, CCC_graph, args, param, dense_recon_max_cells: int
     if args.graph_AE_retain_weights:
         raise NotImplementedError("graph_AE_retain_weights permutes node order in the reference (App. B); not built")
     dev = param["device"]
-    X = np.asarray(X_embed, dtype=np.float32)
-    if args.graph_AE_normalize_embed == "sum1":
-        zD = X / np.clip(X.sum(1, keepdims=True), a_min=1, a_max=None)          # scgnn2.py:622-628
-    elif args.graph_AE_normalize_embed == "binary":
-        zD = (1.0 * (X > np.mean(X, axis=0))).astype(np.float32)
+    pool = param.get("io_pool")
+    if isinstance(X_embed, torch.Tensor) and X_embed.is_cuda:
+        xe = X_embed.float().contiguous()
     else:
-        zD = X
-    xe = torch.from_numpy(X).to(dev)
-    A, knn_idx, knn_dist = build_knn_graph(xe, args.graph_AE_neighborhood_factor)
-    n = X.shape[0]
+        xh = hostio.as_host_tensor(X_embed)
+        xe = torch.empty(xh.shape, dtype=torch.float32, device=dev)
+        xe.copy_(xh, non_blocking=True)
+    if args.graph_AE_normalize_embed == "sum1":
+        xin = xe / xe.sum(1, keepdim=True).clamp(min=1)                         # scgnn2.py:622-628
+    elif args.graph_AE_normalize_embed == "binary":
+        xin = (xe > xe.mean(0)).float()
+    else:
+        xin = xe
+    # ``param["graph_cache"]`` (extension): a dict that keeps the kNN graph of a previous call on the SAME embedding — the
+    # reference rebuilds it on every call (feature2adj, scgnn2.py:555); bench.py uses it to time the training epochs alone.
+    cache = param.get("graph_cache")
+    if cache is not None and cache.get("n") == xe.shape[0] and "A" in cache:
+        A, knn_idx, knn_dist = cache["A"], cache["knn_idx"], cache["knn_dist"]
+    else:
+        A, knn_idx, knn_dist = build_knn_graph(xe, args.graph_AE_neighborhood_factor)
+        if cache is not None:
+            cache.clear()
+            cache.update(n=xe.shape[0], A=A, knn_idx=knn_idx, knn_dist=knn_dist)
+    n = xe.shape[0]
     adj_sum = A.nnz - n                                                         # Σ adj_train (no diagonal)
     pos_weight = float(n * n - adj_sum) / adj_sum                               # scgnn2.py:567
     norm = n * n / float((n * n - adj_sum) * 2)                                 # scgnn2.py:568-569
     labels = ops.CSR(A.rowptr, A.colidx, None, A.shape)                         # A + I: pattern of Â, unit entries
-    xin = torch.from_numpy(np.ascontiguousarray(zD, dtype=np.float32)).to(dev)
+    xin = xin.contiguous()
+    out_kw = dict(pool=pool, cache=cache, keep_dev=bool(param.get("keep_on_device")))
     if args.graph_AE_use_GAT:
         # edge_index = edgeList (i → its k neighbours), directed, no self loops (scgnn2.py:560-563); the kernels
         # index the graph by TARGET node, i.e. the transpose of the regular kNN-list CSR
@@ -122,7 +179,7 @@ def graph_AE_handler(X_embed, CCC_graph, args, param, dense_recon_max_cells: int
         src_csr = ops.CSR(torch.arange(0, n * k + 1, k, dtype=torch.int32, device=dev), knn_idx.reshape(-1).contiguous(), None, (n, n))
         T, _ = ops.csr_transpose(src_csr)
         Tt, t_perm = ops.csr_transpose(T)
-        geng = GATEngine(X.shape[1], args.gat_hid_embed, args.graph_AE_embedding_size, args.gat_multi_heads, device=dev,
+        geng = GATEngine(xe.shape[1], args.gat_hid_embed, args.graph_AE_embedding_size, args.gat_multi_heads, device=dev,
                          lr=args.graph_AE_learning_rate, precision=param.get("precision"), seed=param.get("seed"))
         z = None
         for epoch in range(args.graph_AE_epoch):
@@ -130,8 +187,8 @@ def graph_AE_handler(X_embed, CCC_graph, args, param, dense_recon_max_cells: int
             if logger.isEnabledFor(logging.INFO):
                 logger.info(f"Epoch: {epoch+1}/{args.graph_AE_epoch}, Current loss: {geng.loss.item():.4f}")
         param["_graph_AE_engine"] = geng
-        return _graph_ae_outputs(z, n, knn_idx, knn_dist, A, dense_recon_max_cells)
-    eng = GraphAEEngine(X.shape[1], args.graph_AE_embedding_size, device=dev, lr=args.graph_AE_learning_rate,
+        return _graph_ae_outputs(z, n, knn_idx, knn_dist, A, dense_recon_max_cells, **out_kw)
+    eng = GraphAEEngine(xe.shape[1], args.graph_AE_embedding_size, device=dev, lr=args.graph_AE_learning_rate,
                         precision=param.get("precision"), seed=param.get("seed"))
     gen = torch.Generator(device=dev)
     gen.manual_seed(int(param.get("seed") or 0))
@@ -143,24 +200,215 @@ def graph_AE_handler(X_embed, CCC_graph, args, param, dense_recon_max_cells: int
         if logger.isEnabledFor(logging.INFO):
             logger.info(f"Epoch: {epoch+1}/{args.graph_AE_epoch}, Current loss: {eng.loss.item():.4f}")
     param["_graph_AE_engine"] = eng
-    return _graph_ae_outputs(z, n, knn_idx, knn_dist, A, dense_recon_max_cells)
+    return _graph_ae_outputs(z, n, knn_idx, knn_dist, A, dense_recon_max_cells, **out_kw)
 
 
-def _graph_ae_outputs(z, n, knn_idx, knn_dist, A, dense_recon_max_cells):
-    embed_out = z.cpu().numpy()
+def _graph_ae_outputs(z, n, knn_idx, knn_dist, A, dense_recon_max_cells, pool=None, cache=None, keep_dev=False):
+    """(graph_embed, recon_graph | None, edgeList, adj) like scgnn2.py:597-600.  ``edgeList`` is ([N·k, 2] int64 pairs, fp64
+    weights 1/(d+1e-16)) instead of a Python list of tuples; ``adj`` the 0/1 union-symmetrised adjacency without diagonal."""
+    if keep_dev:
+        return z, None, (knn_idx, knn_dist), A
+    embed_host = hostio.pinned_empty(pool, "graph_embed", tuple(z.shape))
+    embed_host.copy_(z, non_blocking=True)
     recon = (z @ z.t()).cpu().numpy() if n <= dense_recon_max_cells else None   # InnerProductDecoder output, small N only
-    k = knn_idx.shape[1]
-    edge_index = np.stack([np.repeat(np.arange(n), k), knn_idx.cpu().numpy().reshape(-1).astype(np.int64)], 1)
-    edge_w = 1.0 / (knn_dist.cpu().numpy().reshape(-1) + 1e-16)                 # scgnn2.py:686
-    adj = A.to_scipy()
-    adj.data[:] = 1.0
-    adj.setdiag(0)
-    adj.eliminate_zeros()
-    return embed_out, recon, (edge_index, edge_w), adj
+    if cache is not None and "edge_list" in cache:
+        edge_list, adj = cache["edge_list"], cache["adj"]
+    else:
+        k = knn_idx.shape[1]
+        src = torch.arange(n, device=z.device, dtype=torch.int64).repeat_interleave(k)
+        edge_index = torch.stack([src, knn_idx.reshape(-1).long()], 1).cpu().numpy()
+        edge_w = (1.0 / (knn_dist.reshape(-1).double() + 1e-16)).cpu().numpy()  # scgnn2.py:686
+        edge_list = (edge_index, edge_w)
+        import scipy.sparse as sp
+        rp = A.rowptr.long()
+        rows = torch.repeat_interleave(torch.arange(n, device=z.device), rp[1:] - rp[:-1])
+        off = A.colidx.long() != rows                                           # drop the diagonal of A + I on the device
+        counts = torch.zeros(n + 1, dtype=torch.int64, device=z.device)
+        counts[1:] = torch.bincount(rows[off], minlength=n)
+        indptr = torch.cumsum(counts, 0).cpu().numpy()
+        indices = A.colidx[off].cpu().numpy()
+        adj = sp.csr_matrix((np.ones(indices.shape[0], dtype=np.float32), indices, indptr), shape=(n, n))
+        if cache is not None:
+            cache["edge_list"], cache["adj"] = edge_list, adj
+    torch.cuda.current_stream(z.device).synchronize()
+    return embed_host.numpy(), recon, edge_list, adj
+
+
+def _edge_list_arrays(edgeList):
+    """edgeList as ([E, 2] int pairs, [E] weights) — accepts this module's array form or the reference's list of (i, j, w) tuples."""
+    if isinstance(edgeList, tuple) and len(edgeList) == 2 and hasattr(edgeList[0], "shape"):
+        idx, w = edgeList
+        if isinstance(idx, torch.Tensor):      # device form (knn_idx [N, k] int32, knn_dist [N, k] fp64) from keep_on_device
+            n, k = idx.shape
+            src = np.repeat(np.arange(n), k)
+            return np.stack([src, idx.cpu().numpy().reshape(-1).astype(np.int64)], 1), 1.0 / (w.cpu().numpy().reshape(-1) + 1e-16)
+        return np.asarray(idx), np.asarray(w)
+    arr = np.asarray(edgeList, dtype=np.float64)
+    return arr[:, :2].astype(np.int64), arr[:, 2]
+
+
+def generateLouvainCluster(edgeList, n_nodes: Optional[int] = None):
+    """Louvain communities of the undirected weighted kNN graph (scgnn2.py:193-215): returns (labels list, n_communities).
+    networkx.Graph.add_weighted_edges_from keeps ONE weight per undirected pair (the last one written; both directions carry
+    the same 1/(d+1e-16)), loops dropped — here: the elementwise maximum of W and Wᵀ in CSR, then ``b2_louvain_csr_host``."""
+    import scipy.sparse as sp
+    idx, w = _edge_list_arrays(edgeList)
+    n = int(idx.max()) + 1 if n_nodes is None else n_nodes
+    keep = idx[:, 0] != idx[:, 1]
+    W = sp.csr_matrix((w[keep], (idx[keep, 0], idx[keep, 1])), shape=(n, n))
+    W = W.maximum(W.T).tocsr()
+    W.sort_indices()
+    labels, nc, _ = ops.louvain_host(W.indptr, W.indices, W.data)
+    return labels.tolist(), nc
+
+
+def trimClustering(listResult, minMemberinCluster=5, maxClusterNumber=30):
+    """scgnn2.py:230-254: clusters that are too small or numbered ≥ maxClusterNumber are merged into one label.  (The reference
+    counts members starting from 0 — ``numDict[item] = 0`` on first sight — so "fewer than 5" means ≤ 5 cells; kept.)  Labels are
+    renumbered contiguously afterwards: the reference's ``cluster_output_handler`` would index past its list otherwise."""
+    lab = np.asarray(listResult).copy()
+    ids, counts = np.unique(lab, return_counts=True)
+    size = len(ids)
+    drop = [c for c in range(size) if (dict(zip(ids, counts)).get(c, 0) - 1) < minMemberinCluster or c >= maxClusterNumber]
+    lab[np.isin(lab, drop)] = maxClusterNumber
+    _, lab = np.unique(lab, return_inverse=True)
+    return lab.tolist()
+
+
+def cluster_output_handler(listResult):
+    lab = np.asarray(listResult)
+    return list(listResult), [np.nonzero(lab == c)[0].tolist() for c in range(len(set(lab.tolist())))]
+
+
+def _normalizer(X, base, axis=0):
+    from sklearn.preprocessing import minmax_scale
+    upper, lower = np.quantile(base, q=0.9), np.quantile(base, q=0.1)
+    if upper != lower:
+        return minmax_scale(X, feature_range=(lower, upper), axis=axis)
+    return minmax_scale(X, feature_range=(np.quantile(base, q=0), np.quantile(base, q=1)), axis=axis)
+
+
+def kmeans_fit_predict(embed, k: int, device, seed: int = 0, init_max_cells: int = 200_000):
+    """``KMeans(n_clusters=k, n_init="auto", random_state=0).fit_predict(embed)`` (scgnn2.py:186): k-means++ seeding by
+    sklearn's own routine on the host (on a fixed-seed subsample above ``init_max_cells`` cells), Lloyd iterations on the device."""
+    from sklearn.cluster import kmeans_plusplus
+    xe = embed if isinstance(embed, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(embed, dtype=np.float32))
+    xe = xe.to(device).float().contiguous()
+    n = xe.shape[0]
+    if n > init_max_cells:
+        sel = np.sort(np.random.RandomState(seed).choice(n, init_max_cells, replace=False))
+        host = xe[torch.from_numpy(sel).to(device)].cpu().numpy()
+    else:
+        host = xe.cpu().numpy()
+    host = host - host.mean(0)                      # KMeans centres the data before seeding (sklearn _kmeans.py: X -= X_mean)
+    rs = np.random.RandomState(seed)
+    seeds_rs = np.random.RandomState(rs.randint(np.iinfo(np.int32).max))
+    centers, _ = kmeans_plusplus(host.astype(np.float32), k, random_state=seeds_rs)
+    mean = xe.mean(0, keepdim=True)
+    xc = (xe - mean).contiguous()
+    C0 = torch.from_numpy(np.ascontiguousarray(centers, dtype=np.float32)).to(device)
+    labels, _, _ = ops.kmeans(xc, C0)
+    return labels
+
+
+def clustering_handler(edgeList, args, param):
+    """scgnn2.py:138-190: Louvain on the kNN graph fixes the cluster COUNT (k = round(max(k_louvain·resolution, 2))), KMeans on
+    the chosen embedding gives the labels."""
+    logger.info("Start Clustering")
+    ge, fe = param["graph_embed"], param["feature_embed"]
+    to_np = lambda a: a.cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    if args.clustering_embed == "feature":
+        embed = fe
+    elif args.clustering_embed == "both":
+        embed = np.concatenate((to_np(ge), _normalizer(to_np(fe), base=to_np(ge), axis=0)), axis=1).astype(np.float32)
+    else:
+        if args.clustering_embed != "graph":
+            logger.error("clustering_embed argument not recognized, using graph embed")
+        embed = ge
+    param["clustering_embed"] = embed
+    n = embed.shape[0]
+    listResult, _ = generateLouvainCluster(edgeList, n)
+    k_louvain = len(np.unique(listResult))
+    logger.info(f" Louvain clusters count: {k_louvain}")
+    resolution = 0.8 if n < 2000 else 0.5
+    param["k_float"] = max(k_louvain * resolution, 2)
+    k = round(param["k_float"])
+    logger.info(f" Adjusted clusters count: {k}")
+    if not args.clustering_louvain_only:
+        if args.clustering_method == "KMeans":
+            listResult = kmeans_fit_predict(embed, k, param["device"], seed=0,
+                                            init_max_cells=param.get("kmeans_init_max_cells", 200_000)).cpu().numpy().tolist()
+        elif args.clustering_method == "AffinityPropagation":
+            from sklearn.cluster import AffinityPropagation          # O(N²) host method, small data only — same call as the reference
+            listResult = AffinityPropagation(random_state=args.seed).fit_predict(to_np(embed)).tolist()
+    if len(set(listResult)) > 30 or len(set(listResult)) <= 1:
+        logger.info(f" Stopping: Number of clusters is {len(set(listResult))}")
+        listResult = trimClustering(listResult, minMemberinCluster=5, maxClusterNumber=30)
+    logger.info(f"Total Cluster Number: {len(set(listResult))}")
+    return cluster_output_handler(listResult)
+
+
+def graph_celltype_regu_handler(adj, cluster_labels, device=None):
+    """scgnn2.py:716-724 in sparse form: instead of the two dense N×N matrices returns what the Cluster-AE loss takes from them,
+    per cell: (w_graph [N] = column sums of the row-normalised adjacency inside the cell's cluster, w_celltype [N] = 1)."""
+    lab = torch.as_tensor(np.asarray(cluster_labels), dtype=torch.int32)
+    if isinstance(adj, ops.CSR):
+        A = adj
+    else:                                                                       # scipy 0/1 adjacency without diagonal
+        A = ops.CSR.from_scipy(adj, device, with_values=False)
+    lab = lab.to(A.rowptr.device)
+    w_graph = ops.graph_regu_weights(A, lab)
+    return w_graph, torch.ones_like(w_graph)
+
+
+def cluster_AE_handler(X_recon, TRS, clusterIndexList, args, param, model_state):
+    """scgnn2.py:821-880: one Cluster-AE per cluster, initialised from the Feature-AE weights, trained on the cluster's rows of
+    X_recon with the "Celltype" regulariser; returns the stitched reconstruction (numpy, or a device tensor under
+    ``keep_on_device``).  Clusters larger than ``cluster_AE_batch_size`` are trained in mini-batches with the full-cluster
+    regulariser weights (the reference's dense [cluster × cluster] @ [batch × gene] product requires a single batch)."""
+    logger.info("Starting Cluster AE")
+    dev = param["device"]
+    bs, epochs = args.cluster_AE_batch_size, args.cluster_AE_epoch
+    if args.cluster_AE_dropout_prob:
+        raise NotImplementedError("cluster_AE_dropout_prob > 0 is not built (the example default is 0)")
+    to_dev = lambda a: a.float().contiguous() if (isinstance(a, torch.Tensor) and a.is_cuda) else hostio.as_host_tensor(a).to(dev)
+    Xr = to_dev(X_recon)
+    xd = param.get("_x_dropout_dev")
+    if xd is None:
+        xd = to_dev(param["x_dropout"])
+        param["_x_dropout_dev"] = xd
+    w_graph, w_ct = param["impute_regu"]
+    roww = (0.3 + 0.3 * w_graph + 0.1 * w_ct).contiguous()
+    out = torch.zeros_like(Xr)
+    nf = param["n_feature_orig"]
+    for ci, members in enumerate(clusterIndexList):
+        logger.info(f"Training cluster {ci+1}/{len(clusterIndexList)} -> size = {len(members)}")
+        if len(members) == 0:
+            continue
+        rows = torch.as_tensor(np.asarray(members), dtype=torch.int64, device=dev)
+        xc, xdc, wc = Xr[rows].contiguous(), xd[rows][:, :nf].contiguous(), roww[rows].contiguous()
+        eng = FeatureAEEngine(Xr.shape[1], device=dev, lr=args.cluster_AE_learning_rate, precision=param.get("precision"))
+        eng.load_state_dict(model_state["model"])
+        m = xc.shape[0]
+        rc = torch.empty_like(xc)
+        for epoch in range(epochs):
+            eng.loss_acc.zero_()
+            for b0 in range(0, m, bs):
+                b1 = min(m, b0 + bs)
+                _, r = eng.train_step(xc[b0:b1], None, args.cluster_AE_regu_strength, "Celltype", row_weight=wc[b0:b1],
+                                      x_dropout=xdc[b0:b1])
+                if epoch == epochs - 1:
+                    rc[b0:b1].copy_(r)
+        out[rows] = rc
+    if param.get("keep_on_device"):
+        return out
+    host = hostio.pinned_empty(param.get("io_pool"), "cluster_recon", tuple(out.shape))
+    host.copy_(out)
+    return host.numpy()
 
 
 class ScGNN2:
-    """Drop-in for ``dance.modules.single_modality.imputation.scgnn2.ScGNN2`` (pre-EM stage)."""
+    """Drop-in for ``dance.modules.single_modality.imputation.scgnn2.ScGNN2`` (pre-EM stage + EM iterations)."""
 
     def __init__(self, args, device: str = "auto", precision: Optional[str] = None, seed: Optional[int] = None):
         self.args = args
@@ -179,40 +427,57 @@ class ScGNN2:
         param["total_epoch"] = epochs
         param["n_feature_orig"] = x.shape[1]
         param["x_dropout"] = x
+        # inside fit() every stage hands DEVICE tensors to the next one (no N×G round trips between handlers); only the final
+        # imputed matrix is copied back.  The public handlers keep their numpy-in / numpy-out contract when called directly.
+        param["keep_on_device"] = True
+        param["io_pool"] = hostio.IOPool()
         x_embed, x_feature_recon, model_state = feature_AE_handler(x, trs_mat, args, param)
         graph_embed, _, edge_list, adj = graph_AE_handler(x_embed, None, args, param)
-        self.x_embed, self.graph_embed, self.edge_list, self.adj = x_embed, graph_embed, edge_list, adj
-        self.model_state = model_state
-        if epochs > 0:
-            raise NotImplementedError(
-                "EM iterations (clustering_handler, graph_celltype_regu_handler, cluster_AE_handler; reference "
-                "scgnn2.py:56-66) are SURVEY §8(f) 'next' rows and are not built yet; run with total_epoch=0")
-        self.x_imputed = x_feature_recon
+        x_imputed = x_feature_recon
+        logger.info("Entering main loop")
+        for i in range(epochs):
+            logger.info(f"\n==========> scGNN Epoch {i+1}/{epochs} <==========")
+            param["epoch_num"] = i + 1
+            param["feature_embed"], param["graph_embed"] = x_embed, graph_embed
+            cluster_labels, cluster_lists_of_idx = clustering_handler(edge_list, args, param)
+            param["impute_regu"] = graph_celltype_regu_handler(adj, cluster_labels, self.device)
+            x_imputed = cluster_AE_handler(x_feature_recon, trs_mat, cluster_lists_of_idx, args, param, model_state)
+            x_embed, x_feature_recon, model_state = feature_AE_handler(x_imputed, trs_mat, args, param, model_state)
+            graph_embed, _, edge_list, adj = graph_AE_handler(x_embed, None, args, param)
+            self.cluster_labels = cluster_labels
+        param["keep_on_device"] = False
+        self.x_embed, self.graph_embed = x_embed.cpu().numpy(), graph_embed.cpu().numpy()
+        self.edge_list, self.adj, self.model_state = edge_list, adj, model_state
+        # the reference returns the LAST Cluster-AE output (x_imputed), or — with total_epoch = 0 — nothing at all
+        # (self.x_imputed is unbound, scgnn2.py:68); here the pre-EM Feature-AE reconstruction is returned in that case
+        self.x_imputed = x_imputed.cpu().numpy() if isinstance(x_imputed, torch.Tensor) else x_imputed
+        param.pop("_x_dropout_dev", None)
 
     def predict(self, x: Optional[Any] = None) -> np.ndarray:
         return self.x_imputed
 
     def score(self, true_expr, imputed_expr, mask=None, metric="MSE", log1p=True, test_idx=None):
-        """Same scoring as the reference (scgnn2.py:73-121): 'RMSE' | 'PCC' | 'MRE'."""
-        allowd_metrics = {"RMSE", "PCC", "MRE"}
-        if metric not in allowd_metrics:
-            raise ValueError("scoring metric %r." % allowd_metrics)
-        if test_idx is None:
-            test_idx = range(len(true_expr))
-        true_target = true_expr[test_idx].to(self.device)
-        imputed_target = imputed_expr[test_idx].to(self.device)
-        if log1p:
-            imputed_target = torch.log1p(imputed_target)
+        """Imputation quality on the test cells, reference semantics (scgnn2.py:73-121): the prediction is optionally log1p-ed,
+        entries under ``mask`` are overwritten with the truth (so they do not count), then RMSE over all test entries or
+        PCC / MRE over the held-out (``~mask``) entries.  The default ``metric="MSE"`` is rejected like in the reference."""
+        supported = ("RMSE", "PCC", "MRE")
+        if metric not in supported:
+            raise ValueError(f"scoring metric must be one of {set(supported)!r}")
+        rows = torch.arange(len(true_expr)) if test_idx is None else torch.as_tensor(np.asarray(test_idx))
+        truth = torch.as_tensor(true_expr)[rows].to(self.device)
+        pred = torch.as_tensor(imputed_expr)[rows].to(self.device)
+        pred = torch.log1p(pred) if log1p else pred.clone()
+        held_out = None
         if mask is not None:
-            imputed_target[mask[test_idx]] = true_target[mask[test_idx]].to(imputed_target.dtype)
+            seen = torch.as_tensor(np.asarray(mask))[rows].to(self.device)
+            pred = torch.where(seen, truth.to(pred.dtype), pred)
+            held_out = ~seen
         if metric == "RMSE":
-            return np.sqrt(torch.nn.functional.mse_loss(true_target, imputed_target).item())
-        elif metric == "PCC":
-            return np.corrcoef(true_target.cpu()[~mask[test_idx]], imputed_target.cpu()[~mask[test_idx]])[0, 1]
-        elif metric == "MRE":
-            actual = true_target.cpu()[~mask[test_idx]]
-            predicted = imputed_target.cpu()[~mask[test_idx]]
-            abs_error = torch.abs(predicted - actual)
-            abs_actual = torch.abs(actual)
-            abs_actual[abs_actual < 1e-10] = 1e-10
-            return torch.mean(abs_error / abs_actual).item()
+            return float(torch.sqrt(torch.mean((truth - pred)**2)).item())
+        if held_out is None:
+            raise ValueError(f"metric {metric!r} is evaluated on the masked-out entries and needs `mask`")
+        t, p = truth[held_out].double(), pred[held_out].double()
+        if metric == "PCC":
+            tc, pc = t - t.mean(), p - p.mean()
+            return float((tc @ pc / torch.sqrt((tc @ tc) * (pc @ pc))).item())
+        return float(torch.mean(torch.abs(p - t) / torch.abs(t).clamp(min=1e-10)).item())      # MRE

@@ -170,9 +170,45 @@ class CSR:
         return self._t
 
 
+_X16 = {torch.bfloat16: ("b2_spmm_csr_bf16", 0), torch.float16: ("b2_spmm_csr_f16", 1)}
+
+
+def to_x16(X: torch.Tensor, dtype=torch.bfloat16, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 → bf16 / fp16 copy of a row-major matrix (operand of the 16-bit aggregate)."""
+    _chk(X, torch.float32, "X", 2)
+    if dtype not in _X16:
+        raise B2Error(f"to_x16: dtype must be torch.bfloat16 or torch.float16, got {dtype}")
+    if out is None:
+        out = torch.empty(X.shape, dtype=dtype, device=X.device)
+    _chk(out, dtype, "out", 2)
+    check(lib().b2_convert_f32_to_x16(_p(X), _rowmajor(X, "X"), _p(out), _rowmajor(out, "out"), X.shape[0], X.shape[1], _X16[dtype][1],
+                                      _stream()), "b2_convert_f32_to_x16")
+    return out
+
+
 def spmm(A: CSR, X: torch.Tensor, reduce: str = "sum", act: Optional[str] = None,
-         out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """``Y = act(A @ X)`` (reduce='sum') or row-mean (reduce='mean')."""
+         out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, out16: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``Y = act(A @ X)`` (reduce='sum') or row-mean (reduce='mean').  A bf16 / fp16 ``X`` selects the 16-bit-operand kernel
+    (fp32 accumulation, fp32 ``out``; ``out16`` additionally receives the result in the operand's type)."""
+    if isinstance(X, torch.Tensor) and X.dtype in _X16:
+        fn, _ = _X16[X.dtype]
+        _chk(X, X.dtype, "X", 2)
+        n_rows, n_cols = A.shape
+        if X.shape[0] != n_cols:
+            raise B2Error(f"spmm: A is {A.shape} but X has {X.shape[0]} rows")
+        F = X.shape[1]
+        if out is None and out16 is None:
+            out = torch.empty((n_rows, F), dtype=torch.float32, device=X.device)
+        if out is not None:
+            _chk(out, torch.float32, "out", 2)
+        if out16 is not None:
+            _chk(out16, X.dtype, "out16", 2)
+        colidx_ptr = _p(A.colidx) if A.nnz else _p(A.rowptr)
+        check(getattr(lib(), fn)(_p(A.rowptr), colidx_ptr, _p(A.vals) if A.nnz else None, _p(X), _rowmajor(X, "X"),
+                                 _p(out), _rowmajor(out, "out") if out is not None else 0,
+                                 _p(out16), _rowmajor(out16, "out16") if out16 is not None else 0,
+                                 n_rows, n_cols, F, {"sum": 0, "mean": 1}[reduce], ACT[act], _p(bias), _stream()), fn)
+        return out if out is not None else out16
     _chk(X, torch.float32, "X", 2)
     ldx = _rowmajor(X, "X")
     n_rows, n_cols = A.shape
@@ -801,3 +837,87 @@ def adj_reparam_bwd(dz, mu, log_std, eps, coef_kl: float):
     check(lib().b2_adj_reparam_bwd_f32(_p(dz), _p(mu), _p(log_std), _p(eps), mu.numel(), coef_kl, _p(dmu), _p(dls), _stream()),
           "b2_adj_reparam_bwd_f32")
     return dmu, dls
+
+
+# ----------------------------------------------------------------------------- scGNN EM-iteration stages (csrc/em.cu)
+def kmeans(X: torch.Tensor, centers: torch.Tensor, max_iter: int = 300, tol: float = 1e-4):
+    """Lloyd iterations of ``sklearn.cluster.KMeans(init=centers, n_init=1)`` on the device (scgnn2.py:186).
+
+    ``centers`` [k, d] is updated in place.  Stops when no label changes or when ‖ΔC‖² ≤ tol·mean(var(X, axis=0)) (sklearn's
+    rule), then runs a final assignment so that labels are consistent with the returned centres.
+    Returns (labels int32 [n], inertia float, n_iter)."""
+    _chk(X, torch.float32, "X", 2)
+    _chk(centers, torch.float32, "centers", 2)
+    n, d = X.shape
+    k = centers.shape[0]
+    if centers.shape[1] != d or not centers.is_contiguous():
+        raise B2Error("kmeans: centers must be a contiguous [k, d] tensor")
+    labels = torch.full((n, ), -1, dtype=torch.int32, device=X.device)
+    stats = torch.zeros(3, dtype=torch.float64, device=X.device)
+    nbytes = lib().b2_kmeans_workspace_bytes(k, d)
+    ws = _workspace(nbytes, X.device)
+    tol_abs = float(tol * X.var(dim=0, unbiased=False).mean().item())
+
+    def step(update):
+        check(lib().b2_kmeans_step_f32(_p(X), _rowmajor(X, "X"), n, d, _p(centers), k, _p(labels), int(update), _p(stats), _p(ws),
+                                       ws.numel(), _stream()), "b2_kmeans_step_f32")
+        return stats.tolist()
+
+    it = 0
+    for it in range(1, max_iter + 1):
+        inertia, shift2, changed = step(True)
+        if changed == 0 or shift2 <= tol_abs:
+            break
+    inertia, _, _ = step(False)
+    return labels, inertia, it
+
+
+def graph_regu_weights(A: CSR, labels: torch.Tensor) -> torch.Tensor:
+    """Per-cell column sums of the row-normalised adjacency restricted to the cell's own cluster (see b2_graph_regu_weights_f32)."""
+    _chk(labels, torch.int32, "labels", 1)
+    n = A.shape[0]
+    w = torch.empty(n, dtype=torch.float32, device=labels.device)
+    check(lib().b2_graph_regu_weights_f32(_p(A.rowptr), _p(A.colidx), _p(labels), n, _p(w), _stream()), "b2_graph_regu_weights_f32")
+    return w
+
+
+def celltype_loss_grad(recon, target, x_dropout, row_weight, relu_mask=True, grad=None, loss_out=None):
+    """loss_function_graph(regularizer_type="Celltype") (scgnn2.py:1316-1326): returns (loss_out[1] accumulated, d loss / d recon)."""
+    for t, nm in ((recon, "recon"), (target, "target"), (x_dropout, "x_dropout")):
+        _chk(t, torch.float32, nm, 2)
+        if not t.is_contiguous():
+            raise B2Error(f"celltype_loss_grad: {nm} must be contiguous")
+    _chk(row_weight, torch.float32, "row_weight", 1)
+    rows, cols = recon.shape
+    if target.shape != recon.shape or x_dropout.shape[0] != rows or row_weight.shape[0] != rows or x_dropout.shape[1] > cols:
+        raise B2Error("celltype_loss_grad: shape mismatch")
+    if grad is None:
+        grad = torch.empty_like(recon)
+    if loss_out is None:
+        loss_out = torch.zeros(1, dtype=torch.float32, device=recon.device)
+    scratch = torch.empty(2, dtype=torch.float64, device=recon.device)
+    check(lib().b2_celltype_loss_grad_f32(_p(recon), _p(target), _p(x_dropout), _p(row_weight), rows, cols, x_dropout.shape[1],
+                                          int(relu_mask), _p(grad), _p(loss_out), _p(scratch), _stream()), "b2_celltype_loss_grad_f32")
+    return loss_out, grad
+
+
+def l1_grad_add(param, grad, coef: float = 1.0, l1_out=None):
+    _chk(param, torch.float32, "param")
+    _chk(grad, torch.float32, "grad")
+    if not (param.is_contiguous() and grad.is_contiguous()) or param.numel() != grad.numel():
+        raise B2Error("l1_grad_add: param / grad must be contiguous and equally sized")
+    check(lib().b2_l1_grad_add_f32(_p(param), _p(grad), param.numel(), float(coef), _p(l1_out), _stream()), "b2_l1_grad_add_f32")
+
+
+def louvain_host(indptr, indices, weights=None, max_levels: int = 0, min_gain: float = 1e-7):
+    """Multilevel Louvain on a symmetric CSR in host memory (numpy arrays): returns (labels int32 [n], n_communities, modularity)."""
+    import numpy as np
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+    n = indptr.shape[0] - 1
+    labels = np.empty(n, dtype=np.int32)
+    nc, mod = C.c_int32(), C.c_double()
+    check(lib().b2_louvain_csr_host(indptr.ctypes.data, indices.ctypes.data, None if w is None else w.ctypes.data, n, labels.ctypes.data,
+                                    C.byref(nc), C.byref(mod), int(max_levels), float(min_gain)), "b2_louvain_csr_host")
+    return labels, nc.value, mod.value

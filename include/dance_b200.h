@@ -67,6 +67,21 @@ int b2_spmm_csr_f32(const int32_t* rowptr, const int32_t* colidx, const float* v
                     int32_t n_rows, int32_t n_cols, int32_t F,
                     int reduce, int act, const float* bias /* length F or NULL, added before act */, void* stream);
 
+/* The same aggregate with a 16-bit dense operand (bf16 / fp16 storage, fp32 accumulation) — the reduced-precision
+ * configurations (BASELINE config 3 "GraphSCI … bf16"; dglnn.GraphConv under autocast, graphsci.py:112-115) and the
+ * bandwidth-optimised form of torch.spmm(adj, support) scgnn2.py:500: every non-zero gathers F·2 instead of F·4 bytes.
+ *   X       : [n_cols, F] bf16 / fp16, leading dimension ldx (elements), rows 16-byte aligned, F % 8 == 0, F <= 256
+ *   Y       : fp32 output or NULL;  Y16 : output in the operand's 16-bit type or NULL (feeds the next layer's aggregate
+ *             without a conversion pass); at least one of the two. */
+int b2_spmm_csr_bf16(const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                     const void* X, int64_t ldx, float* Y, int64_t ldy, void* Y16, int64_t ldy16,
+                     int32_t n_rows, int32_t n_cols, int32_t F, int reduce, int act, const float* bias, void* stream);
+int b2_spmm_csr_f16(const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                    const void* X, int64_t ldx, float* Y, int64_t ldy, void* Y16, int64_t ldy16,
+                    int32_t n_rows, int32_t n_cols, int32_t F, int reduce, int act, const float* bias, void* stream);
+/* fp32 [rows, cols] -> bf16 (dtype 0) / fp16 (dtype 1), round-to-nearest-even; replaces tensor.to(torch.bfloat16). */
+int b2_convert_f32_to_x16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int32_t cols, int dtype, void* stream);
+
 /* CSR transpose (deterministic: entries of each output row ordered by source
  * row).  Used to obtain Aᵀ for the SpMM backward of non-symmetric graphs
  * (GAT edge lists, cell→gene / gene→cell halves of CellFeatureGraph).
@@ -434,6 +449,34 @@ int b2_adj_loss_grad_f32(const float* z, const float* mu, const float* log_std, 
                          const float* class_weight, int32_t g, float coef_ce, float* dz, double* acc2, void* stream);
 int b2_adj_reparam_bwd_f32(const float* dz, const float* mu, const float* log_std, const float* eps, int64_t n_elem,
                            float coef_kl, float* dmu, float* dlog_std, void* stream);
+
+/* ------------------------------------------------------------------------
+ * scGNN EM-iteration stages
+ *   b2_kmeans_step_f32        : one Lloyd iteration of sklearn.cluster.KMeans(...).fit_predict(embed), scgnn2.py:186 —
+ *       labels <- nearest centre (ties: lowest index); update != 0: centres <- cluster means (empty clusters keep theirs).
+ *       stats (device, 3 doubles) = {inertia w.r.t. the old centres, ||dC||^2, number of changed labels}.
+ *   b2_graph_regu_weights_f32 : graph_celltype_regu_handler + the `[clusterIndex][:, clusterIndex]` slicing of
+ *       cluster_AE_handler (scgnn2.py:716-730, 844-846) in sparse form: w_j = sum_{i in N(j), label_i = label_j} 1/deg_i =
+ *       column sums of the row-normalised adjacency restricted to j's cluster (pattern = A + I CSR, symmetric).
+ *   b2_celltype_loss_grad_f32 : loss_function_graph(regularizer_type="Celltype"), scgnn2.py:1316-1326, with the dense
+ *       `M @ mse` products folded into per-row weights: value = sum_j row_weight_j * sum_g (r-x)^2 + || (x_dropout - r)[x_dropout != 0] ||_2
+ *       (callers pass row_weight = 0.3 + 0.3*w_graph + 0.1*w_celltype); grad = d value / d recon masked by recon > 0.
+ *       scratch2: 2 device doubles.
+ *   b2_l1_grad_add_f32        : the `loss + 1*l1` term of train_handler (scgnn2.py:1268-1274): grad += coef*sign(p).
+ *   b2_louvain_csr_host       : generateLouvainCluster (scgnn2.py:193-215; networkx -> igraph.community_multilevel) as
+ *       multilevel modularity optimisation on a symmetric weighted CSR in HOST memory (both directions stored).
+ *       Deterministic (index order, ties keep the current community).
+ * ---------------------------------------------------------------------- */
+size_t b2_kmeans_workspace_bytes(int32_t k, int32_t d);
+int b2_kmeans_step_f32(const float* X, int64_t ldx, int32_t n, int32_t d, float* C, int32_t k, int32_t* labels, int update,
+                       double* stats, void* workspace, size_t workspace_bytes, void* stream);
+int b2_graph_regu_weights_f32(const int32_t* rowptr, const int32_t* colidx, const int32_t* labels, int32_t n, float* w, void* stream);
+int b2_celltype_loss_grad_f32(const float* recon, const float* target, const float* x_dropout, const float* row_weight,
+                              int64_t rows, int32_t cols, int32_t cols_orig, int relu_mask, float* grad, float* loss_out,
+                              double* scratch2, void* stream);
+int b2_l1_grad_add_f32(const float* param, float* grad, int64_t n, float coef, float* l1_out, void* stream);
+int b2_louvain_csr_host(const int64_t* rowptr, const int32_t* colidx, const double* weights, int32_t n, int32_t* labels_out,
+                        int32_t* n_comm_out, double* modularity_out, int max_levels, double min_gain);
 
 #ifdef __cplusplus
 }

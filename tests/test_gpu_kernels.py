@@ -67,6 +67,41 @@ def test_spmm_skewed_degrees(cuda):
     assert rel_err(Y, m.astype(np.float64) @ X.astype(np.float64)) < 1e-6
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("F", [8, 16, 32, 64, 104, 256])
+@pytest.mark.parametrize("reduce", ["sum", "mean"])
+def test_spmm_16bit_operand(cuda, dtype, F, reduce):
+    """bf16 / fp16 operand, fp32 accumulation: exact (to summation order) against the fp64 product with the ROUNDED operand, and
+    within the storage format's rounding of the fp32 aggregate; conversion kernel == torch's round-to-nearest-even cast."""
+    from dance_b200 import ops
+    m = _rand_csr(333, 301, 0.08, seed=F)
+    X = torch.from_numpy(np.random.default_rng(2).normal(size=(301, F)).astype(np.float32)).to(cuda)
+    X16 = ops.to_x16(X, dtype)
+    assert torch.equal(X16, X.to(dtype))
+    bias = torch.randn(F, device=cuda)
+    A = ops.CSR.from_scipy(m, cuda)
+    Y = ops.spmm(A, X16, reduce=reduce, act="relu", bias=bias)
+    ref = m.astype(np.float64) @ X16.double().cpu().numpy()
+    if reduce == "mean":
+        ref = ref / np.maximum(np.diff(m.indptr), 1)[:, None]
+    ref = np.maximum(ref + bias.double().cpu().numpy(), 0)
+    assert Y.dtype == torch.float32 and rel_err(Y, ref) < 1e-6
+    # 16-bit output copy (feeds the next layer) and agreement with the fp32-operand kernel at storage precision
+    out16 = torch.empty(333, F, dtype=dtype, device=cuda)
+    Y2 = ops.spmm(A, X16, reduce=reduce, act="relu", bias=bias, out=torch.empty_like(Y), out16=out16)
+    assert torch.equal(Y2, Y) and torch.equal(out16, Y.to(dtype))
+    Y32 = ops.spmm(A, X, reduce=reduce, act="relu", bias=bias)
+    assert rel_err(Y, Y32) < (4e-3 if dtype == torch.bfloat16 else 5e-4)
+    # padded leading dimension + unweighted graph
+    wide = torch.zeros(301, F + 24, dtype=dtype, device=cuda)
+    wide[:, :F] = X16
+    Au = ops.CSR.from_scipy(m, cuda, with_values=False)
+    ones = m.copy(); ones.data[:] = 1
+    Yu = ops.spmm(Au, wide[:, :F])
+    assert rel_err(Yu, ones.astype(np.float64) @ X16.double().cpu().numpy()) < 1e-6
+    assert np.all(Yu[1].cpu().numpy() == 0)   # empty row
+
+
 def test_spmm_empty_matrix(cuda):
     from dance_b200 import ops
     m = sp.csr_matrix((10, 10), dtype=np.float32)
