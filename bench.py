@@ -48,29 +48,20 @@ def load_peaks():
 
 
 # ------------------------------------------------------------------------------------ synthetic data
-def synth_expression_gpu(n, g, device, seed=0, density=0.10, chunk=65536):
-    """Device-side generator of the SURVEY §8d expression matrix (NB counts, 10 latent types,
-    ~10 % non-zeros, normalize_total(1e4)+log1p through the library's own kernel)."""
-    from dance_b200 import ops
-    gen = torch.Generator(device=device).manual_seed(seed)
-    mu_g = torch.exp(torch.randn(g, device=device, generator=gen))
-    shift = torch.ones(10, g, device=device)
-    for t in range(10):
-        idx = torch.randperm(g, device=device, generator=gen)[:max(1, g // 20)]
-        shift[t, idx] = 4.0
-    X = torch.empty(n, g, dtype=torch.float32, device=device)
-    for i0 in range(0, n, chunk):
-        i1 = min(n, i0 + chunk)
-        m = i1 - i0
-        s_c = torch.exp(0.5 * torch.randn(m, 1, device=device, generator=gen))
-        types = torch.randint(0, 10, (m, ), device=device, generator=gen)
-        mean = s_c * mu_g[None, :] * shift[types]
-        lam = torch._standard_gamma(torch.full_like(mean, 2.0)) * (mean / 2.0)   # NB = Poisson(Gamma), dispersion 0.5
-        cnt = torch.poisson(lam, generator=gen)
-        nz = (cnt > 0).float().mean().clamp_min(1e-6)
-        keep = torch.rand(cnt.shape, device=device, generator=gen) < (density / nz).clamp(max=1.0)
-        X[i0:i1] = cnt * keep
-    ops.normalize_total_log1p_(X, target_sum=1e4, max_fraction=1.0)
+DATA_SEED = 0
+
+
+def synth_expression(n, g, device, row_begin=0):
+    """Rows [row_begin, row_begin+n) of the SURVEY §8d expression matrix (dance_b200.synth: every value is a hash of
+    (seed, global cell index, gene), identical on every arm / device / sharding), log-normalised (normalize_total(1e4) + log1p)."""
+    from dance_b200 import synth
+    X = synth.expression_counts(n, g, seed=DATA_SEED, density=0.10, row_begin=row_begin, device=device)
+    if X.is_cuda:
+        from dance_b200 import ops
+        ops.normalize_total_log1p_(X, target_sum=1e4, max_fraction=1.0)
+    else:   # CPU arm: the reference formula (scanpy normalize_total + log1p), zero-count cells untouched
+        tot = X.sum(1, keepdim=True)
+        X = torch.log1p(torch.where(tot > 0, X * (1e4 / tot.clamp(min=1e-30)), X))
     return X
 
 
@@ -126,17 +117,51 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ CPU (reference) arm
-def cpu_reference_step_factory(n_cells, genes, seed=0):
-    """The reference's CPU arithmetic for one step on `n_cells` cells: oracle.port (torch-CPU
-    restatement, pinned against the reference's own code) — Feature_AE epoch + Graph_AE GCN epoch
-    with the dense N×N decoder/labels exactly like scgnn2.py:557,425,603-615."""
-    from oracle import port
+def cpu_reference_step_factory(n_cells, genes):
+    """One scGNN step on `n_cells` cells on the host cores: Feature_AE epoch + Graph_AE GCN epoch with the dense N×N
+    decoder / labels exactly like scgnn2.py:557,425,603-615.  When the reference tree is present (build container) the
+    reference's OWN classes run through oracle/ref_loader.py (kind "reference": Feature_AE, train_handler, Graph_AE,
+    gae_loss_function, preprocess_graph, feature2adj); on the GPU box (/root/reference absent) the pinned restatement
+    oracle/port.py runs the same arithmetic (kind "port")."""
+    from oracle import port, ref_loader
     torch.set_num_threads(os.cpu_count())
-    X = torch.from_numpy(port.synthetic_expression(n_cells, genes, seed=seed))
-    torch.manual_seed(seed)
+    X = synth_expression(n_cells, genes, "cpu")
+    torch.manual_seed(0)
+    if ref_loader.available():
+        ref = ref_loader.scgnn2()
+        cpu_reference_step_factory.kind = "reference"
+        fae = ref.Feature_AE(dim=genes)
+        opt = torch.optim.Adam(fae.parameters(), lr=1e-3)
+        with torch.no_grad():
+            z0, _ = fae(X)
+        _, adj, _ = ref.feature2adj(z0.numpy(), K_NN, False)      # (adj, adj_train, edgeList), scgnn2.py:650-672
+        adj_norm = ref.preprocess_graph(adj)                      # same sequence as graph_AE_handler, scgnn2.py:555-569
+        import scipy.sparse as sp
+        labels = torch.FloatTensor((adj + sp.eye(n_cells)).toarray())
+        pw = float(n_cells * n_cells - adj.sum()) / adj.sum()
+        norm = n_cells * n_cells / float((n_cells * n_cells - adj.sum()) * 2)
+        gae = ref.Graph_AE(128, EMB, 0, 2, 64)
+        gopt = torch.optim.Adam(gae.parameters(), lr=1e-2)
+        loader = torch.utils.data.DataLoader(ref.ExpressionDataset(X.numpy()), batch_size=BATCH)
+        trs = torch.zeros_like(X)
+        param = {"device": "cpu", "epoch_num": 0, "total_epoch": 0, "n_feature_orig": genes}
+
+        def step():
+            _, z_all, _ = ref.train_handler(model=fae, train_loader=loader, optimizer=opt, TRS=trs, total_epoch=1, impute_regu=None,
+                                            regu_type=["LTMG", "noregu"], regu_strength=0.9, masked_prob=0, param=param)
+            gae.train()
+            gopt.zero_grad()
+            embed, gae_info, recon = gae(z_all.detach(), adj_norm, use_GAT=False)
+            loss = ref.gae_loss_function(preds=recon, labels=labels, mu=gae_info[0], logvar=gae_info[1], n_nodes=n_cells, norm=norm,
+                                         pos_weight=pw)
+            loss.backward()
+            gopt.step()
+            return float(loss.item())
+
+        return step
+    cpu_reference_step_factory.kind = "port"
     fae = port.FeatureAE(genes)
     opt = torch.optim.Adam(fae.parameters(), lr=1e-3)
-    # graph on the initial embedding (outside the timed step, like the GPU arm)
     with torch.no_grad():
         z0, _ = fae(X)
     adj, _ = port.feature2adj(z0.numpy(), K_NN)
@@ -179,6 +204,7 @@ def time_cpu(n_cells, genes, steps, warmup):
             best_t, best_th = dt, th
     torch.set_num_threads(best_th)
     time_cpu.threads = best_th
+    time_cpu.kind = cpu_reference_step_factory.kind
     ts = []
     for _ in range(steps):
         t0 = time.perf_counter()
@@ -187,31 +213,39 @@ def time_cpu(n_cells, genes, steps, warmup):
     return float(np.median(ts)), ts
 
 
+def cpu_sample_text(n_cpu, args):
+    return (f"{n_cpu} of {args.cells} cells × {args.genes} genes (same generator, rows 0..{n_cpu - 1}); 1 step = Feature_AE epoch + Graph_AE GCN "
+            f"epoch with the reference's dense {n_cpu}×{n_cpu} decoder (scgnn2.py:425,557) on torch-CPU, best of 16/32/64/all intra-op "
+            f"threads; the O(N²) decoder makes the per-cell CPU cost at the full {args.cells} cells ≈{max(1, args.cells // n_cpu)}× higher than in this sample")
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_cpu = args.cpu_cells
+    n_cpu = min(args.cpu_cells, args.cells)
     med, ts = time_cpu(n_cpu, args.genes, args.steps, max(1, min(args.warmup, 1)))
     val = n_cpu / med
     line = {
         "impl": "reference", "metric": "cells/sec fwd+bwd scGNN", "value": val, "unit": "cells/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, loss_mode="exact-dense"),
-        "cpu_baseline": {"value": val, "unit": "cells/s", "cores": time_cpu.threads, "host_cores": os.cpu_count(), "kind": "port",
-                         "sample": f"{n_cpu} of {args.cells} cells × {args.genes} genes, 1 step = Feature_AE epoch + Graph_AE GCN epoch "
-                                   f"with the reference's dense {n_cpu}×{n_cpu} decoder (scgnn2.py:425,557); oracle/port.py on torch-CPU"},
+        "config": workload_config(args),
+        "cpu_baseline": {"value": val, "unit": "cells/s", "cores": time_cpu.threads, "host_cores": os.cpu_count(), "kind": time_cpu.kind,
+                         "sample": cpu_sample_text(n_cpu, args)},
         "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, loss_mode):
-    return {"workload": f"scGNN {args.cells} cells × {args.genes} genes: Feature_AE epoch (batch {BATCH}) + Graph_AE GCN epoch, k={K_NN} kNN graph",
+def workload_config(args):
+    """Identical for both arms (the driver compares it): what one step computes; HOW each arm evaluates the decoder (dense N×N on the
+    CPU sample, matrix-free blockwise on the GPU) is an implementation property reported outside `config`."""
+    return {"workload": f"scGNN {args.cells} cells × {args.genes} genes: Feature_AE epoch (batch {BATCH}) + Graph_AE GCN epoch with the exact "
+                        f"all-pairs inner-product decoder loss, k={K_NN} kNN graph",
             "cells": args.cells, "genes": args.genes, "feature_ae_batch": BATCH, "knn_k": K_NN, "graph_ae_embedding": EMB,
-            "decoder_loss": loss_mode, "gemm_precision": args.precision,
-            "l2_policy": "inputs larger than L2 (X is %.1f GB per rank-shard; every step streams it)" % (args.cells * args.genes * 4 / 1e9)}
+            "data_seed": DATA_SEED, "density": 0.10,
+            "l2_policy": "inputs larger than L2 (X is %.1f GB; every step streams it)" % (args.cells * args.genes * 4 / 1e9)}
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -227,6 +261,7 @@ def main():
     ap.add_argument("--cpu-cells", type=int, default=16384, help="bounded CPU sample (cells) for cpu_baseline / --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-checks", action="store_true", help="skip the fp64 spot checks and the 16-bit aggregate side measurement")
     ap.add_argument("--cuda-profiler", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
@@ -256,14 +291,19 @@ def main():
     n_loc = r1 - r0
 
     # ---- setup (outside the timed region) ------------------------------------------------
-    X = synth_expression_gpu(n_loc, G, dev, seed=1234 + rank)
+    from dance_b200 import hostio, synth
+    from dance_b200.parallel import epoch_steps
+    X = synth_expression(n_loc, G, dev, row_begin=r0)
+    fp = synth.fingerprint(X)
     fae = FeatureAEEngine(G, device=dev, lr=1e-3, precision=args.precision, seed=0)
     gae = GraphAEEngine(128, EMB, device=dev, lr=1e-2, precision=args.precision, seed=1)
+    n_steps = None
     if comm.enabled:
         fae.grad_hook = comm.allreduce_sum_
         gae.set_sharding(comm, bounds)
+        n_steps = epoch_steps(bounds, BATCH)       # every rank issues the same number of gradient all-reduces per epoch
     z_all = torch.empty(n_loc, 128, dtype=torch.float32, device=dev)
-    fae.train_epoch(X, BATCH, "LTMG", 0.9, None, z_all, None)   # also serves as the first warm-up epoch
+    fae.train_epoch(X, BATCH, "LTMG", 0.9, None, z_all, None, n_steps=n_steps)   # also serves as the first warm-up epoch
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     z_full = comm.all_gather_rows(z_all, bounds) if comm.enabled else z_all
@@ -290,7 +330,7 @@ def main():
     ops.reset_counters()
 
     def step(x_src):
-        fae.train_epoch(x_src, BATCH, "LTMG", 0.9, None, z_all, None)
+        fae.train_epoch(x_src, BATCH, "LTMG", 0.9, None, z_all, None, n_steps=n_steps)
         eps.normal_(generator=gen)
         gae.train_step(z_all, A, labels, norm, pos_weight, eps)
 
@@ -311,6 +351,9 @@ def main():
     for _ in range(args.warmup):
         step(X)
     torch.cuda.synchronize()
+
+    # ---- parity spot checks on the exact code paths the timed region runs (fp64 closed forms on sampled rows) ----------------
+    checks = parity_checks(ops, gae, A, labels, norm, pos_weight, N, r0, n_loc, comm, dev) if not args.no_checks else None
 
     # ---- timed region: device-resident inputs -----------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -334,56 +377,118 @@ def main():
     ktimes = ops.kernel_times()
     ops.enable_kernel_timing(False)
 
-    # ---- e2e: host-resident X, pinned, H2D per batch inside the timed region --------------------
+    # ---- 16-bit-operand aggregate on the same graph (the bf16 configuration's SpMM; not part of the fp32-grade step) ----------
+    spmm16 = None
+    if world == 1 and not args.no_checks:
+        S = gae._buffers(n_loc)["s1"]
+        S16 = ops.to_x16(S, torch.bfloat16)
+        out = torch.empty_like(S)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        ts = []
+        for it in range(6):
+            flush.zero_()                                   # evict L2 between timed launches
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record()
+            ops.spmm(A, S16, out=out)
+            e_.record()
+            torch.cuda.synchronize()
+            if it:
+                ts.append(s_.elapsed_time(e_))
+        ms16 = float(np.median(ts))
+        b16 = A.nnz * 8 + (n_loc + 1) * 4 + N * 32 * 2 + n_loc * 32 * 4
+        spmm16 = {"kernel": "spmm_csr_x16_kernel (Â·support, F=32, bf16 operand, fp32 accumulate/output)", "bound": "hbm",
+                  "achieved": b16 / (ms16 * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                  "frac": b16 / (ms16 * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": traffic_from_profiles("spmm_csr_x16_kernel"),
+                  "ms_per_launch": ms16, "algorithmic_bytes": b16, "l2_policy": "256 MB flush between launches", "peak_source": peaks["source"]}
+        del flush, S16, out
+
+    # ---- e2e: the public handlers (numpy in / numpy out), host-resident pinned X, copies inside the timed region ---------------
     e2e = None
     if not args.no_e2e:
+        from types import SimpleNamespace
+        from dance_b200.modules import scgnn2 as mod
         Xh = torch.empty((n_loc, G), dtype=torch.float32, pin_memory=True)
         Xh.copy_(X)
-        stage = [torch.empty((BATCH, G), dtype=torch.float32, device=dev) for _ in range(2)]
-        copy_stream = torch.cuda.Stream(device=dev)
-        main_stream = torch.cuda.current_stream()
-        loss_host = torch.empty(2, dtype=torch.float32, pin_memory=True)
-        nb = (n_loc + BATCH - 1) // BATCH
+        Xnp = Xh.numpy()
+        del X
+        torch.cuda.empty_cache()
+        hargs = SimpleNamespace(feature_AE_batch_size=BATCH, feature_AE_epoch=[1, 1], feature_AE_learning_rate=1e-3,
+                                feature_AE_regu_strength=0.9, feature_AE_dropout_prob=0, feature_AE_concat_prev_embed=None,
+                                graph_AE_epoch=1, graph_AE_use_GAT=False, graph_AE_GAT_dropout=0, graph_AE_learning_rate=1e-2,
+                                graph_AE_embedding_size=EMB, graph_AE_concat_prev_embed=None, graph_AE_normalize_embed=None,
+                                graph_AE_neighborhood_factor=K_NN, graph_AE_retain_weights=False, gat_multi_heads=2, gat_hid_embed=64)
+        param = {"device": dev, "epoch_num": 0, "total_epoch": 0, "n_feature_orig": G, "precision": args.precision, "seed": 0,
+                 "io_pool": hostio.IOPool(), "graph_cache": {}}
+        out_bytes = {}
 
         def e2e_step():
-            # double-buffered: batch b+1 is copied on the side stream while batch b trains
-            evs = [None, None]
-            free = [None, None]
-            fae.loss_acc.zero_()
+            x_embed, x_recon, _ = mod.feature_AE_handler(Xnp, None, hargs, param)
+            g_embed, _, edge_list, adj = mod.graph_AE_handler(x_embed, None, hargs, param)
+            out_bytes["d2h"] = x_embed.nbytes + x_recon.nbytes + g_embed.nbytes
+            out_bytes["h2d"] = Xnp.nbytes + x_embed.nbytes
 
-            def issue(b):
-                buf = b & 1
-                b0, b1 = b * BATCH, min(n_loc, (b + 1) * BATCH)
-                with torch.cuda.stream(copy_stream):
-                    if free[buf] is not None:
-                        copy_stream.wait_event(free[buf])
-                    stage[buf][:b1 - b0].copy_(Xh[b0:b1], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(copy_stream)
-                    evs[buf] = ev
-            issue(0)
-            for b in range(nb):
-                buf = b & 1
-                if b + 1 < nb:
-                    issue(b + 1)
-                b0, b1 = b * BATCH, min(n_loc, (b + 1) * BATCH)
-                main_stream.wait_event(evs[buf])
-                z, _ = fae.train_step(stage[buf][:b1 - b0], None, 0.9, "LTMG")
-                z_all[b0:b1].copy_(z)
-                fr = torch.cuda.Event()
-                fr.record(main_stream)
-                free[buf] = fr
-            eps.normal_(generator=gen)
-            gae.train_step(z_all, A, labels, norm, pos_weight, eps)
-            loss_host[0:1].copy_(fae.loss_acc, non_blocking=True)
-            loss_host[1:2].copy_(gae.loss, non_blocking=True)
+        if world == 1:
+            e2e_step()      # first call: allocates the pinned output buffers and builds + caches the kNN graph (not part of a step)
+            e2e_step()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                e2e_step()
+            torch.cuda.synchronize()
+            e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+            e2e = {"value": N / (e2e_ms / 1e3), "unit": "cells/s", "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": int(out_bytes["h2d"]), "d2h_bytes_per_step": int(out_bytes["d2h"]),
+                   "api": "dance_b200.modules.scgnn2.feature_AE_handler + graph_AE_handler (numpy in / numpy out), feature_AE_epoch=1, graph_AE_epoch=1",
+                   "note": "host wall clock around the two public handler calls. X is a pinned numpy array; the handler streams it in batch by "
+                           "batch on a side stream while earlier batches train and streams the N×G reconstruction back to pinned host memory "
+                           "the same way; returns X_embed, X_recon, graph_embed, edgeList, adj as host arrays. The kNN graph of the step's "
+                           "embedding is taken from param['graph_cache'] (built in the untimed first call), like the reference arm which "
+                           "builds its graph outside the timed step; graph_build_s reports that cost."}
+        else:
+            # multi-GPU: the handlers are single-device; the sharded engines are driven with per-batch pinned uploads instead
+            stage = [torch.empty((BATCH, G), dtype=torch.float32, device=dev) for _ in range(2)]
+            up = hostio.Uploader(Xh, dev)
+            main_stream = torch.cuda.current_stream()
+            loss_host = torch.empty(2, dtype=torch.float32, pin_memory=True)
+            from dance_b200.parallel import batch_schedule
+            sched = batch_schedule(n_loc, BATCH, n_steps)
 
-        e2e_step()
-        e2e_ms = timed(e2e_step, args.steps) / args.steps
-        e2e = {"value": N / (e2e_ms / 1e3), "unit": "cells/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": int(n_loc * G * 4) * world, "d2h_bytes_per_step": 8 * world,
-               "note": "X pinned on the host, copied batch-by-batch on a side stream (double-buffered) inside the timed region; "
-                       "per-step D2H = the two loss scalars"}
+            def e2e_step_mg():
+                fae.loss_acc.zero_()
+                free = [None, None]
+                evs = {}
+                def issue(b):
+                    if sched[b] is None:
+                        return
+                    if free[b & 1] is not None:
+                        up.stream.wait_event(free[b & 1])
+                    b0, b1 = sched[b]
+                    evs[b] = up.copy_rows(b0, b1, stage[b & 1][:b1 - b0])
+                issue(0)
+                for b, rng in enumerate(sched):
+                    if b + 1 < len(sched):
+                        issue(b + 1)
+                    if rng is None:
+                        fae.idle_step()
+                        continue
+                    b0, b1 = rng
+                    main_stream.wait_event(evs.pop(b))
+                    z, _ = fae.train_step(stage[b & 1][:b1 - b0], None, 0.9, "LTMG")
+                    z_all[b0:b1].copy_(z)
+                    fr = torch.cuda.Event()
+                    fr.record(main_stream)
+                    free[b & 1] = fr
+                eps.normal_(generator=gen)
+                gae.train_step(z_all, A, labels, norm, pos_weight, eps)
+                loss_host[0:1].copy_(fae.loss_acc, non_blocking=True)
+                loss_host[1:2].copy_(gae.loss, non_blocking=True)
+
+            e2e_step_mg()
+            e2e_ms = timed(e2e_step_mg, args.steps) / args.steps
+            e2e = {"value": N / (e2e_ms / 1e3), "unit": "cells/s", "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": int(N * G * 4), "d2h_bytes_per_step": 8 * world,
+                   "api": "sharded engines (FeatureAEEngine.train_step / GraphAEEngine.train_step) under torch.distributed",
+                   "note": "X pinned on each rank's host, copied batch-by-batch on a side stream (double-buffered) inside the timed region; "
+                           "per-step D2H = the two loss scalars per rank (the numpy-returning handlers are single-device)"}
         del Xh
 
     if rank != 0:
@@ -401,11 +506,10 @@ def main():
     roof_spmm = None
     if spmm_ms:
         ach = spmm_bytes / (spmm_ms * 1e-3) / 1e9
-        roof_spmm = {"kernel": "spmm_csr_kernel (Â·support, F=32)", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": ach / peaks["hbm_gbs"], "traffic": None, "launches": spmm_n, "ms_per_launch": spmm_ms,
-                     "algorithmic_bytes": spmm_bytes, "peak_source": peaks["source"]}
+        roof_spmm = {"kernel": "spmm_csr_kernel (Â·support, F=32, fp32 operand)", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": ach / peaks["hbm_gbs"], "traffic": traffic_from_profiles("spmm_csr_kernel"), "launches": spmm_n, "ms_per_launch": spmm_ms,
+                     "algorithmic_bytes": spmm_bytes, "gather_bytes_through_l2": nnz_loc * F * 4, "peak_source": peaks["source"]}
     gemm_ms, gemm_n, gemm_total = kt("gemm_f32")
-    nb_loc = (n_loc + BATCH - 1) // BATCH
     fae_flops = 6.0 * n_loc * (G * 512 + 512 * 128 + 128 * 512 + 512 * G)       # fwd + dX + dW, 2 flops per MAC
     gcn_flops = 6.0 * n_loc * (128 * 32 + 32 * 2 * EMB)
     roof_gemm = None
@@ -413,7 +517,7 @@ def main():
         ach = (fae_flops + gcn_flops) / (gemm_total * 1e-3) / 1e12
         roof_gemm = {"kernel": "gemm_tc_kernel (tcgen05 kind::tf32, %s)" % args.precision, "bound": "tensor", "achieved": ach,
                      "peak": peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"], "unit": "TFLOP/s",
-                     "frac": ach / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]), "traffic": None, "launches": gemm_n,
+                     "frac": ach / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]), "traffic": traffic_from_profiles("gemm_tc_kernel"), "launches": gemm_n,
                      "ms_total": gemm_total, "algorithmic_flops": fae_flops + gcn_flops, "peak_source": peaks["source"],
                      "note": "achieved = fp32-equivalent algorithmic FLOPs; tf32x3 issues 3 tensor-core products per algorithmic product "
                              "and kind::tf32 runs at half the bf16 rate, so the ceiling of this mode is peak/6"}
@@ -422,40 +526,168 @@ def main():
     dominant = max(ktimes.items(), key=lambda kv: kv[1]["ms"])[0] if ktimes else None
     roofline = roof_gemm if dominant == "gemm_f32" else (roof_spmm if dominant == "spmm_csr_f32" else None)
     if roofline is None:
-        # the exact N×N decoder is SFU/FMA-bound; report it on the tensor roofline with its matmul flops (2·d per logit, S and G·Z)
+        # the exact N×N decoder is SFU/issue-bound; report it on the tensor roofline with its matmul flops (2·d per logit, S and G·Z)
         dec_flops = 2.0 * 2 * EMB * float(n_loc) * N
         ach = dec_flops / (dec_total * 1e-3) / 1e12 if dec_total else 0.0
-        roofline = {"kernel": "gae_allpairs_tch_kernel (matrix-free z·zᵀ BCE decoder: tcgen05 kind::f16 hi/lo split, S and G in TMEM)",
+        roofline = {"kernel": "gae decoder (matrix-free z·zᵀ BCE: tcgen05 kind::f16 hi/lo split, S in TMEM)",
                     "bound": "tensor", "achieved": ach,
                     "peak": peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"], "unit": "TFLOP/s",
-                    "frac": ach / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]), "traffic": None,
+                    "frac": ach / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]), "traffic": traffic_from_profiles("gae_allpairs"),
                     "launches": dec_n, "ms_total": dec_total, "peak_source": peaks["source"],
-                    "note": "dominant kernel of the step; algorithmic flops = the two K=16 products per logit (S and G·Z). Its real ceiling is "
-                            "the per-logit elementwise work (2 MUFU + 9 ALU instructions on 16 warps, ncu: issue 58 %, XU 58 %), not the tensor "
-                            "pipe (10 % active) or HBM — see DESIGN.md §decoder and profiles/; roofline_spmm / roofline_gemm are the HBM- and "
-                            "tensor-bound kernels"}
+                    "logits_per_s": float(n_loc) * N / (dec_total * 1e-3) if dec_total else None,
+                    "note": "dominant kernel of the step; algorithmic flops = the two K=16 products per logit (S and G·Z) over ALL N² ordered "
+                            "pairs. Its real ceiling is the per-logit elementwise work (2 MUFU + ~9 ALU instructions), not the tensor pipe or "
+                            "HBM — see DESIGN.md §decoder and profiles/; roofline_spmm / roofline_gemm are the HBM- and tensor-bound kernels"}
 
-    cpu_baseline = None
+    cpu_baseline, matched = None, None
     if not args.no_cpu_baseline and world == 1:
-        med, ts = time_cpu(args.cpu_cells, G, steps=2, warmup=1)
-        cpu_baseline = {"value": args.cpu_cells / med, "unit": "cells/s", "cores": time_cpu.threads, "host_cores": os.cpu_count(), "kind": "port",
-                        "sample": f"{args.cpu_cells} of {N} cells × {G} genes; same step (Feature_AE epoch + Graph_AE GCN epoch) with the "
-                                  f"reference's dense {args.cpu_cells}² decoder; oracle/port.py on torch-CPU, best of 16/32/64/all intra-op threads = {time_cpu.threads}; "
-                                  f"the O(N²) decoder makes per-cell CPU cost at the full {N} cells ≈{N // args.cpu_cells}× higher than in this sample",
-                        "s_per_step": med}
+        n_cpu = min(args.cpu_cells, N)
+        med, ts = time_cpu(n_cpu, G, steps=2, warmup=1)
+        cpu_baseline = {"value": n_cpu / med, "unit": "cells/s", "cores": time_cpu.threads, "host_cores": os.cpu_count(), "kind": time_cpu.kind,
+                        "sample": cpu_sample_text(n_cpu, args), "s_per_step": med}
+        # like-for-like line: the GPU arm on exactly the CPU arm's sample (same rows of the same matrix, same step)
+        gm = gpu_step_ms(n_cpu, G, dev, args.precision)
+        matched = {"cells": n_cpu, "gpu_cells_per_s": n_cpu / (gm / 1e3), "gpu_ms_per_step": gm, "cpu_cells_per_s": n_cpu / med,
+                   "ratio": (n_cpu / (gm / 1e3)) / (n_cpu / med),
+                   "note": "same-N comparison; the headline value / reference ratio is cross-N (GPU at the full size, CPU on this sample)"}
 
     line = {
         "metric": "cells/sec fwd+bwd scGNN", "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32 (tcgen05 3xTF32 split GEMMs, fp32 everything else)" if args.precision == "tf32x3" else args.precision,
         "data": "synthetic",
-        "config": dict(workload_config(args, "exact-fused-blockwise (matrix-free, no N×N tensors)"), parallelism=f"cells sharded ×{world}",
-                       nnz=nnz_total),
-        "clocks": clocks, "e2e": e2e, "gpu_launches": launches // args.steps,
-        "roofline": roofline, "roofline_spmm": roof_spmm, "roofline_gemm": roof_gemm, "cpu_baseline": cpu_baseline,
+        "config": workload_config(args),
+        "implementation": {"decoder_loss": "exact-fused-blockwise (matrix-free, no N×N tensors)", "gemm_precision": args.precision,
+                           "parallelism": f"cells sharded ×{world}", "nnz": nnz_total, "data_fingerprint_rank0": fp},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches // args.steps, "checks": checks,
+        "roofline": roofline, "roofline_spmm": roof_spmm, "roofline_spmm_bf16": spmm16, "roofline_gemm": roof_gemm,
+        "cpu_baseline": cpu_baseline, "matched_n": matched,
         "kernel_ms_per_step": phases, "graph_build_s": graph_build_s,
     }
     print(json.dumps(line), flush=True)
+
+
+def traffic_from_profiles(kernel_prefix):
+    """DRAM bytes per launch of a kernel from the committed `ncu --set full` capture summary (profiles/r02_traffic.json:
+    {kernel name prefix: dram__bytes_read.sum + dram__bytes_write.sum}); None when no capture has been committed for it."""
+    p = ROOT / "profiles" / "r02_traffic.json"
+    if not p.exists():
+        return None
+    try:
+        d = json.load(open(p))
+    except Exception:
+        return None
+    for k, v in d.items():
+        if k.startswith(kernel_prefix) or kernel_prefix.startswith(k):
+            return v
+    return None
+
+
+def gae_reference_rows(z, rowptr, colidx, norm, pw, rows, chunk=256):
+    """fp64 closed form of gae_loss_function (scgnn2.py:603-612) for `rows` × all columns on the device (checker, plain torch):
+    returns (Σ cost over those rows · norm / n², gradient rows).  cost = y·pw·softplus(−x) + (1−y)·softplus(x); labels symmetric ⇒
+    ∂/∂z_i = 2·Σ_j c_ij z_j with c = σ(x) off the pattern and −pw·σ(−x) on it."""
+    import torch.nn.functional as F
+    zd = z.double()
+    n = zd.shape[0]
+    rp = rowptr.long()
+    loss = 0.0
+    out = torch.empty(len(rows), zd.shape[1], dtype=torch.float64, device=z.device)
+    for a in range(0, len(rows), chunk):
+        r = rows[a:a + chunk]
+        x = zd[r] @ zd.t()
+        c = torch.sigmoid(x)
+        cost = F.softplus(x)
+        cnt = rp[r + 1] - rp[r]
+        loc = torch.repeat_interleave(torch.arange(len(r), device=z.device), cnt)
+        start = torch.repeat_interleave(rp[r], cnt)
+        within = torch.arange(int(cnt.sum()), device=z.device) - torch.repeat_interleave(torch.cumsum(cnt, 0) - cnt, cnt)
+        cols = colidx.long()[start + within]
+        xe = x[loc, cols]
+        cost[loc, cols] = pw * F.softplus(-xe)
+        c[loc, cols] = -pw * torch.sigmoid(-xe)
+        loss += float(cost.sum())
+        out[a:a + chunk] = 2.0 * (c @ zd)
+    return norm * loss / (float(n) * n), out * (norm / (float(n) * n))
+
+
+def parity_checks(ops, gae, A, labels, norm, pos_weight, N, r0, n_loc, comm, dev):
+    """Spot checks of the code paths the timed region runs, at the benchmark's own size: (1) decoder gradient rows of the full-size
+    call (the j_splits == 1 / non-atomic epilogue branch at 1 GPU) and the loss of a row block against the fp64 closed form;
+    (2) aggregate rows against an fp64 gather-sum.  Raises on a mismatch."""
+    b = gae._buffers(n_loc)
+    z_loc = b["z"]
+    z_all = gae._gather(z_loc, "z")
+    out = {}
+    g = torch.Generator(device=dev).manual_seed(7)
+    rows_loc = torch.randint(0, n_loc, (96, ), device=dev, generator=g)
+    dz = torch.empty(n_loc, z_loc.shape[1], dtype=torch.float32, device=dev)
+    loss = torch.zeros(1, dtype=torch.float32, device=dev)
+    ops.gae_loss_grad(z_all, labels, norm, pos_weight, dz=dz, loss=loss, row_begin=r0, n_rows=n_loc)
+    # reference rows need the label pattern of the sampled rows in GLOBAL numbering: shift the local CSR rows
+    class _Shift:   # minimal view: rowptr indexable by global row id
+        pass
+    rp_full = torch.zeros(N + 1, dtype=A.rowptr.dtype, device=dev)
+    rp_full[r0:r0 + n_loc + 1] = A.rowptr
+    if r0 + n_loc < N:
+        rp_full[r0 + n_loc + 1:] = A.rowptr[-1]
+    _, ref_rows = gae_reference_rows(z_all, rp_full, A.colidx, norm, pos_weight, rows_loc + r0)
+    err = float((dz[rows_loc].double() - ref_rows).norm() / ref_rows.norm())
+    out["decoder_grad_rel_err_96_rows"] = err
+    assert err < 2e-5, f"decoder gradient mismatch at full size: rel err {err}"
+    # loss of a 512-row block through the same entry point (row-sharded form) against fp64
+    blk = torch.arange(0, min(512, n_loc), device=dev)
+    sub = ops.CSR(A.rowptr[:len(blk) + 1].contiguous(), A.colidx[:int(A.rowptr[len(blk)].item())].contiguous(), None, (len(blk), N))
+    lb, _, _, _ = ops.gae_loss_grad(z_all, sub, norm, pos_weight, row_begin=r0, n_rows=len(blk))
+    ref_l, _ = gae_reference_rows(z_all, rp_full, A.colidx, norm, pos_weight, blk + r0)
+    out["decoder_loss_rel_err_512_rows"] = abs(lb.item() - ref_l) / abs(ref_l)
+    assert out["decoder_loss_rel_err_512_rows"] < 1e-5, f"decoder loss mismatch: {lb.item()} vs {ref_l}"
+    # aggregate rows
+    S = gae._gather(b["s1"], "s1")
+    Y = ops.spmm(A, S)
+    rp = A.rowptr.long()
+    rr = rows_loc[:32]
+    e = 0.0
+    for i in rr.tolist():
+        cols = A.colidx[rp[i]:rp[i + 1]].long()
+        ref = (A.vals[rp[i]:rp[i + 1]].double()[:, None] * S[cols].double()).sum(0)
+        e = max(e, float((Y[i].double() - ref).norm() / ref.norm().clamp(min=1e-30)))
+    out["spmm_rel_err_32_rows"] = e
+    assert e < 1e-5, f"aggregate mismatch: {e}"
+    out["decoder_loss"] = float(loss.item())
+    return out
+
+
+def gpu_step_ms(n, G, dev, precision, steps=5):
+    """Device-timed ms per scGNN step on the first `n` cells of the dataset (the CPU arm's sample) — single GPU."""
+    from dance_b200 import ops
+    from dance_b200.engine import FeatureAEEngine, GraphAEEngine
+    X = synth_expression(n, G, dev)
+    fae = FeatureAEEngine(G, device=dev, lr=1e-3, precision=precision, seed=0)
+    gae = GraphAEEngine(128, EMB, device=dev, lr=1e-2, precision=precision, seed=1)
+    z_all = torch.empty(n, 128, dtype=torch.float32, device=dev)
+    fae.train_epoch(X, BATCH, "LTMG", 0.9, None, z_all, None)
+    idx, _ = ops.knn(z_all, K_NN, include_rank0=False, return_dist=False)
+    A = ops.knn_graph_build(idx)
+    labels = ops.CSR(A.rowptr, A.colidx, None, A.shape)
+    adj_sum = A.nnz - n
+    pw, norm = float(n * n - adj_sum) / adj_sum, n * n / float((n * n - adj_sum) * 2)
+    eps = torch.randn(n, EMB, device=dev)
+
+    def step():
+        fae.train_epoch(X, BATCH, "LTMG", 0.9, None, z_all, None)
+        gae.train_step(z_all, A, labels, norm, pw, eps)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        step()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / steps
 
 
 if __name__ == "__main__":
