@@ -301,9 +301,8 @@ def kmeans_fit_predict(embed, k: int, device, seed: int = 0, init_max_cells: int
     else:
         host = xe.cpu().numpy()
     host = host - host.mean(0)                      # KMeans centres the data before seeding (sklearn _kmeans.py: X -= X_mean)
-    rs = np.random.RandomState(seed)
-    seeds_rs = np.random.RandomState(rs.randint(np.iinfo(np.int32).max))
-    centers, _ = kmeans_plusplus(host.astype(np.float32), k, random_state=seeds_rs)
+    # KMeans.fit hands its RandomState(random_state) straight to the k-means++ routine (sklearn _kmeans.py, _init_centroids)
+    centers, _ = kmeans_plusplus(host.astype(np.float32), k, random_state=np.random.RandomState(seed))
     mean = xe.mean(0, keepdim=True)
     xc = (xe - mean).contiguous()
     C0 = torch.from_numpy(np.ascontiguousarray(centers, dtype=np.float32)).to(device)
