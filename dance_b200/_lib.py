@@ -18,6 +18,8 @@ c_i32, c_i64, c_f32, c_vp, c_sz = C.c_int32, C.c_int64, C.c_float, C.c_void_p, C
 _SIGNATURES = {
     "b2_last_error": (C.c_char_p, []),
     "b2_version": (C.c_int, []),
+    "b2_set_path": (C.c_int, [C.c_int, C.c_int]),
+    "b2_get_path": (C.c_int, [C.c_int]),
     "b2_launch_count": (c_i64, []),
     "b2_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "b2_spmm_csr_f32": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32, C.c_int, C.c_int, c_vp, c_vp]),
@@ -41,6 +43,9 @@ _SIGNATURES = {
     "b2_gae_loss_workspace_bytes": (c_sz, [c_i32, c_i32]),
     "b2_gae_loss_grad_f32": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_f32, C.c_int,
                                        c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
+    "b2_gae_sym_super_blocks": (C.c_int, [c_i32]),
+    "b2_gae_loss_grad_sym_f32": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_f32,
+                                           C.c_int, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "b2_adam_step_f32": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_vp]),
     "b2_relu_bwd_f32": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "b2_reparam_fwd_f32": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_vp]),

@@ -286,8 +286,8 @@ size_t workspace_bytes(int32_t n) {
 }
 
 bool eligible(int32_t n, int32_t d, int32_t n_rows) {
-  static const bool no_tc = getenv("B2_GAE_NO_TC") != nullptr;   // A/B path selector (both paths are exact), read once
-  if (no_tc) return false;
+  const int mode = path_mode(B2_PATH_GAE_DECODER);           // 0 auto · 2 this kernel
+  if (mode != 0 && mode != 2) return false;
   return d >= 1 && d <= DW && (int64_t)n * n_rows >= (1ll << 22);
 }
 

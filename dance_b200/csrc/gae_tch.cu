@@ -386,8 +386,8 @@ size_t workspace_bytes(int32_t n) {
 }
 
 bool eligible(int32_t n, int32_t d, int32_t n_rows) {
-  static const bool off = getenv("B2_GAE_NO_TC") || getenv("B2_GAE_NO_F16");   // A/B path selectors (exact fallbacks), read once
-  if (off) return false;
+  const int mode = path_mode(B2_PATH_GAE_DECODER);           // 0 auto · 3 this kernel · 4 symmetric (row shards fall back to this one)
+  if (mode == 1 || mode == 2) return false;
   return d >= 1 && d <= DW && (int64_t)n * n_rows >= (1ll << 22);
 }
 

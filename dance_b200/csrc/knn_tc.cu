@@ -260,8 +260,7 @@ size_t workspace_bytes(int32_t n, int32_t d, int32_t n_q) {
 }
 
 bool eligible(int32_t n, int32_t d, int32_t n_q, int M) {
-  static const bool no_tc = getenv("B2_KNN_NO_TC") != nullptr;   // A/B path selector (both paths are bit-exact), read once
-  if (no_tc) return false;
+  if (path_mode(B2_PATH_KNN_FILTER) == 1) return false;      // SIMT filter requested (both filters are bit-exact)
   return M == MC && d >= 8 && padded_d(d) <= 64 * MAX_ATOMS && (int64_t)n * n_q >= (1ll << 24);
 }
 

@@ -259,6 +259,14 @@ int launch(const float* z, int64_t ldz, int32_t n, int32_t d, int32_t row_begin,
            double* loss_acc, void* ws, size_t ws_bytes, cudaStream_t st);
 }  // namespace gtch
 
+namespace gsym {   // gae_sym.cu: symmetric (unordered block pairs) tcgen05 version — half the elementwise work of gae_tch.cu
+size_t workspace_bytes(int32_t n);
+int super_blocks(int32_t n);
+bool eligible(int32_t n, int32_t d);
+int launch(const float* z, int64_t ldz, int32_t n, int32_t d, int32_t sb_begin, int32_t sb_end, float coef, float* dz,
+           double* loss_acc, void* ws, size_t ws_bytes, cudaStream_t st);
+}  // namespace gsym
+
 template <int D>
 static int launch_gae_edges(const float* z, int64_t ldz, const int32_t* rp, const int32_t* ci, int32_t row_begin, int32_t n_rows,
                             float coef, float pw, int use_pw, float* dz, double* acc, cudaStream_t st) {
@@ -313,8 +321,9 @@ extern "C" int b2_mse_sum_loss_grad_f32(const float* recon, const float* target,
 
 extern "C" size_t b2_gae_loss_workspace_bytes(int32_t n, int32_t d) {
   // 256 B of accumulators + the hi/lo tf32 split of z (padded to 32 columns) for the tensor-core path
-  const size_t a = gtc::workspace_bytes(n), b = gtch::workspace_bytes(n);
-  return 256 + (d <= 32 ? (a > b ? a : b) : 0);
+  const size_t a = gtc::workspace_bytes(n), b = gtch::workspace_bytes(n), c = gsym::workspace_bytes(n);
+  const size_t m = a > b ? (a > c ? a : c) : (b > c ? b : c);
+  return 256 + (d <= 32 ? m : 0);
 }
 
 extern "C" int b2_gae_loss_grad_f32(const float* z, int64_t ldz, const float* mu, const float* logvar, int64_t ldm,
@@ -336,7 +345,14 @@ extern "C" int b2_gae_loss_grad_f32(const float* z, int64_t ldz, const float* mu
   int rc;
   // large problems: the all-pairs part runs on tcgen05 (gae_tc.cu); the CUDA-core kernel serves small graphs
   bool tc_done = false;
-  if (gtch::eligible(n, d, n_rows) && workspace_bytes >= 256 + gtch::workspace_bytes(n)) {
+  // full row range: the symmetric kernel evaluates every unordered block pair once (gae_sym.cu); a row shard of a multi-GPU run
+  // goes through b2_gae_loss_grad_sym_f32 instead (super-block ranges + all-reduce of dz), or falls through to the row-sweep kernel
+  if (row_begin == 0 && n_rows == n && gsym::eligible(n, d) && workspace_bytes >= 256 + gsym::workspace_bytes(n)) {
+    rc = gsym::launch(z, ldz, n, d, 0, gsym::super_blocks(n), coef, dz, acc, reinterpret_cast<char*>(workspace) + 256, workspace_bytes - 256, st);
+    if (rc == B2_OK) tc_done = true;
+    else if (rc != B2_ERR_UNSUPPORTED) return rc;
+  }
+  if (!tc_done && gtch::eligible(n, d, n_rows) && workspace_bytes >= 256 + gtch::workspace_bytes(n)) {
     rc = gtch::launch(z, ldz, n, d, row_begin, n_rows, coef, dz, acc, reinterpret_cast<char*>(workspace) + 256, workspace_bytes - 256, st);
     if (rc == B2_OK) tc_done = true;
     else if (rc != B2_ERR_UNSUPPORTED) return rc;
@@ -353,6 +369,60 @@ extern "C" int b2_gae_loss_grad_f32(const float* z, int64_t ldz, const float* mu
     case 64: rc = launch_gae<64>(z, ldz, lab_rowptr, lab_colidx, n, row_begin, n_rows, coef, pos_weight, use_pos_weight, dz, acc, tc_done, st); break;
     default:
       set_error("b2_gae_loss_grad_f32: embedding size %d unsupported (8, 16, 32, 64)", d);
+      return B2_ERR_UNSUPPORTED;
+  }
+  if (rc != B2_OK) return rc;
+  if (mu) {
+    int64_t blocks = ceil_div<int64_t>((int64_t)n_rows * d, 256);
+    if (blocks < 1) blocks = 1;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    gae_kld_kernel<<<(unsigned)blocks, 256, 0, st>>>(mu, logvar, ldm, n, n_rows, d, dmu, dlogvar, ldd, acc);
+    B2_CHECK_LAUNCH("gae_kld_kernel");
+  }
+  gae_finish_kernel<<<1, 1, 0, st>>>(acc, loss_out);
+  B2_CHECK_LAUNCH("gae_finish_kernel");
+  return B2_OK;
+}
+
+
+// Pair-sharded form of b2_gae_loss_grad_f32 for multi-GPU runs (the symmetric decoder cannot be row-sharded: a tile feeds the
+// gradient of BOTH its row block and its column block).  Rank r evaluates the super-blocks [sb_begin, sb_end) of the cyclic
+// block-pair schedule (b2_gae_sym_super_blocks(n) in total, equal work each) plus the label / KLD terms of its own rows
+// [row_begin, row_begin + n_rows):
+//   dz_full [n, d]  : zero-filled here, receives this rank's all-pairs contributions to ALL rows and the label terms of its own
+//                     rows — the caller sums dz_full over ranks (all-reduce) and keeps its rows;
+//   loss_out        : this rank's share of the loss (sum over ranks = the loss).
+extern "C" int b2_gae_sym_super_blocks(int32_t n) { return b2::gsym::super_blocks(n); }
+
+extern "C" int b2_gae_loss_grad_sym_f32(const float* z, int64_t ldz, const float* mu, const float* logvar, int64_t ldm,
+                                        const int32_t* lab_rowptr, const int32_t* lab_colidx, int32_t n, int32_t d,
+                                        int32_t sb_begin, int32_t sb_end, int32_t row_begin, int32_t n_rows, float norm, float pos_weight,
+                                        int use_pos_weight, float* dz_full, float* dmu, float* dlogvar, int64_t ldd, float* loss_out,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  B2_REQUIRE(z && lab_rowptr && lab_colidx && dz_full && loss_out, "b2_gae_loss_grad_sym_f32: null pointer");
+  B2_REQUIRE(n > 0 && d > 0 && d <= 16 && ldz >= d, "b2_gae_loss_grad_sym_f32: bad shape (d <= 16)");
+  B2_REQUIRE(row_begin >= 0 && n_rows >= 0 && row_begin + n_rows <= n, "b2_gae_loss_grad_sym_f32: bad row range");
+  B2_REQUIRE(sb_begin >= 0 && sb_begin <= sb_end && sb_end <= gsym::super_blocks(n), "b2_gae_loss_grad_sym_f32: bad super-block range");
+  B2_REQUIRE(workspace && workspace_bytes >= 256 + gsym::workspace_bytes(n), "b2_gae_loss_grad_sym_f32: workspace too small");
+  B2_REQUIRE((mu == nullptr) == (logvar == nullptr), "b2_gae_loss_grad_sym_f32: mu/logvar must both be given or both NULL");
+  if (mu) B2_REQUIRE(dmu && dlogvar && ldm >= d && ldd >= d, "b2_gae_loss_grad_sym_f32: dmu/dlogvar required with mu/logvar");
+  cudaStream_t st = as_stream(stream);
+  double* acc = reinterpret_cast<double*>(workspace);
+  B2_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), st));
+  B2_CHECK_CUDA(cudaMemsetAsync(dz_full, 0, sizeof(float) * (size_t)n * d, st));
+  const float coef = (use_pos_weight ? norm : 1.f) / ((float)n * (float)n);
+  int rc = gsym::launch(z, ldz, n, d, sb_begin, sb_end, coef, dz_full, acc, reinterpret_cast<char*>(workspace) + 256, workspace_bytes - 256, st);
+  if (rc != B2_OK) {
+    if (rc == B2_ERR_UNSUPPORTED) set_error("b2_gae_loss_grad_sym_f32: tensor maps could not be built");
+    return rc;
+  }
+  float* dz_rows = dz_full + (size_t)row_begin * d;
+  switch (d) {
+    case 8: rc = launch_gae<8>(z, ldz, lab_rowptr, lab_colidx, n, row_begin, n_rows, coef, pos_weight, use_pos_weight, dz_rows, acc, true, st); break;
+    case 16: rc = launch_gae<16>(z, ldz, lab_rowptr, lab_colidx, n, row_begin, n_rows, coef, pos_weight, use_pos_weight, dz_rows, acc, true, st); break;
+    default:
+      set_error("b2_gae_loss_grad_sym_f32: embedding size %d unsupported (8, 16)", d);
       return B2_ERR_UNSUPPORTED;
   }
   if (rc != B2_OK) return rc;

@@ -35,6 +35,10 @@ int sm_count() {
 
 const char* last_error() { return g_err; }
 
+// kernel-path selectors (b2_set_path): every selectable path computes the same result, the switch exists for A/B tests
+static int g_path[B2_PATH_COUNT] = {0, 0};
+int path_mode(int which) { return (which >= 0 && which < B2_PATH_COUNT) ? g_path[which] : 0; }
+
 }  // namespace b2
 
 extern "C" {
@@ -44,6 +48,15 @@ const char* b2_last_error(void) { return b2::last_error(); }
 int b2_version(void) { return 100; }
 
 int64_t b2_launch_count(void) { return (int64_t)b2::g_launch_count; }
+
+int b2_set_path(int which, int mode) {
+  B2_REQUIRE(which >= 0 && which < B2_PATH_COUNT, "b2_set_path: unknown selector %d", which);
+  B2_REQUIRE(mode >= 0 && mode <= (which == B2_PATH_GAE_DECODER ? 4 : 1), "b2_set_path: mode %d out of range for selector %d", mode, which);
+  b2::g_path[which] = mode;
+  return B2_OK;
+}
+
+int b2_get_path(int which) { return b2::path_mode(which); }
 
 int b2_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;

@@ -12,6 +12,7 @@ Reference being replaced:
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -294,8 +295,21 @@ class GraphAEEngine:
         z, mu, logvar = self.forward(x, adj, eps)
         dmu, dlv = b["dml"][:, :e], b["dml"][:, e:]
         z_all = self._gather(z, "z")
-        ops.gae_loss_grad(z_all, labels, norm, pos_weight, mu, logvar, True, dz=b["dz"], dmu=dmu, dlogvar=dlv, loss=self.loss,
-                          row_begin=row_begin, n_rows=n_loc)
+        n_all = z_all.shape[0]
+        path = ops.get_path("gae")
+        if sharded and e <= 16 and (path == "sym" or (path == "auto" and n_all * n_all >= (1 << 24))):
+            # the symmetric decoder is partitioned by block PAIR (each logit tile feeds two row blocks): this rank takes its share of
+            # the equal-work super-blocks, writes partial gradients for ALL rows and the ranks sum them (one 64 MB all-reduce at 1 M)
+            from .parallel import shard_bounds
+            sb0, sb1 = shard_bounds(ops.gae_sym_super_blocks(n_all), comm.world)[comm.rank]
+            dzf = self._bufs.setdefault(("dz_full", n_all), torch.empty(n_all, e, dtype=torch.float32, device=self.device))
+            ops.gae_loss_grad_sym(z_all, labels, norm, pos_weight, sb0, sb1, mu, logvar, True, dz_full=dzf, dmu=dmu, dlogvar=dlv,
+                                  loss=self.loss, row_begin=row_begin, n_rows=n_loc)
+            comm.allreduce_sum_(dzf)
+            b["dz"].copy_(dzf[row_begin:row_begin + n_loc])
+        else:
+            ops.gae_loss_grad(z_all, labels, norm, pos_weight, mu, logvar, True, dz=b["dz"], dmu=dmu, dlogvar=dlv, loss=self.loss,
+                              row_begin=row_begin, n_rows=n_loc)
         ops.reparam_bwd(b["dz"], logvar, eps, dmu, dlv)                  # chain through z = mu + eps·exp(logvar)
         ops.spmm(adj_t, self._gather(b["dml"], "dml"), out=b["ds2"])     # d support2 = Âᵀ · d[mu|logvar]
         ops.gemm(b["h1"], b["ds2"], transA=True, out=G["gc23.weight"], precision=pr)

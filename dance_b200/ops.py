@@ -125,6 +125,22 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return buf
 
 
+_PATHS = {"gae": (0, {"auto": 0, "cuda": 1, "tf32": 2, "f16": 3, "sym": 4}), "knn": (1, {"auto": 0, "simt": 1})}
+
+
+def set_path(which: str, mode: str = "auto") -> None:
+    """Select the kernel path of the decoder ("gae": auto | cuda | tf32 | f16 | sym) or of the kNN candidate filter
+    ("knn": auto | simt).  All paths return the same result; the switch exists for A/B tests and timing."""
+    sel, modes = _PATHS[which]
+    check(lib().b2_set_path(sel, modes[mode]), "b2_set_path")
+
+
+def get_path(which: str) -> str:
+    sel, modes = _PATHS[which]
+    v = lib().b2_get_path(sel)
+    return next(k for k, m in modes.items() if m == v)
+
+
 def device_info() -> Tuple[int, int, int]:
     a, b, c = C.c_int(), C.c_int(), C.c_int()
     check(lib().b2_device_info(C.byref(a), C.byref(b), C.byref(c)), "b2_device_info")
@@ -337,6 +353,50 @@ def gae_loss_grad(z, labels: CSR, norm: float, pos_weight: float, mu=None, logva
                                      _p(dz), _p(dmu), _p(dlogvar), ldd, _p(loss), _p(ws), ws.numel(), _stream()),
           "b2_gae_loss_grad_f32")
     return loss, dz, dmu, dlogvar
+
+
+def gae_sym_super_blocks(n: int) -> int:
+    """Equal-work units of the symmetric decoder's block-pair schedule (see gae_loss_grad_sym)."""
+    return int(lib().b2_gae_sym_super_blocks(n))
+
+
+def gae_loss_grad_sym(z, labels: CSR, norm: float, pos_weight: float, sb_begin: int, sb_end: int, mu=None, logvar=None,
+                      use_pos_weight=True, dz_full=None, dmu=None, dlogvar=None, loss=None, row_begin: int = 0,
+                      n_rows: Optional[int] = None):
+    """Pair-sharded matrix-free Graph-AE loss (multi-GPU form of :func:`gae_loss_grad`): this rank evaluates super-blocks
+    ``[sb_begin, sb_end)`` of the unordered block-pair schedule and the label / KLD terms of its rows.  Returns
+    ``(loss_share[1], dz_full[n, d], dmu, dlogvar)``; all-reduce ``dz_full`` and ``loss_share`` over ranks."""
+    _chk(z, torch.float32, "z", 2)
+    n, d = z.shape
+    n_rows = n if n_rows is None else n_rows
+    if labels.shape[0] != n_rows or labels.shape[1] != n:
+        raise B2Error(f"gae_loss_grad_sym: labels must be [{n_rows}, {n}], got {tuple(labels.shape)}")
+    if dz_full is None:
+        dz_full = torch.empty((n, d), dtype=torch.float32, device=z.device)
+    _chk(dz_full, torch.float32, "dz_full", 2)
+    if tuple(dz_full.shape) != (n, d) or not dz_full.is_contiguous():
+        raise B2Error(f"gae_loss_grad_sym: dz_full must be a contiguous [{n}, {d}] buffer")
+    ldm = ldd = 0
+    if mu is not None:
+        _chk(mu, torch.float32, "mu", 2)
+        _chk(logvar, torch.float32, "logvar", 2)
+        ldm = _rowmajor(mu, "mu")
+        if _rowmajor(logvar, "logvar") != ldm:
+            raise B2Error("gae_loss_grad_sym: mu and logvar must share a leading dimension")
+        if dmu is None:
+            dmu = torch.empty((n_rows, d), dtype=torch.float32, device=z.device)
+            dlogvar = torch.empty((n_rows, d), dtype=torch.float32, device=z.device)
+        ldd = _rowmajor(dmu, "dmu")
+        if _rowmajor(dlogvar, "dlogvar") != ldd:
+            raise B2Error("gae_loss_grad_sym: dmu and dlogvar must share a leading dimension")
+    if loss is None:
+        loss = torch.empty(1, dtype=torch.float32, device=z.device)
+    ws = _workspace(lib().b2_gae_loss_workspace_bytes(n, d), z.device)
+    check(lib().b2_gae_loss_grad_sym_f32(_p(z), _rowmajor(z, "z"), _p(mu), _p(logvar), ldm, _p(labels.rowptr), _p(labels.colidx), n, d,
+                                         sb_begin, sb_end, row_begin, n_rows, float(norm), float(pos_weight), int(use_pos_weight),
+                                         _p(dz_full), _p(dmu), _p(dlogvar), ldd, _p(loss), _p(ws), ws.numel(), _stream()),
+          "b2_gae_loss_grad_sym_f32")
+    return loss, dz_full, dmu, dlogvar
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, step: int, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0):

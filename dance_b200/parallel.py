@@ -48,6 +48,30 @@ def batch_schedule(n_local: int, batch_size: int, n_steps: Optional[int] = None)
     return sched
 
 
+def sym_schedule(n_blocks: int, super_block: int) -> List[Tuple[int, int]]:
+    """Logit tiles (I, J) of 128-row blocks that super-block ``super_block`` of the symmetric decoder evaluates — the host-side
+    statement of ``gsym::Sweep`` (csrc/gae_sym.cu), used to shard the decoder over ranks and to test the schedule.
+
+    Block I owns the unordered pairs {I, (I+o) mod nb}, o = 0..h with h = nb // 2; for even nb the antipodal pair (o = h) belongs
+    to the smaller index.  A super-block is the two adjacent blocks (2·sb, 2·sb+1); together the super-blocks cover every
+    unordered pair exactly once with (almost) equal work."""
+    nb, h = n_blocks, n_blocks // 2
+    even = nb % 2 == 0
+    out = []
+    for I in (2 * super_block, 2 * super_block + 1):
+        if I >= nb:
+            continue
+        for o in range(h + 1):
+            if o == h and o > 0 and even and I + h >= nb:
+                continue
+            out.append((I, (I + o) % nb))
+    return out
+
+
+def sym_super_blocks(n: int, block: int = 128) -> int:
+    return ((n + block - 1) // block + 1) // 2
+
+
 class Comm:
     """Thin wrapper over a torch.distributed process group (or a no-op for world size 1)."""
 

@@ -45,6 +45,14 @@ extern "C" {
 #define B2_PREC_TF32X3 1    /* tcgen05 kind::tf32, 3-product split, ~fp32 accuracy */
 #define B2_PREC_TF32 2      /* tcgen05 kind::tf32, single product                */
 
+/* Kernel-path selectors for A/B tests: every selectable path returns the same result (bit-exact for the kNN filter, to
+ * rounding for the decoder); mode 0 = automatic choice by problem size. */
+#define B2_PATH_GAE_DECODER 0 /* 1 CUDA cores · 2 tcgen05 tf32 split · 3 tcgen05 fp16 row sweep · 4 tcgen05 fp16 symmetric */
+#define B2_PATH_KNN_FILTER 1  /* 1 SIMT candidate filter */
+#define B2_PATH_COUNT 2
+int b2_set_path(int which, int mode);
+int b2_get_path(int which);
+
 const char* b2_last_error(void);
 int b2_version(void);
 /* Number of CUDA kernels this library has launched in the calling process (bench.py's `gpu_launches`). */
@@ -449,6 +457,19 @@ int b2_adj_loss_grad_f32(const float* z, const float* mu, const float* log_std, 
                          const float* class_weight, int32_t g, float coef_ce, float* dz, double* acc2, void* stream);
 int b2_adj_reparam_bwd_f32(const float* dz, const float* mu, const float* log_std, const float* eps, int64_t n_elem,
                            float coef_kl, float* dmu, float* dlog_std, void* stream);
+
+/* Pair-sharded form of b2_gae_loss_grad_f32 for multi-GPU runs (InnerProductDecoder + gae_loss_function, scgnn2.py:423-426,
+ * 603-619).  The all-pairs part is evaluated over UNORDERED 128-row block pairs (each logit tile feeds the gradient of its row
+ * block and of its column block), so it is partitioned by pair, not by row: rank r takes super-blocks [sb_begin, sb_end) of the
+ * b2_gae_sym_super_blocks(n) equal-work units, plus the label / KLD terms of its own rows [row_begin, row_begin + n_rows).
+ * dz_full [n, d] is zero-filled here and receives contributions to ALL rows: sum it over ranks (all-reduce); loss_out holds
+ * this rank's share of the loss.  d <= 16.  Workspace: b2_gae_loss_workspace_bytes(n, d). */
+int b2_gae_sym_super_blocks(int32_t n);
+int b2_gae_loss_grad_sym_f32(const float* z, int64_t ldz, const float* mu, const float* logvar, int64_t ldm,
+                             const int32_t* lab_rowptr, const int32_t* lab_colidx, int32_t n, int32_t d,
+                             int32_t sb_begin, int32_t sb_end, int32_t row_begin, int32_t n_rows, float norm, float pos_weight,
+                             int use_pos_weight, float* dz_full, float* dmu, float* dlogvar, int64_t ldd, float* loss_out,
+                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
  * scGNN EM-iteration stages

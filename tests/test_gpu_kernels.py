@@ -202,7 +202,7 @@ def test_knn_bit_exact_vs_oracle(cuda, n, d, k):
 @pytest.mark.parametrize("n,d,k", [(6000, 128, 15), (5000, 50, 15), (4500, 16, 10)])
 def test_knn_tensor_core_filter_bit_exact(cuda, n, d, k):
     """n·n_q ≥ 2^24 routes the candidate filter through tcgen05 (fp16 hi/lo split); the fp64 refine + proof keep the result
-    bit-exact with the reference ranking; duplicates, a query range, and the SIMT filter (B2_KNN_NO_TC) agree."""
+    bit-exact with the reference ranking; duplicates, a query range, and the SIMT filter (ops.set_path("knn", "simt")) agree."""
     import os
     from dance_b200 import ops
     from oracle import port
@@ -214,11 +214,11 @@ def test_knn_tensor_core_filter_bit_exact(cuda, n, d, k):
     idx, dist = ops.knn(Xc, k)
     assert np.array_equal(idx.cpu().numpy().astype(np.int64), idx_ref)
     assert np.array_equal(dist.cpu().numpy(), dist_ref)
-    os.environ["B2_KNN_NO_TC"] = "1"
+    ops.set_path("knn", "simt")
     try:
         idx_s, _ = ops.knn(Xc, k)
     finally:
-        del os.environ["B2_KNN_NO_TC"]
+        ops.set_path("knn", "auto")
     assert torch.equal(idx, idx_s)
     part, _ = ops.knn(Xc, k, q_begin=300, q_end=n - 200)      # n·n_q still above the threshold: sharded queries on the TC path
     assert torch.equal(part, idx[300:n - 200])
@@ -393,6 +393,71 @@ def test_gae_loss_tensor_core_single_column_range(cuda):
     assert rel_err(torch.cat([dza, dzb]), ref_dz) < 2e-5
 
 
+@pytest.mark.parametrize("n,d", [(128, 16), (100, 16), (256, 16), (300, 16), (384, 8), (1000, 16), (1537, 12), (2048, 16), (2049, 16)])
+def test_gae_symmetric_decoder_small_graphs(cuda, n, d):
+    """gae_sym.cu forced onto small graphs: 1, 2, 3, 8, 13, 16, 17 row blocks (odd / even counts, antipodal pairs, a ragged last
+    block, a lone last super-block) against the fp64 closed form and against the row-sweep kernel."""
+    from dance_b200 import ops
+    gen = torch.Generator(device=cuda).manual_seed(n * 31 + d)
+    z = (torch.randn(n, d, device=cuda, generator=gen) * 0.6).contiguous()
+    idx = torch.randint(0, n, (n, 5), device=cuda, dtype=torch.int32, generator=gen)
+    A = ops.knn_graph_build(idx.contiguous())
+    L = ops.CSR(A.rowptr, A.colidx, None, A.shape)
+    norm, pw = 0.51, 37.0
+    ref_loss, ref_dz = gae_reference_rows(z, A.rowptr, A.colidx, norm, pw, torch.arange(n, device=cuda))
+    ops.set_path("gae", "sym")
+    try:
+        loss, dz, _, _ = ops.gae_loss_grad(z, L, norm, pw)
+        loss2, dz2, _, _ = ops.gae_loss_grad(z, L, norm, pw)
+    finally:
+        ops.set_path("gae", "auto")
+    assert abs(loss.item() - ref_loss) < 2e-6 * abs(ref_loss), (loss.item(), ref_loss)
+    assert rel_err(dz, ref_dz) < 2e-5
+    assert rel_err(dz2, dz) < 1e-6 and abs(loss2.item() - loss.item()) < 1e-6 * abs(loss.item())   # atomics reorder sums only
+    ops.set_path("gae", "f16")
+    try:
+        loss_r, dz_r, _, _ = ops.gae_loss_grad(z, L, norm, pw)
+    finally:
+        ops.set_path("gae", "auto")
+    assert rel_err(dz, dz_r) < 2e-5 and abs(loss.item() - loss_r.item()) < 2e-6 * abs(ref_loss)
+
+
+@pytest.mark.parametrize("n,parts", [(5000, 2), (19_333, 3)])
+def test_gae_symmetric_decoder_pair_sharded(cuda, n, parts):
+    """b2_gae_loss_grad_sym_f32: contiguous super-block ranges + row ranges of the label terms; the summed partial gradients and
+    loss shares equal the single-call result and the fp64 closed form (the multi-GPU decomposition, run on one device)."""
+    from dance_b200 import ops
+    from dance_b200.parallel import shard_bounds
+    d = 16
+    gen = torch.Generator(device=cuda).manual_seed(n)
+    z = (torch.randn(n, d, device=cuda, generator=gen) * 0.5).contiguous()
+    mu = torch.randn(n, d, device=cuda, generator=gen) * 0.3
+    lv = torch.randn(n, d, device=cuda, generator=gen) * 0.1
+    idx = torch.randint(0, n, (n, 6), device=cuda, dtype=torch.int32, generator=gen)
+    A = ops.knn_graph_build(idx.contiguous())
+    L = ops.CSR(A.rowptr, A.colidx, None, A.shape)
+    norm, pw = 0.5002, 900.0
+    full_loss, full_dz, full_dmu, full_dlv = ops.gae_loss_grad(z, L, norm, pw, mu, lv)
+    nsb = ops.gae_sym_super_blocks(n)
+    rp = A.rowptr.long()
+    dz_sum = torch.zeros(n, d, device=cuda)
+    loss_sum = 0.0
+    dmu_parts, dlv_parts = [], []
+    for (s0, s1), (r0, r1) in zip(shard_bounds(nsb, parts), shard_bounds(n, parts)):
+        sub = ops.CSR((A.rowptr[r0:r1 + 1] - A.rowptr[r0]).contiguous(), A.colidx[rp[r0]:rp[r1]].contiguous(), None, (r1 - r0, n))
+        l, dzf, dmu, dlv = ops.gae_loss_grad_sym(z, sub, norm, pw, s0, s1, mu[r0:r1].contiguous(), lv[r0:r1].contiguous(), row_begin=r0,
+                                                 n_rows=r1 - r0)
+        dz_sum += dzf
+        loss_sum += l.item()
+        dmu_parts.append(dmu); dlv_parts.append(dlv)
+    assert abs(loss_sum - full_loss.item()) < 2e-6 * abs(full_loss.item())
+    assert rel_err(dz_sum, full_dz) < 1e-5
+    assert rel_err(torch.cat(dmu_parts), full_dmu) < 1e-6 and rel_err(torch.cat(dlv_parts), full_dlv) < 1e-6
+    rows = torch.arange(0, n, 37, device=cuda)
+    _, ref_rows = gae_reference_rows(z, A.rowptr, A.colidx, norm, pw, rows)
+    assert rel_err(dz_sum[rows], ref_rows) < 2e-5
+
+
 @pytest.mark.parametrize("n,d", [(3000, 16), (2500, 16), (4133, 8), (2304, 32)])
 def test_gae_loss_tensor_core_path(cuda, n, d):
     """tcgen05 decoder (S in TMEM → SFU → G in TMEM → dZ) vs the dense fp64 formula and vs the CUDA-core kernel."""
@@ -409,11 +474,11 @@ def test_gae_loss_tensor_core_path(cuda, n, d):
     pw, norm = port.gae_norm_constants(adj)
     ref_loss, ref_dz = _dense_gae_reference(z, Ld, norm, pw)
     loss_tc, dz_tc, _, _ = ops.gae_loss_grad(z, L, norm, pw)
-    os.environ["B2_GAE_NO_TC"] = "1"
+    ops.set_path("gae", "cuda")
     try:
         loss_cc, dz_cc, _, _ = ops.gae_loss_grad(z, L, norm, pw)
     finally:
-        del os.environ["B2_GAE_NO_TC"]
+        ops.set_path("gae", "auto")
     assert abs(loss_tc.item() - ref_loss) < 2e-6 * abs(ref_loss), (loss_tc.item(), ref_loss)
     assert abs(loss_cc.item() - ref_loss) < 2e-6 * abs(ref_loss)
     assert rel_err(dz_tc.cpu().numpy(), ref_dz.cpu().numpy()) < 2e-5

@@ -160,6 +160,68 @@ def _dp_feature_ae_case(rank, world):
     return (torch.norm(flat - flat_ref) / torch.norm(flat_ref)).item()
 
 
+def test_symmetric_decoder_schedule_covers_every_block_pair_once():
+    """gsym::Sweep (csrc/gae_sym.cu) restated on the host: over all super-blocks every unordered pair of 128-row blocks appears
+    exactly once, the work per super-block is balanced, and contiguous super-block ranges (the multi-GPU shards) partition it."""
+    from dance_b200.parallel import shard_bounds, sym_schedule, sym_super_blocks
+    for nb in list(range(1, 14)) + [31, 32, 61]:
+        nsb = (nb + 1) // 2
+        assert sym_super_blocks(nb * 128) == nsb and sym_super_blocks(nb * 128 - 5) == nsb
+        seen = {}
+        loads = []
+        for sb in range(nsb):
+            tiles = sym_schedule(nb, sb)
+            loads.append(len(tiles))
+            for I, J in tiles:
+                key = (min(I, J), max(I, J))
+                assert key not in seen, (nb, key)
+                seen[key] = sb
+                assert I in (2 * sb, 2 * sb + 1)
+        assert len(seen) == nb * (nb + 1) // 2, nb
+        full = [l for l, sb in zip(loads, range(nsb)) if 2 * sb + 1 < nb]
+        if full:
+            assert max(full) - min(full) <= 2, (nb, loads)
+        for world in (2, 3):
+            parts = [sum(loads[a:b]) for a, b in shard_bounds(nsb, world)]
+            assert sum(parts) == sum(loads)
+
+
+def _pair_sharded_decoder_case(rank, world):
+    """Pair-sharded decoder gradient (GraphAEEngine.train_step under sharding): each rank evaluates the tiles of its super-blocks —
+    dZ_I += G·Z_J and dZ_J += Gᵀ·Z_I for I ≠ J — into a full-size buffer; the all-reduced sum equals the dense gradient and the
+    loss shares (off-diagonal tiles counted twice) add up to the dense loss.  torch-CPU arithmetic in place of the CUDA kernel."""
+    from dance_b200.parallel import Comm, shard_bounds, sym_schedule, sym_super_blocks
+    comm = Comm()
+    torch.manual_seed(0)
+    n, d, B = 333, 16, 32                         # small blocks so that several super-blocks exist
+    z = torch.randn(n, d, dtype=torch.float64) * 0.5
+    nb = (n + B - 1) // B
+    nsb = (nb + 1) // 2
+    sb0, sb1 = shard_bounds(nsb, world)[rank]
+    dz = torch.zeros(n, d, dtype=torch.float64)
+    loss = torch.zeros(1, dtype=torch.float64)
+    for sb in range(sb0, sb1):
+        for I, J in sym_schedule(nb, sb):
+            ri, rj = slice(I * B, min(n, (I + 1) * B)), slice(J * B, min(n, (J + 1) * B))
+            S = z[ri] @ z[rj].t()
+            G = torch.sigmoid(S)
+            dz[ri] += G @ z[rj]
+            if I != J:
+                dz[rj] += G.t() @ z[ri]
+            loss += torch.nn.functional.softplus(S).sum() * (1 if I == J else 2)
+    dz *= 2
+    comm.allreduce_sum_(dz)
+    comm.allreduce_sum_(loss)
+    S = z @ z.t()
+    ref = 2 * torch.sigmoid(S) @ z
+    return (torch.norm(dz - ref) / torch.norm(ref)).item(), abs(loss.item() - torch.nn.functional.softplus(S).sum().item()) / loss.item()
+
+
+def test_pair_sharded_decoder_matches_dense_gloo():
+    for rank, errs in _run("_pair_sharded_decoder_case").items():
+        assert max(errs) < 1e-12, (rank, errs)
+
+
 def _uneven_epoch_case(rank, world):
     """Feature-AE data parallelism with uneven shards: 21 cells on 2 ranks, batch 5 → 11 / 10 rows = 3 / 2 local
     batches.  Driving FeatureAEEngine.train_epoch's schedule (parallel.batch_schedule + idle steps) with the oracle's torch-CPU
