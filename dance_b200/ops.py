@@ -981,3 +981,54 @@ def louvain_host(indptr, indices, weights=None, max_levels: int = 0, min_gain: f
     check(lib().b2_louvain_csr_host(indptr.ctypes.data, indices.ctypes.data, None if w is None else w.ctypes.data, n, labels.ctypes.data,
                                     C.byref(nc), C.byref(mod), int(max_levels), float(min_gain)), "b2_louvain_csr_host")
     return labels, nc.value, mod.value
+
+
+# ----------------------------------------------------------------------------- pre-processing reductions (csrc/prep.cu)
+def gene_stats(X: torch.Tensor, want_sumsq: bool = True, want_nnz: bool = True):
+    """Per-gene (column) Σx, Σx², #(x>0) in fp64: returns (sum, sumsq | None, nnz | None)."""
+    _chk(X, torch.float32, "X", 2)
+    n, g = X.shape
+    mk = lambda: torch.empty(g, dtype=torch.float64, device=X.device)
+    s, q, k = mk(), (mk() if want_sumsq else None), (mk() if want_nnz else None)
+    check(lib().b2_gene_stats_f32(_p(X), _rowmajor(X, "X"), n, g, _p(s), _p(q), _p(k), _stream()), "b2_gene_stats_f32")
+    return s, q, k
+
+
+def cell_stats(X: torch.Tensor, want_nnz: bool = True):
+    """Per-cell (row) Σx and #(x>0) in fp64."""
+    _chk(X, torch.float32, "X", 2)
+    n, g = X.shape
+    s = torch.empty(n, dtype=torch.float64, device=X.device)
+    k = torch.empty(n, dtype=torch.float64, device=X.device) if want_nnz else None
+    check(lib().b2_cell_stats_f32(_p(X), _rowmajor(X, "X"), n, g, _p(s), _p(k), _stream()), "b2_cell_stats_f32")
+    return s, k
+
+
+def subset(X: torch.Tensor, rows: Optional[torch.Tensor] = None, cols: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``X[rows][:, cols]`` as a new dense matrix (``None`` keeps the axis)."""
+    _chk(X, torch.float32, "X", 2)
+    if rows is not None:
+        _chk(rows, torch.int64, "rows", 1)
+    if cols is not None:
+        _chk(cols, torch.int32, "cols", 1)
+    n_out = X.shape[0] if rows is None else rows.numel()
+    g_out = X.shape[1] if cols is None else cols.numel()
+    out = torch.empty((n_out, g_out), dtype=torch.float32, device=X.device)
+    check(lib().b2_subset_f32(_p(X), _rowmajor(X, "X"), _p(rows), _p(cols), n_out, g_out, _p(out), max(g_out, 1), _stream()), "b2_subset_f32")
+    return out
+
+
+def cellwise_mask(X: torch.Tensor, mask_rate: float = 0.1, min_gene_counts: int = 5, distr: str = "exp", add_test_mask: bool = False,
+                  seed: int = 0):
+    """CellwiseMaskData masks (train, valid, test) as bool [n, g] device tensors."""
+    _chk(X, torch.float32, "X", 2)
+    if distr not in ("exp", "uniform"):
+        raise ValueError(f"Unknown distribution function option {distr!r}, available options are: 'exp', 'uniform'")
+    n, g = X.shape
+    mk = lambda: torch.empty((n, g), dtype=torch.uint8, device=X.device)
+    tr, va, te = mk(), mk(), mk()
+    over = torch.zeros(1, dtype=torch.int32, device=X.device)
+    check(lib().b2_cellwise_mask_u8(_p(X), _rowmajor(X, "X"), n, g, float(mask_rate), int(min_gene_counts), int(distr == "exp"),
+                                    int(add_test_mask), int(seed) & 0xFFFFFFFF, _p(tr), _p(va), _p(te), _p(over), _stream()),
+          "b2_cellwise_mask_u8")
+    return tr.view(torch.bool), va.view(torch.bool), te.view(torch.bool), int(over.item())

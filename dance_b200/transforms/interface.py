@@ -12,7 +12,9 @@ from .base import BaseTransform
 
 _GPU_DISPATCH = {"scanpy.pp.normalize_total": pp.normalize_total, "scanpy.pp.log1p": pp.log1p,
                  "scanpy.preprocessing._normalization.normalize_total": pp.normalize_total,
-                 "scanpy.preprocessing._simple.log1p": pp.log1p}
+                 "scanpy.preprocessing._simple.log1p": pp.log1p,
+                 "scanpy.pp.filter_genes": pp.filter_genes, "scanpy.pp.filter_cells": pp.filter_cells,
+                 "scanpy.preprocessing._simple.filter_genes": pp.filter_genes, "scanpy.preprocessing._simple.filter_cells": pp.filter_cells}
 
 
 class AnnDataTransform(BaseTransform):

@@ -499,6 +499,26 @@ int b2_l1_grad_add_f32(const float* param, float* grad, int64_t n, float coef, f
 int b2_louvain_csr_host(const int64_t* rowptr, const int32_t* colidx, const double* weights, int32_t n, int32_t* labels_out,
                         int32_t* n_comm_out, double* modularity_out, int max_levels, double min_gain);
 
+/* ------------------------------------------------------------------------
+ * Pre-processing operators upstream of scGNN / GraphSCI
+ *   b2_gene_stats_f32   : per-gene Σx, Σx², #(x>0) over the cells (fp64) — sc.pp.filter_genes counts (filter.py:56-158),
+ *                         FilterGenesTopK / FilterGenes summaries sum | var | cv | rv (filter.py:470-489)
+ *   b2_cell_stats_f32   : per-cell Σx, #(x>0) — sc.pp.filter_cells counts
+ *   b2_subset_f32       : out[i, j] = X[rows[i], cols[j]] (NULL = identity) — AnnData._inplace_subset_var / filter_by_mask
+ *   b2_cellwise_mask_u8 : CellwiseMaskData.__call__ (mask.py:153-291): per cell with more than min_gene_counts stored non-zeros,
+ *                         floor(n_pos·mask_rate) entries are drawn WITHOUT replacement with probability ∝ exp(−x/20) ("exp") or
+ *                         uniformly; with add_test_mask max(1, round(0.1·n)) of them become validation entries, the rest test.
+ *                         The draw is counter-based (hash of seed, cell, gene): same distribution as numpy's rng.choice, not the
+ *                         same stream.  Masks are [n, g] bytes.
+ * ---------------------------------------------------------------------- */
+int b2_gene_stats_f32(const float* X, int64_t ldx, int64_t n, int32_t g, double* sum, double* sumsq, double* nnz, void* stream);
+int b2_cell_stats_f32(const float* X, int64_t ldx, int64_t n, int32_t g, double* sum, double* nnz, void* stream);
+int b2_subset_f32(const float* X, int64_t ldx, const int64_t* rows, const int32_t* cols, int64_t n_out, int32_t g_out,
+                  float* out, int64_t ldo, void* stream);
+int b2_cellwise_mask_u8(const float* X, int64_t ldx, int64_t n, int32_t g, float mask_rate, int32_t min_gene_counts,
+                        int distr_exp, int add_test_mask, uint32_t seed, uint8_t* train, uint8_t* valid, uint8_t* test,
+                        int32_t* overflow_rows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

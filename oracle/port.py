@@ -612,3 +612,41 @@ def synthetic_expression(n: int, g: int, density: float = 0.10, n_types: int = 1
     if log_normalize:
         out = log1p(normalize_total(out, target_sum=1e4))
     return out
+
+
+# ----------------------------------------------------------------------------- f1: filters upstream of scGNN / GraphSCI
+def scanpy_filter(x: np.ndarray, target: str, min_counts=None, min_other=None, max_counts=None, max_other=None):
+    """``scanpy.pp.filter_genes`` / ``filter_cells`` (scanpy 1.10.1 `_simple.py`, un-vendored; published algorithm):
+    number = X.sum(axis) for the *_counts criteria, (X > 0).sum(axis) for the *_cells / *_genes criteria; subset = number >= min
+    or number <= max; exactly one criterion per call.  Called by the reference at dance/transforms/filter.py:121.  Unpinned
+    (scanpy absent; the reference's own tests compare with scanpy itself, tests/transforms/test_filter_cell_gene.py)."""
+    if sum(o is not None for o in (min_counts, min_other, max_counts, max_other)) != 1:
+        raise ValueError("Only provide one of the optional parameters per call.")
+    axis = 0 if target == "genes" else 1
+    use_counts = min_counts is not None or max_counts is not None
+    number = x.sum(axis) if use_counts else (x > 0).sum(axis)
+    lo = min_counts if min_counts is not None else min_other
+    hi = max_counts if max_counts is not None else max_other
+    return (number >= lo) if lo is not None else (number <= hi), number
+
+
+def gene_summary(x: np.ndarray, mode: str) -> np.ndarray:
+    """FilterGenes summary statistic, dance/transforms/filter.py:480-489 (dense branch)."""
+    if mode == "sum":
+        return np.array(x.sum(0)).ravel()
+    if mode == "var":
+        return np.array((x**2).mean(0) - np.square(x.mean(0))).ravel()
+    if mode == "cv":
+        return np.nan_to_num(np.array(x.std(0) / x.mean(0)), posinf=0, neginf=0).ravel()
+    if mode == "rv":
+        return np.nan_to_num(np.array(x.var(0) / x.mean(0)), posinf=0, neginf=0).ravel()
+    raise ValueError(mode)
+
+
+def topk_gene_mask(summary: np.ndarray, num_genes: int, top: bool = True) -> np.ndarray:
+    """FilterGenesTopK._get_preserve_mask, dance/transforms/filter.py:653-664."""
+    num_genes = min(num_genes, summary.size)
+    order = summary.argsort()
+    mask = np.zeros(summary.size, dtype=bool)
+    mask[order[-num_genes:] if top else order[:num_genes]] = True
+    return mask
