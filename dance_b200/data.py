@@ -25,6 +25,11 @@ class AnnDataLite:
         n, g = X.shape
         self.obs = obs if obs is not None else {}
         self.var = var if var is not None else {}
+        # like AnnData: positional string names are fixed at construction and survive subsetting
+        if isinstance(self.obs, dict) and "names" not in self.obs:
+            self.obs["names"] = np.array([str(i) for i in range(n)])
+        if isinstance(self.var, dict) and "names" not in self.var:
+            self.var["names"] = np.array([str(i) for i in range(g)])
         self.obsm, self.varm = dict(obsm or {}), dict(varm or {})
         self.obsp, self.varp = dict(obsp or {}), dict(varp or {})
         self.layers, self.uns = _LazyHostDict(layers or {}), dict(uns or {})

@@ -167,12 +167,20 @@ class ScDeepSort:
         unsure = pred_prob.max(1) < unsure_rate / self.num_labels
         return (pred, unsure) if return_unsure else pred
 
-    def score(self, graph: GraphLite, y, **kw) -> float:
-        """Default metric 'acc' of BaseClassificationMethod (modules/base.py:156-168): one-hot y, argmax match."""
+    @staticmethod
+    def preprocessing_pipeline(n_components: int = 400, log_level="INFO"):
+        """scdeepsort.py:134-140."""
+        from ..transforms import Compose, PCACellFeatureGraph, SetConfig
+        return Compose(PCACellFeatureGraph(n_components=n_components, split_name="train"), SetConfig({"label_channel": "cell_type"}),
+                       log_level=log_level)
+
+    def score(self, graph: GraphLite, y, **kw):
+        """Default metric 'acc' of BaseClassificationMethod (modules/base.py:156-168): one-hot y, argmax match.  Returned as a
+        numpy scalar (the example calls ``score.item()``, examples/.../scdeepsort.py:72)."""
         pred = self.predict(graph)
-        y = np.asarray(y)
+        y = y.cpu().numpy() if isinstance(y, torch.Tensor) else np.asarray(y)
         true = y.argmax(1) if y.ndim == 2 else y
-        return float((pred == true).mean())
+        return np.float64((pred == true).mean())
 
     # ---- the aggregate the reference computes and discards ----------------------------------------
     def neighbour_mean(self, graph: GraphLite, h: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -37,6 +37,11 @@ def _stub(name: str, **attrs) -> types.ModuleType:
 
 
 def _install_stubs():
+    if getattr(sys.modules.get("dance"), "__b2_dropin__", False):
+        # the repo's own drop-in namespace (dance_b200/shims) is NOT the reference: unload it so that the reference files bind to the
+        # inert stubs below and never to product code
+        for k in [k for k in sys.modules if k == "dance" or k.startswith("dance.")]:
+            del sys.modules[k]
     if "dance" in sys.modules and not getattr(sys.modules["dance"], "__b2_stub__", False):
         return  # a real dance is importable: use it
     logger = logging.getLogger("dance-ref-stub")
