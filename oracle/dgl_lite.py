@@ -241,3 +241,30 @@ class DataLoader:
                 blocks.insert(0, b)
                 cur = b.src_nodes
             yield cur, seeds, blocks
+
+
+class TAGConv(torch.nn.Module):
+    """``dgl.nn.TAGConv(in_feats, out_feats, k=2, bias=True, activation=None)`` of dgl 1.1.3 (un-vendored): with
+    norm = in_degree^-1/2 (clamped to ≥ 1), fstack = [h]; k times: h ← norm · Σ_{u→v} (norm_u · h_u · e_w); then
+    Linear(in·(k+1) → out) on the concatenation.  Called by the reference at sctag.py:101-102, 173-174.  Restatement — unpinned."""
+
+    def __init__(self, in_feats, out_feats, k=2, bias=True, activation=None):
+        super().__init__()
+        self.k, self.activation = k, activation
+        self.lin = torch.nn.Linear(in_feats * (k + 1), out_feats, bias=bias)
+        torch.nn.init.xavier_normal_(self.lin.weight, gain=torch.nn.init.calculate_gain("relu"))
+        if bias:
+            torch.nn.init.zeros_(self.lin.bias)
+
+    def forward(self, g, feat, edge_weight=None):
+        src, dst = g.edges()
+        n = g.num_nodes()
+        norm = torch.bincount(dst, minlength=n).float().clamp(min=1).pow(-0.5).unsqueeze(1)
+        fstack = [feat]
+        for _ in range(self.k):
+            h = fstack[-1] * norm
+            m = h[src] if edge_weight is None else h[src] * edge_weight.reshape(-1, 1)
+            h = torch.zeros(n, feat.shape[1], dtype=feat.dtype).index_add(0, dst, m) * norm
+            fstack.append(h)
+        out = self.lin(torch.cat(fstack, dim=-1))
+        return self.activation(out) if self.activation is not None else out
