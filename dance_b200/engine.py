@@ -338,6 +338,12 @@ class GATEngine:
                  precision: Optional[str] = None, seed: Optional[int] = None):
         self.device, self.lr, self.precision, self.nh = torch.device(device), lr, precision, heads
         self.layers = [dict(fin=dim, F=hid, concat=True, act="elu"), dict(fin=hid * heads, F=embedding_size, concat=False, act=None)]
+        for L in self.layers:
+            if L["fin"] == L["F"]:
+                # GATLayer adds the RAW input to every head when FIN == FOUT and leaves skip_proj unused / untrained
+                # (scgnn2.py:1163-1171); this engine always evaluates the packed projection+skip GEMM
+                raise NotImplementedError(f"GAT layer with equal input and per-head output width ({L['fin']}) uses an identity skip "
+                                          "connection in the reference; that branch is not built — choose gat_hid_embed != input width")
         shapes = []
         for l, L in enumerate(self.layers):
             W = heads * L["F"]

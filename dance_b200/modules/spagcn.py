@@ -94,6 +94,20 @@ def refine(sample_id, pred, dis, shape: str = "hexagon"):
     return labels[out.cpu().numpy()].tolist()
 
 
+def _fingerprint(a) -> tuple:
+    """Cheap content key of an array (shape + a strided sample + two moments): detects in-place mutation between calls without a
+    full pass over an N×N matrix."""
+    t = a if isinstance(a, torch.Tensor) else np.asarray(a)
+    flat = t.reshape(-1)
+    n = flat.shape[0]
+    step = max(1, n // 4096)
+    sample = flat[::step][:4096]
+    if isinstance(sample, torch.Tensor):
+        sample = sample.detach().double().cpu().numpy()
+    sample = np.asarray(sample, dtype=np.float64)
+    return (tuple(t.shape), float(sample.sum()), float((sample * sample).sum()), float(sample[-1]) if len(sample) else 0.0)
+
+
 class SimpleGCDEC:
     """One graph convolution + DEC clustering head; explicit forward/backward on the C-ABI kernels."""
 
@@ -144,7 +158,7 @@ class SimpleGCDEC:
     # ---- graph binding ----------------------------------------------------------------------
     def bind(self, X, adj):
         """Upload ``X`` [N, nfeat] and the dense ``adj`` [N, N] and form ``AX = adj · X`` once."""
-        key = (id(X), id(adj))
+        key = (id(X), id(adj), _fingerprint(X), _fingerprint(adj))   # identity AND content: an in-place edit of X / adj re-binds
         if self._bound is not None and self._bound[0] == key:
             return
         Xd, Ad = _dev(X, self.device), _dev(adj, self.device)

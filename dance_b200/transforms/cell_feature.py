@@ -37,7 +37,17 @@ class CellPCA(BaseTransform):
         if self.n_components > min(feat.shape):
             self.logger.warning(f"n_components={self.n_components} must be between 0 and min(n_samples, n_features)={min(feat.shape)}")
             self.n_components = min(feat.shape)
-        res = ops.pca(_to_cuda(feat), int(self.n_components))
+        fitted = data.data.uns.get("pca") if hasattr(data.data, "uns") else None
+        if fitted is not None:
+            # a pre-fitted decomposition in uns["pca"] is applied, not re-fitted (reference cell_feature.py:176-178: pca.transform):
+            # any object / mapping with `mean_` and `components_` (sklearn's PCA attributes) is accepted
+            get = (lambda k: fitted[k]) if isinstance(fitted, dict) else (lambda k: getattr(fitted, k))
+            mean = torch.as_tensor(np.asarray(get("mean_"), dtype=np.float32)).cuda()
+            comp = torch.as_tensor(np.ascontiguousarray(get("components_"), dtype=np.float32)).cuda()
+            centred = (_to_cuda(feat) - mean).contiguous()
+            data.data.obsm[self.out] = ops.gemm(centred, comp, transB=True).cpu().numpy()
+            return data
+        res = ops.pca(_to_cuda(feat), _resolve_components(self.n_components, feat, self.logger))
         data.data.obsm[self.out] = res["scores"].cpu().numpy()
         if self.save_info:
             ev = res["explained_variance"].cpu().numpy()
@@ -47,6 +57,23 @@ class CellPCA(BaseTransform):
             data.data.uns["pca_explained_variance"] = ev
             data.data.uns["pca_explained_variance_ratio"] = ev / total_var
         return data
+
+
+def _resolve_components(n_components, feat, logger) -> int:
+    """sklearn's ``PCA(n_components)`` rule: an int is the number of components; a float in (0, 1) the smallest number of
+    components whose cumulative explained-variance ratio exceeds it (full decomposition, then truncated)."""
+    if isinstance(n_components, (int, np.integer)) or float(n_components) >= 1:
+        return int(n_components)
+    frac = float(n_components)
+    if not 0.0 < frac < 1.0:
+        raise ValueError(f"n_components={n_components!r} must be a positive int or a float in (0, 1)")
+    kmax = min(feat.shape)
+    res = ops.pca(_to_cuda(feat), kmax)
+    ev = res["explained_variance"].double().cpu().numpy()
+    total = float(np.var(np.asarray(feat, dtype=np.float64), axis=0, ddof=1).sum())
+    k = int(np.searchsorted(np.cumsum(ev) / total, frac, side="right") + 1)
+    logger.info(f"n_components={frac} → {k} components")
+    return min(k, kmax)
 
 
 class WeightedFeaturePCA(BaseTransform):
@@ -66,7 +93,7 @@ class WeightedFeaturePCA(BaseTransform):
         if self.n_components > min(feat.shape):
             self.logger.warning(f"n_components={self.n_components} must be between 0 and min(n_samples, n_features)={min(feat.shape)}")
             self.n_components = min(feat.shape)
-        k = int(self.n_components)
+        k = _resolve_components(self.n_components, np.asarray(feat).T, self.logger)
         # genes × cells: genes are the PCA samples (cell_feature.py:61)
         Xt = _to_cuda(np.asarray(feat).T) if feat_dev is None else feat_dev.t().contiguous()
         res = ops.pca(Xt, k)
