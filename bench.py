@@ -261,6 +261,8 @@ def main():
     ap.add_argument("--cpu-cells", type=int, default=16384, help="bounded CPU sample (cells) for cpu_baseline / --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--comm", type=str, default="torch", choices=["torch", "native"],
+                    help="collectives of the data path under N > 1: torch.distributed (NCCL) or the C-ABI's own NCCL communicator (b2_comm_*)")
     ap.add_argument("--no-checks", action="store_true", help="skip the fp64 spot checks and the 16-bit aggregate side measurement")
     ap.add_argument("--cuda-profiler", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -298,9 +300,13 @@ def main():
     fae = FeatureAEEngine(G, device=dev, lr=1e-3, precision=args.precision, seed=0)
     gae = GraphAEEngine(128, EMB, device=dev, lr=1e-2, precision=args.precision, seed=1)
     n_steps = None
+    dcomm = comm                                   # communicator of the data path (gradient all-reduce, operand all-gathers)
+    if comm.enabled and args.comm == "native":
+        from dance_b200.parallel import NativeComm
+        dcomm = NativeComm(rank, world)
     if comm.enabled:
-        fae.grad_hook = comm.allreduce_sum_
-        gae.set_sharding(comm, bounds)
+        fae.grad_hook = dcomm.allreduce_sum_
+        gae.set_sharding(dcomm, bounds)
         n_steps = epoch_steps(bounds, BATCH)       # every rank issues the same number of gradient all-reduces per epoch
     z_all = torch.empty(n_loc, 128, dtype=torch.float32, device=dev)
     fae.train_epoch(X, BATCH, "LTMG", 0.9, None, z_all, None, n_steps=n_steps)   # also serves as the first warm-up epoch
@@ -558,6 +564,7 @@ def main():
         "data": "synthetic",
         "config": workload_config(args),
         "implementation": {"decoder_loss": "exact-fused-blockwise (matrix-free, no N×N tensors)", "gemm_precision": args.precision,
+                           "collectives": ("C-ABI NCCL communicator (b2_comm_*)" if args.comm == "native" else "torch.distributed NCCL") if world > 1 else None,
                            "parallelism": f"cells sharded ×{world}", "nnz": nnz_total, "data_fingerprint_rank0": fp},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches // args.steps, "checks": checks,
         "roofline": roofline, "roofline_spmm": roof_spmm, "roofline_spmm_bf16": spmm16, "roofline_gemm": roof_gemm,

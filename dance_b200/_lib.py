@@ -26,6 +26,15 @@ _SIGNATURES = {
     "b2_spmm_csr_bf16": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32, C.c_int, C.c_int, c_vp, c_vp]),
     "b2_spmm_csr_f16": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32, C.c_int, C.c_int, c_vp, c_vp]),
     "b2_convert_f32_to_x16": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, C.c_int, c_vp]),
+    "b2_comm_available": (C.c_int, []),
+    "b2_comm_version": (C.c_int, []),
+    "b2_comm_unique_id": (C.c_int, [c_vp]),
+    "b2_comm_init_rank": (C.c_int, [C.POINTER(c_vp), c_vp, C.c_int, C.c_int]),
+    "b2_comm_destroy": (C.c_int, [c_vp]),
+    "b2_comm_world": (C.c_int, [c_vp]),
+    "b2_comm_rank": (C.c_int, [c_vp]),
+    "b2_allreduce_sum_f32": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "b2_allgather_f32": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "b2_gene_stats_f32": (C.c_int, [c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "b2_cell_stats_f32": (C.c_int, [c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp]),
     "b2_subset_f32": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp]),

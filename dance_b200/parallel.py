@@ -129,3 +129,83 @@ class Comm:
     def barrier(self):
         if self.enabled:
             dist.barrier(group=self.group)
+
+
+class NativeComm:
+    """The same collectives through the C-ABI's own NCCL communicator (``b2_comm_*``, csrc/comm.cu) — what a non-Python binder
+    uses.  Drop-in for :class:`Comm` in the engines: ``allreduce_sum_`` / ``all_gather_rows`` / ``allreduce_max_`` / ``barrier``.
+    The 128-byte NCCL id is created on rank 0 and handed to the other ranks through ``exchange`` (any callable that broadcasts
+    bytes from rank 0; by default the torch.distributed process group that torchrun already set up — only for this bootstrap)."""
+
+    def __init__(self, rank: int, world: int, exchange=None):
+        import ctypes as C
+        from . import ops
+        self._ops, self._C = ops, C
+        self.rank, self.world, self.enabled = rank, world, world > 1
+        self._handle = C.c_void_p()
+        lib = ops.lib()
+        if not lib.b2_comm_available():
+            raise RuntimeError("NativeComm: libnccl.so.2 could not be loaded")
+        buf = (C.c_char * 128)()
+        if rank == 0:
+            ops.check(lib.b2_comm_unique_id(buf), "b2_comm_unique_id")
+        raw = bytes(buf)
+        if world > 1:
+            if exchange is None:
+                def exchange(b):
+                    t = torch.frombuffer(bytearray(b), dtype=torch.uint8).clone()
+                    if dist.get_backend() == "nccl":
+                        t = t.cuda()
+                    dist.broadcast(t, src=0)
+                    return bytes(t.cpu().numpy().tobytes())
+            raw = exchange(raw)
+        idbuf = (C.c_char * 128).from_buffer_copy(raw)
+        ops.check(lib.b2_comm_init_rank(C.byref(self._handle), idbuf, world, rank), "b2_comm_init_rank")
+
+    def close(self):
+        if self._handle:
+            self._ops.lib().b2_comm_destroy(self._handle)
+            self._handle = self._C.c_void_p()
+
+    def allreduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
+        if self.enabled:
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("NativeComm.allreduce_sum_: contiguous float32 tensor required")
+            self._ops.check(self._ops.lib().b2_allreduce_sum_f32(self._handle, t.data_ptr(), t.numel(), self._ops._stream()), "b2_allreduce_sum_f32")
+        return t
+
+    def allreduce_max_(self, t: torch.Tensor) -> torch.Tensor:
+        """max over ranks of a small non-negative vector, via gather + local max (timing bookkeeping only)."""
+        if self.enabled:
+            full = torch.empty(self.world * t.numel(), dtype=torch.float32, device=t.device)
+            self._ops.check(self._ops.lib().b2_allgather_f32(self._handle, t.contiguous().data_ptr(), full.data_ptr(), t.numel(),
+                                                             self._ops._stream()), "b2_allgather_f32")
+            t.copy_(full.view(self.world, -1).max(0).values.view_as(t))
+        return t
+
+    def all_gather_rows(self, local: torch.Tensor, bounds, out: Optional[torch.Tensor] = None):
+        if not self.enabled:
+            return local
+        n_total, F = bounds[-1][1], local.shape[1]
+        if out is None:
+            out = torch.empty((n_total, F), dtype=local.dtype, device=local.device)
+        sizes = [b - a for a, b in bounds]
+        mx = max(sizes)
+        lib = self._ops.lib()
+        if len(set(sizes)) == 1:
+            self._ops.check(lib.b2_allgather_f32(self._handle, local.contiguous().data_ptr(), out.data_ptr(), mx * F, self._ops._stream()),
+                            "b2_allgather_f32")
+            return out
+        pad = torch.zeros((mx, F), dtype=local.dtype, device=local.device)
+        pad[:local.shape[0]] = local
+        buf = torch.empty((self.world * mx, F), dtype=local.dtype, device=local.device)
+        self._ops.check(lib.b2_allgather_f32(self._handle, pad.data_ptr(), buf.data_ptr(), mx * F, self._ops._stream()), "b2_allgather_f32")
+        for r, (a, b) in enumerate(bounds):
+            out[a:b] = buf[r * mx:r * mx + (b - a)]
+        return out
+
+    def barrier(self):
+        if self.enabled:
+            t = torch.zeros(1, dtype=torch.float32, device="cuda")
+            self.allreduce_sum_(t)
+            torch.cuda.current_stream().synchronize()

@@ -500,6 +500,26 @@ int b2_louvain_csr_host(const int64_t* rowptr, const int32_t* colidx, const doub
                         int32_t* n_comm_out, double* modularity_out, int max_levels, double min_gain);
 
 /* ------------------------------------------------------------------------
+ * Cell-sharded data parallelism inside the C-ABI: NCCL over NVLink, resolved with dlopen at run time
+ * (b2_comm_available() == 0 when libnccl.so.2 cannot be loaded).  One communicator per process / GPU:
+ *   rank 0: b2_comm_unique_id(id) → ship the 128 bytes to the other ranks by any channel → every rank: b2_comm_init_rank
+ *   b2_allreduce_sum_f32 : in-place sum of a flat fp32 buffer — the gradient bucket of the Feature-AE / Graph-AE engines (the
+ *                          only collective of the sample-parallel paths), the partial dz of b2_gae_loss_grad_sym_f32, the loss
+ *   b2_allgather_f32     : equal-sized row blocks → full operand (the N×32 support of the row-sharded aggregate, z of the decoder)
+ * Collectives are enqueued on `stream`; replaces torch.distributed in dance_b200/parallel.py for non-Python binders.
+ * ---------------------------------------------------------------------- */
+typedef struct b2_comm b2_comm;
+int b2_comm_available(void);
+int b2_comm_version(void);
+int b2_comm_unique_id(void* id128 /* 128 bytes */);
+int b2_comm_init_rank(b2_comm** out, const void* id128, int world, int rank);
+int b2_comm_destroy(b2_comm* comm);
+int b2_comm_world(const b2_comm* comm);
+int b2_comm_rank(const b2_comm* comm);
+int b2_allreduce_sum_f32(b2_comm* comm, float* buf, int64_t n, void* stream);
+int b2_allgather_f32(b2_comm* comm, const float* local, float* full, int64_t count, void* stream);
+
+/* ------------------------------------------------------------------------
  * Pre-processing operators upstream of scGNN / GraphSCI
  *   b2_gene_stats_f32   : per-gene Σx, Σx², #(x>0) over the cells (fp64) — sc.pp.filter_genes counts (filter.py:56-158),
  *                         FilterGenesTopK / FilterGenes summaries sum | var | cv | rv (filter.py:470-489)
