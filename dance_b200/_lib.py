@@ -41,7 +41,7 @@ _SIGNATURES = {
     "b2_cellwise_mask_u8": (C.c_int, [c_vp, c_i64, c_i64, c_i32, c_f32, c_i32, C.c_int, C.c_int, C.c_uint32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b2_kmeans_workspace_bytes": (c_sz, [c_i32, c_i32]),
     "b2_kmeans_step_f32": (C.c_int, [c_vp, c_i64, c_i32, c_i32, c_vp, c_i32, c_vp, C.c_int, c_vp, c_vp, c_sz, c_vp]),
-    "b2_graph_regu_weights_f32": (C.c_int, [c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    "b2_graph_regu_weights_f32": (C.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "b2_celltype_loss_grad_f32": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, C.c_int, c_vp, c_vp, c_vp, c_vp]),
     "b2_l1_grad_add_f32": (C.c_int, [c_vp, c_vp, c_i64, c_f32, c_vp, c_vp]),
     "b2_louvain_csr_host": (C.c_int, [c_vp, c_vp, c_vp, c_i32, c_vp, C.POINTER(c_i32), C.POINTER(C.c_double), C.c_int, C.c_double]),
@@ -149,6 +149,15 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _lib = handle
+        # A/B selector of the decoder kernel for a whole process (read once at load; tests switch paths with ops.set_path):
+        #   B2_FORCE_GAE_PATH = cuda | tf32 | f16 | sym
+        import os
+        forced = os.environ.get("B2_FORCE_GAE_PATH")
+        if forced:
+            modes = {"auto": 0, "cuda": 1, "tf32": 2, "f16": 3, "sym": 4}
+            if forced not in modes:
+                raise B2Error(f"B2_FORCE_GAE_PATH={forced!r}: expected one of {sorted(modes)}")
+            handle.b2_set_path(0, modes[forced])
     return _lib
 
 

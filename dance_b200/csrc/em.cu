@@ -1,8 +1,8 @@
 // scGNN EM-iteration stages: the pieces between two Feature-AE / Graph-AE rounds.
 //   * KMeans on the graph embedding (Lloyd iterations; the reference calls sklearn KMeans, scgnn2.py:186)
-//   * the cell-type / graph regulariser of the Cluster-AE in SPARSE form — the reference builds two dense N×N matrices
-//     (normalize_cell_cell_matrix of the adjacency and of the same-cluster indicator, scgnn2.py:716-752) only to take
-//     `(M @ mse).sum()` (scgnn2.py:1323-1326), which equals Σ_j colsum_j(M)·mse_j: per-cell weights, no N×N storage
+//   * the cell-type / graph regulariser of the Cluster-AE WITHOUT the reference's two dense N×N matrices
+//     (normalize_cell_cell_matrix of the adjacency and of the same-cluster indicator, scgnn2.py:716-752): the loss only takes
+//     `(M @ mse).sum()` (scgnn2.py:1323-1326) = Σ_j colsum_j(M)·mse_j, i.e. per-cell weights
 //   * loss_function_graph(regularizer_type="Celltype") value + gradient (scgnn2.py:1316-1326) and the L1 term of
 //     train_handler (scgnn2.py:1268-1274)
 //   * Louvain community detection on the symmetric kNN graph (host C++, CSR in / labels out; the reference goes through
@@ -66,27 +66,31 @@ __global__ void kmeans_update_kernel(float* __restrict__ C, const double* __rest
 
 __global__ void kmeans_changed_kernel(const int32_t* changed, double* stats) { stats[2] = (double)changed[0]; }
 
-// ---- sparse cell-type / graph regulariser weights ------------------------------------------------------------------------
-// pattern = A + I (CSR of the normalised adjacency).  adjnorm = row-normalised 0/1 adjacency without the diagonal
-// (normalize_cell_cell_matrix, scgnn2.py:726-730); the Cluster-AE of cluster c uses adjnorm[c][:, c] and takes
-// (adjnorm_cc @ mse).sum() = Σ_j w_j·mse_j with  w_j = Σ_{i ∈ N(j), label_i = label_j} 1/deg_i   (pattern symmetric).
+// ---- cell-type / graph regulariser weights -----------------------------------------------------------------------------------
+// graph_celltype_regu_handler (scgnn2.py:716-730) calls normalize_cell_cell_matrix on `sp.csr_matrix.todense(adj)`, i.e. on an
+// np.matrix, for which `avg_mtx * x` is a MATRIX product: adjdense[i, j] = Σ_k (1/deg_i)·adj[k, j] = deg_j / deg_i — a dense
+// rank-one matrix, whatever the edges are (App. B-style quirk; it defines parity).  The Cluster-AE of cluster c takes
+// (adjdense[c][:, c] @ mse).sum() = Σ_{j∈c} w_j·mse_j  with  w_j = deg_j · Σ_{i∈c} 1/deg_i.  Two passes over the degrees, no N×N.
+// pattern = A + I (CSR of the normalised adjacency) or A: deg = row length without the diagonal entry.
+__device__ __forceinline__ int32_t plain_degree(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int64_t i) {
+  int32_t deg = rowptr[i + 1] - rowptr[i];
+  for (int32_t q = rowptr[i]; q < rowptr[i + 1]; ++q) deg -= (colidx[q] == (int32_t)i) ? 1 : 0;
+  return deg;
+}
+__global__ void __launch_bounds__(256)
+cluster_inv_degree_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const int32_t* __restrict__ labels,
+                          int32_t n, int32_t n_clusters, double* __restrict__ sums) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t deg = plain_degree(rowptr, colidx, i), c = labels[i];
+    if (deg > 0 && c >= 0 && c < n_clusters) atomicAdd(sums + c, 1.0 / (double)deg);
+  }
+}
 __global__ void __launch_bounds__(256)
 graph_regu_weights_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const int32_t* __restrict__ labels,
-                          int32_t n, float* __restrict__ w) {
+                          int32_t n, int32_t n_clusters, const double* __restrict__ sums, float* __restrict__ w) {
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
-    const int lj = labels[j];
-    double s = 0.0;
-    for (int32_t e = rowptr[j]; e < rowptr[j + 1]; ++e) {
-      const int32_t i = colidx[e];
-      if (i == j || labels[i] != lj) continue;
-      int32_t deg = rowptr[i + 1] - rowptr[i];
-      // the pattern holds the diagonal: degree of the plain adjacency = row length − 1 (binary search-free: count it)
-      bool has_diag = false;
-      for (int32_t q = rowptr[i]; q < rowptr[i + 1]; ++q) has_diag |= (colidx[q] == i);
-      deg -= has_diag ? 1 : 0;
-      if (deg > 0) s += 1.0 / (double)deg;
-    }
-    w[j] = (float)s;
+    const int32_t c = labels[j];
+    w[j] = (c >= 0 && c < n_clusters) ? (float)((double)plain_degree(rowptr, colidx, j) * sums[c]) : 0.f;
   }
 }
 
@@ -191,12 +195,16 @@ extern "C" int b2_kmeans_step_f32(const float* X, int64_t ldx, int32_t n, int32_
   return B2_OK;
 }
 
-extern "C" int b2_graph_regu_weights_f32(const int32_t* rowptr, const int32_t* colidx, const int32_t* labels, int32_t n, float* w,
-                                         void* stream) {
+extern "C" int b2_graph_regu_weights_f32(const int32_t* rowptr, const int32_t* colidx, const int32_t* labels, int32_t n, int32_t n_clusters,
+                                         double* cluster_sums, float* w, void* stream) {
   using namespace b2;
-  B2_REQUIRE(rowptr && colidx && labels && w, "b2_graph_regu_weights_f32: null pointer");
+  B2_REQUIRE(rowptr && colidx && labels && w && cluster_sums && n_clusters > 0, "b2_graph_regu_weights_f32: bad arguments");
   if (n <= 0) return B2_OK;
-  graph_regu_weights_kernel<<<grid_for(n, 1), 256, 0, as_stream(stream)>>>(rowptr, colidx, labels, n, w);
+  cudaStream_t st = as_stream(stream);
+  B2_CHECK_CUDA(cudaMemsetAsync(cluster_sums, 0, sizeof(double) * (size_t)n_clusters, st));
+  cluster_inv_degree_kernel<<<grid_for(n, 1), 256, 0, st>>>(rowptr, colidx, labels, n, n_clusters, cluster_sums);
+  B2_CHECK_LAUNCH("cluster_inv_degree_kernel");
+  graph_regu_weights_kernel<<<grid_for(n, 1), 256, 0, st>>>(rowptr, colidx, labels, n, n_clusters, cluster_sums, w);
   B2_CHECK_LAUNCH("graph_regu_weights_kernel");
   return B2_OK;
 }

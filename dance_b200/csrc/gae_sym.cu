@@ -214,7 +214,7 @@ gae_sym_kernel(const __grid_constant__ Params p) {
   const uint32_t tmem = *tmem_slot;
 
   if (warp < 4) {
-    setmaxnreg_dec<56>();
+    setmaxnreg_dec<48>();   // the register pool is the CTA's LAUNCH allocation (80 x 768): 128x48 + 512x96 + 128x48 = 61440 exactly
     if (warp == 0 && lane == 0) {
       // ===================== TMA producer =====================
       const int blocks_owned = sw.I1 >= 0 ? 2 : 1;
@@ -254,27 +254,31 @@ gae_sym_kernel(const __grid_constant__ Params p) {
       auto next_tile = [&](int& s, int& g) {              // advance to the next active tile (s == n_steps: end)
         do { if (++g == 2) { g = 0; ++s; } } while (s < sw.n_steps && !sw.active(g, s));
       };
-      auto issue_s = [&](int s, int g) {
+      // g = which owned block the tile belongs to (operands, dZ_I accumulator); q = parity of the tile in the CTA's tile sequence =
+      // elementwise group / S buffer / G buffer.  Alternating by SEQUENCE (not by block) guarantees that consecutive tiles never
+      // share a group: with two tiles of one group in a row the S-two-ahead order would deadlock (S(t+2) needs the group to have
+      // read S(t+1), which waits for G's buffer, which waits for D(t) — queued behind S(t+2)).
+      auto issue_s = [&](int s, int g, int q) {
         const int stage = s % STAGES;
-        mbar_wait(s_empty + 8 * g, ((cnt_s >> g) & 1u) ^ 1u);
+        mbar_wait(s_empty + 8 * q, ((cnt_s >> q) & 1u) ^ 1u);
         mbar_wait(full_bar + 8 * stage, (s / STAGES) & 1);
         tc_fence_after();
         const uint32_t st = s_ring + stage * STAGE_BYTES, zi = s_zi + g * ZI_BYTES;
-        const uint32_t d_s = tmem + TM_S + (uint32_t)(g * BT);
+        const uint32_t d_s = tmem + TM_S + (uint32_t)(q * BT);
         // SWIZZLE_32B K-major: 32-byte rows (the whole K = 16), 8-row groups 256 B apart — one k-step
         const uint64_t a_hi = umma_desc(zi, 16, 256, 6), a_lo = umma_desc(zi + ZA_BYTES, 16, 256, 6);
         const uint64_t b_hi = umma_desc(st, 16, 256, 6), b_lo = umma_desc(st + ZA_BYTES, 16, 256, 6);
         umma_f16(d_s, a_lo, b_hi, idesc_s, 0);
         umma_f16(d_s, a_hi, b_lo, idesc_s, 1);
         umma_f16(d_s, a_hi, b_hi, idesc_s, 1);
-        umma_commit(s_full + 8 * g);
-        cnt_s ^= 1u << g;
+        umma_commit(s_full + 8 * q);
+        cnt_s ^= 1u << q;
       };
-      auto issue_d = [&](int s, int g) {
+      auto issue_d = [&](int s, int g, int q) {
         const int stage = s % STAGES;
-        mbar_wait(g_full + 8 * g, (cnt_d >> g) & 1u);
+        mbar_wait(g_full + 8 * q, (cnt_d >> q) & 1u);
         tc_fence_after();
-        const uint32_t g_hi = s_g + g * G_BYTES, g_lo = g_hi + G_PLANE;
+        const uint32_t g_hi = s_g + q * G_BYTES, g_lo = g_hi + G_PLANE;
         const uint32_t zt_j = s_ring + stage * STAGE_BYTES + 2 * ZA_BYTES;
         const uint32_t d1 = tmem + TM_D1 + (uint32_t)(g * 2 * DW);
 #pragma unroll
@@ -304,21 +308,22 @@ gae_sym_kernel(const __grid_constant__ Params p) {
             umma_f16(d2, umma_desc(g_lo + (uint32_t)ks * 2048u, BT * 128, 1024, 2), b, idesc_d2, 1);
           }
         }
-        umma_commit(g_empty + 8 * g);
-        cnt_d ^= 1u << g;
+        umma_commit(g_empty + 8 * q);
+        cnt_d ^= 1u << q;
         if (sw.last_of_step(g, s)) {
           umma_commit(stage_free + 8 * stage);
           if (sw.has_d2(s)) { umma_commit(d2_full + 8 * (s % 3)); use_d2 ^= 1u << (s % 3); }
         }
       };
       // S runs two tiles ahead of the D products (the tensor pipe executes in order; see gae_tch.cu)
-      int ss = 0, sg = -1, ds = 0, dg = -1;
+      int ss = 0, sg = -1, sk = 0, ds = 0, dg = -1, dk = 0;     // (step, block, sequence index) of the next S / D tile
       next_tile(ss, sg);
       next_tile(ds, dg);
-      for (int pre = 0; pre < 2 && ss < sw.n_steps; ++pre) { issue_s(ss, sg); next_tile(ss, sg); }
+      for (int pre = 0; pre < 2 && ss < sw.n_steps; ++pre) { issue_s(ss, sg, sk & 1); ++sk; next_tile(ss, sg); }
       while (ds < sw.n_steps) {
-        if (ss < sw.n_steps) { issue_s(ss, sg); next_tile(ss, sg); }
-        issue_d(ds, dg);
+        if (ss < sw.n_steps) { issue_s(ss, sg, sk & 1); ++sk; next_tile(ss, sg); }
+        issue_d(ds, dg, dk & 1);
+        ++dk;
         next_tile(ds, dg);
       }
       umma_commit(d1_full);
@@ -329,40 +334,44 @@ gae_sym_kernel(const __grid_constant__ Params p) {
     setmaxnreg_inc<96>();
     const int sub = warp & 3;                     // TMEM lane quarter
     const int part = (warp - 4) >> 2;             // 0..3
-    const int g = part >> 1;                      // group = owned block index (tiles of I_g)
+    const int q = part >> 1;                      // elementwise group = parity of the tile in the CTA's tile sequence
     const int half = part & 1;                    // 64-column half of the tile
     const int row = sub * 32 + lane;              // row inside the tile
     const uint32_t lane_off = (uint32_t)(sub * 32) << 16;
-    const int I = sw.block(g);
     constexpr float LN2 = 0.6931471805599453f;
     float abs_w = 0.f, lg_w = 0.f;
     int chunks_w = 0;                             // 16-logit chunks processed, weighted like the sums
-    if (g == 1) { const long long t0 = clock64(); while (clock64() - t0 < STAGGER_CYCLES) { } }
-    int ng = 0;
-    const uint32_t g_hi = s_g + g * G_BYTES + (uint32_t)half * (BT * 128) + (uint32_t)row * 128u, g_lo = g_hi + G_PLANE;
+    if (q == 1) { const long long t0 = clock64(); while (clock64() - t0 < STAGGER_CYCLES) { } }
+    int ng = 0;                                   // tiles this group has processed (phase of its S / G buffers)
+    const uint32_t g_hi = s_g + q * G_BYTES + (uint32_t)half * (BT * 128) + (uint32_t)row * 128u, g_lo = g_hi + G_PLANE;
     const uint32_t xr = (uint32_t)(row & 7);
-    if (I >= 0) {
+    {
+      int seq = -1;                               // index of the tile in the CTA's tile sequence (same enumeration as the MMA issuer)
       for (int s = 0; s < sw.n_steps; ++s) {
+       for (int g = 0; g < 2; ++g) {
         if (!sw.active(g, s)) continue;
+        ++seq;
+        if ((seq & 1) != q) continue;
+        const int I = sw.block(g);
         const int J = sw.J(s);
         const int wgt = sw.diag(g, s) ? 1 : 2;
         const bool masked = ragged && (I == p.nb - 1 || J == p.nb - 1);
         const bool row_ok = !(ragged && I == p.nb - 1 && row >= n_last);
         const int col_end = (ragged && J == p.nb - 1) ? n_last : BT;       // valid columns of this tile
-        mbar_wait(s_full + 8 * g, ng & 1);
+        mbar_wait(s_full + 8 * q, ng & 1);
         tc_fence_after();
-        mbar_wait(g_empty + 8 * g, (ng & 1) ^ 1);                          // D-MMAs of this group's previous tile have read G
+        mbar_wait(g_empty + 8 * q, (ng & 1) ^ 1);                          // the D-MMAs of this group's previous tile have read G
         float abs_t = 0.f, lg_t = 0.f;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           const int cofs = half * 64 + hh * 32;
           uint32_t v0[16], v1[16];
-          tmem_ld_32x32b_x16_nowait(tmem + lane_off + TM_S + (uint32_t)(g * BT + cofs), v0);
-          tmem_ld_32x32b_x16_nowait(tmem + lane_off + TM_S + (uint32_t)(g * BT + cofs + 16), v1);
+          tmem_ld_32x32b_x16_nowait(tmem + lane_off + TM_S + (uint32_t)(q * BT + cofs), v0);
+          tmem_ld_32x32b_x16_nowait(tmem + lane_off + TM_S + (uint32_t)(q * BT + cofs + 16), v1);
           tmem_ld_wait();
           if (hh == 1) {
             tc_fence_before();
-            if (lane == 0) mbar_arrive(s_empty + 8 * g);                   // S[g] is in registers
+            if (lane == 0) mbar_arrive(s_empty + 8 * q);                   // S[q] is in registers
           }
           uint32_t hi0[8], lo0[8], hi1[8], lo1[8];
           auto chunk_math = [&](auto full_tag, const uint32_t (&v)[16], int c0, uint32_t (&hi)[8], uint32_t (&lo)[8]) {
@@ -419,11 +428,12 @@ gae_sym_kernel(const __grid_constant__ Params p) {
         }
         fence_proxy_async();                                               // generic-proxy stores → visible to the tensor core's async proxy
         __syncwarp();
-        if (lane == 0) mbar_arrive(g_full + 8 * g);
+        if (lane == 0) mbar_arrive(g_full + 8 * q);
         abs_w += (float)wgt * abs_t;
         lg_w += (float)wgt * lg_t;
         chunks_w += wgt * 4;
         ++ng;
+       }
       }
     }
     // Σ softplus over this thread's logits (both orientations of off-diagonal tiles) = ln2·[½Σ|v| + Σlog2(1+e)], the ½Σv half is
@@ -431,15 +441,16 @@ gae_sym_kernel(const __grid_constant__ Params p) {
     double loss = (double)LN2 * (0.5 * (double)abs_w + (double)lg_w + 11.0 * 16.0 * (double)chunks_w);
     loss = warp_sum(loss);
     if (lane == 0 && loss != 0.0) atomicAdd(p.loss_acc, loss * (double)p.coef);
-    if (half == 0 && I >= 0) {
+    const int I_epi = sw.block(q);                // the half-0 warps of group q also drain the dZ accumulator of owned block q
+    if (half == 0 && I_epi >= 0) {
       // dZ_I epilogue: [G·Z_hi | G·Z_lo] → global (atomic: other CTAs add their Gᵀ·Z contributions to the same rows)
       mbar_wait(d1_full, 0);
       tc_fence_after();
       uint32_t a0[16], a1[16];
-      tmem_ld_32x32b_x16(tmem + lane_off + TM_D1 + (uint32_t)(g * 2 * DW), a0);
-      tmem_ld_32x32b_x16(tmem + lane_off + TM_D1 + (uint32_t)(g * 2 * DW + DW), a1);
-      const int gr = I * BT + row;
-      if (gr < p.n && ng > 0) {
+      tmem_ld_32x32b_x16(tmem + lane_off + TM_D1 + (uint32_t)(q * 2 * DW), a0);
+      tmem_ld_32x32b_x16(tmem + lane_off + TM_D1 + (uint32_t)(q * 2 * DW + DW), a1);
+      const int gr = I_epi * BT + row;
+      if (gr < p.n) {
         const float c2 = 2.f * p.coef * p.scale[2] * (1.f / G_SCALE);
         float* dst = p.dz + (size_t)gr * p.d;
         float o[16];

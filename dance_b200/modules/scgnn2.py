@@ -16,7 +16,8 @@ Differences that are deliberate and documented in DESIGN.md:
     weight array instead of a Python list of tuples, and ``CCC_graph_hat`` as None above
     ``dense_recon_max_cells`` cells;
   * the EM iterations never form the two dense N×N regulariser matrices of ``graph_celltype_regu_handler``: the Cluster-AE
-    loss only needs their column sums inside each cluster (``ops.graph_regu_weights``); Louvain runs in host C++ on the
+    loss only needs their column sums inside each cluster (``ops.graph_regu_weights`` — including the reference's
+    np.matrix-product quirk that makes the "normalised adjacency" deg_j / deg_i); Louvain runs in host C++ on the
     sparse graph (the reference densifies it for igraph), KMeans as Lloyd iterations on the device seeded by sklearn's
     k-means++ (same ``random_state=0``; above ``kmeans_init_max_cells`` cells on a fixed-seed subsample).
 """
@@ -348,8 +349,10 @@ def clustering_handler(edgeList, args, param):
 
 
 def graph_celltype_regu_handler(adj, cluster_labels, device=None):
-    """scgnn2.py:716-724 in sparse form: instead of the two dense N×N matrices returns what the Cluster-AE loss takes from them,
-    per cell: (w_graph [N] = column sums of the row-normalised adjacency inside the cell's cluster, w_celltype [N] = 1)."""
+    """scgnn2.py:716-724 without the two dense N×N matrices: returns what the Cluster-AE loss takes from them, per cell —
+    (w_graph [N], w_celltype [N]) = their column sums inside the cell's cluster.  The reference's "normalised" adjacency is
+    deg_j / deg_i (it multiplies np.matrix objects, see csrc/em.cu), so w_graph_j = deg_j · Σ_{i∈cluster(j)} 1/deg_i; the
+    same-cluster indicator is a true ndarray, row-normalised elementwise, whose column sums inside the cluster are 1."""
     lab = torch.as_tensor(np.asarray(cluster_labels), dtype=torch.int32)
     if isinstance(adj, ops.CSR):
         A = adj

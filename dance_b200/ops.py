@@ -932,12 +932,17 @@ def kmeans(X: torch.Tensor, centers: torch.Tensor, max_iter: int = 300, tol: flo
     return labels, inertia, it
 
 
-def graph_regu_weights(A: CSR, labels: torch.Tensor) -> torch.Tensor:
-    """Per-cell column sums of the row-normalised adjacency restricted to the cell's own cluster (see b2_graph_regu_weights_f32)."""
+def graph_regu_weights(A: CSR, labels: torch.Tensor, n_clusters: Optional[int] = None) -> torch.Tensor:
+    """Per-cell column sums, inside the cell's own cluster, of the reference's "normalised" adjacency deg_j / deg_i
+    (see b2_graph_regu_weights_f32): w_j = deg_j · Σ_{i ∈ cluster(j)} 1/deg_i."""
     _chk(labels, torch.int32, "labels", 1)
     n = A.shape[0]
+    if n_clusters is None:
+        n_clusters = int(labels.max().item()) + 1 if n else 1
     w = torch.empty(n, dtype=torch.float32, device=labels.device)
-    check(lib().b2_graph_regu_weights_f32(_p(A.rowptr), _p(A.colidx), _p(labels), n, _p(w), _stream()), "b2_graph_regu_weights_f32")
+    sums = torch.empty(max(n_clusters, 1), dtype=torch.float64, device=labels.device)
+    check(lib().b2_graph_regu_weights_f32(_p(A.rowptr), _p(A.colidx), _p(labels), n, int(n_clusters), _p(sums), _p(w), _stream()),
+          "b2_graph_regu_weights_f32")
     return w
 
 

@@ -477,8 +477,10 @@ int b2_gae_loss_grad_sym_f32(const float* z, int64_t ldz, const float* mu, const
  *       labels <- nearest centre (ties: lowest index); update != 0: centres <- cluster means (empty clusters keep theirs).
  *       stats (device, 3 doubles) = {inertia w.r.t. the old centres, ||dC||^2, number of changed labels}.
  *   b2_graph_regu_weights_f32 : graph_celltype_regu_handler + the `[clusterIndex][:, clusterIndex]` slicing of
- *       cluster_AE_handler (scgnn2.py:716-730, 844-846) in sparse form: w_j = sum_{i in N(j), label_i = label_j} 1/deg_i =
- *       column sums of the row-normalised adjacency restricted to j's cluster (pattern = A + I CSR, symmetric).
+ *       cluster_AE_handler (scgnn2.py:716-730, 844-846) without the N x N matrix.  The reference normalises an np.matrix, so its
+ *       `avg_mtx * x` is a MATRIX product and adjdense[i, j] = deg_j / deg_i (dense, rank one); the column sums inside j's cluster are
+ *       w_j = deg_j * sum_{i in cluster(j)} 1/deg_i.  Pattern = A or A + I CSR (the diagonal is not counted); cluster_sums: n_clusters
+ *       device doubles of scratch.
  *   b2_celltype_loss_grad_f32 : loss_function_graph(regularizer_type="Celltype"), scgnn2.py:1316-1326, with the dense
  *       `M @ mse` products folded into per-row weights: value = sum_j row_weight_j * sum_g (r-x)^2 + || (x_dropout - r)[x_dropout != 0] ||_2
  *       (callers pass row_weight = 0.3 + 0.3*w_graph + 0.1*w_celltype); grad = d value / d recon masked by recon > 0.
@@ -491,7 +493,8 @@ int b2_gae_loss_grad_sym_f32(const float* z, int64_t ldz, const float* mu, const
 size_t b2_kmeans_workspace_bytes(int32_t k, int32_t d);
 int b2_kmeans_step_f32(const float* X, int64_t ldx, int32_t n, int32_t d, float* C, int32_t k, int32_t* labels, int update,
                        double* stats, void* workspace, size_t workspace_bytes, void* stream);
-int b2_graph_regu_weights_f32(const int32_t* rowptr, const int32_t* colidx, const int32_t* labels, int32_t n, float* w, void* stream);
+int b2_graph_regu_weights_f32(const int32_t* rowptr, const int32_t* colidx, const int32_t* labels, int32_t n, int32_t n_clusters,
+                              double* cluster_sums, float* w, void* stream);
 int b2_celltype_loss_grad_f32(const float* recon, const float* target, const float* x_dropout, const float* row_weight,
                               int64_t rows, int32_t cols, int32_t cols_orig, int relu_mask, float* grad, float* loss_out,
                               double* scratch2, void* stream);

@@ -393,7 +393,7 @@ def test_gae_loss_tensor_core_single_column_range(cuda):
     assert rel_err(torch.cat([dza, dzb]), ref_dz) < 2e-5
 
 
-@pytest.mark.parametrize("n,d", [(128, 16), (100, 16), (256, 16), (300, 16), (384, 8), (1000, 16), (1537, 12), (2048, 16), (2049, 16)])
+@pytest.mark.parametrize("n,d", [(128, 16), (100, 16), (256, 16), (300, 16), (384, 8), (1000, 16), (1537, 16), (1664, 8), (2048, 16), (2049, 16)])
 def test_gae_symmetric_decoder_small_graphs(cuda, n, d):
     """gae_sym.cu forced onto small graphs: 1, 2, 3, 8, 13, 16, 17 row blocks (odd / even counts, antipodal pairs, a ragged last
     block, a lone last super-block) against the fp64 closed form and against the row-sweep kernel."""

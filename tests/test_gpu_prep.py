@@ -35,7 +35,7 @@ def test_gene_and_cell_stats_match_numpy(cuda):
     assert np.array_equal(ops.subset(Xd, rows, cols).cpu().numpy(), X[[5, 3, 1200]][:, [516, 0, 7, 7]])
 
 
-@pytest.mark.parametrize("kw", [dict(min_cells=0.05), dict(min_cells=30), dict(max_cells=200), dict(min_counts=40), dict(max_counts=500),
+@pytest.mark.parametrize("kw", [dict(min_cells=0.05), dict(min_cells=30), dict(max_cells=100), dict(min_counts=40), dict(max_counts=500),
                                 dict(min_counts=0.3)])
 def test_filter_genes_scanpy(cuda, kw):
     from dance_b200.data import AnnDataLite, Data
