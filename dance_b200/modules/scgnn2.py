@@ -167,11 +167,23 @@ def graph_AE_handler(X_embed, CCC_graph, args, param, dense_recon_max_cells: int
             cache.clear()
             cache.update(n=xe.shape[0], A=A, knn_idx=knn_idx, knn_dist=knn_dist)
     n = xe.shape[0]
+    # ``param["cell_order"] = "locality"`` (extension): the epochs run on a relabelled copy of the graph in which cells are grouped
+    # by nearest embedding centroid (ops.locality_order) — the aggregate's gathers then stay L2-resident; outputs are un-permuted
+    perm = inv = None
+    A_run = A
+    if param.get("cell_order") == "locality" and not args.graph_AE_use_GAT:
+        if cache is not None and "A_run" in cache:
+            perm, inv, A_run = cache["perm"], cache["inv"], cache["A_run"]
+        else:
+            perm, inv = ops.locality_order(xe, n_anchors=int(param.get("cell_order_anchors", 64)))
+            A_run = ops.knn_graph_build(inv[knn_idx[perm].long()].to(torch.int32).contiguous())
+            if cache is not None:
+                cache.update(perm=perm, inv=inv, A_run=A_run)
     adj_sum = A.nnz - n                                                         # Σ adj_train (no diagonal)
     pos_weight = float(n * n - adj_sum) / adj_sum                               # scgnn2.py:567
     norm = n * n / float((n * n - adj_sum) * 2)                                 # scgnn2.py:568-569
-    labels = ops.CSR(A.rowptr, A.colidx, None, A.shape)                         # A + I: pattern of Â, unit entries
-    xin = xin.contiguous()
+    labels = ops.CSR(A_run.rowptr, A_run.colidx, None, A_run.shape)             # A + I: pattern of Â, unit entries
+    xin = xin.contiguous() if perm is None else xin[perm].contiguous()
     out_kw = dict(pool=pool, cache=cache, keep_dev=bool(param.get("keep_on_device")))
     if args.graph_AE_use_GAT:
         # edge_index = edgeList (i → its k neighbours), directed, no self loops (scgnn2.py:560-563); the kernels
@@ -197,10 +209,12 @@ def graph_AE_handler(X_embed, CCC_graph, args, param, dense_recon_max_cells: int
     z = None
     for epoch in range(args.graph_AE_epoch):
         eps.normal_(generator=gen)                                              # torch.randn_like(std), scgnn2.py:397
-        z, _, _ = eng.train_step(xin, A, labels, norm, pos_weight, eps)
+        z, _, _ = eng.train_step(xin, A_run, labels, norm, pos_weight, eps if perm is None else eps[perm].contiguous())
         if logger.isEnabledFor(logging.INFO):
             logger.info(f"Epoch: {epoch+1}/{args.graph_AE_epoch}, Current loss: {eng.loss.item():.4f}")
     param["_graph_AE_engine"] = eng
+    if inv is not None:
+        z = z[inv].contiguous()                                                 # back to the caller's cell order
     return _graph_ae_outputs(z, n, knn_idx, knn_dist, A, dense_recon_max_cells, **out_kw)
 
 

@@ -1037,3 +1037,21 @@ def cellwise_mask(X: torch.Tensor, mask_rate: float = 0.1, min_gene_counts: int 
                                     int(add_test_mask), int(seed) & 0xFFFFFFFF, _p(tr), _p(va), _p(te), _p(over), _stream()),
           "b2_cellwise_mask_u8")
     return tr.view(torch.bool), va.view(torch.bool), te.view(torch.bool), int(over.item())
+
+
+def locality_order(X: torch.Tensor, n_anchors: int = 64, iters: int = 4, seed: int = 0):
+    """A cell order that keeps each thread block's gathers of the aggregate inside a few L2-resident row ranges: cells are grouped
+    by their nearest of ``n_anchors`` centroids (a few Lloyd iterations from seeded random rows, ``b2_kmeans_step_f32``) and the
+    groups laid out contiguously.  Returns (perm, inv): row i of the reordered problem is cell ``perm[i]``; ``inv[perm] = arange``.
+    Relabelling a kNN index table: ``inv[idx[perm]]``.  The graph and every quantity derived from it are permutation-equivariant,
+    so a model run in this order and un-permuted at the end returns the same result (up to summation order)."""
+    _chk(X, torch.float32, "X", 2)
+    n = X.shape[0]
+    k = max(1, min(n_anchors, n))
+    g = torch.Generator(device=X.device).manual_seed(seed)
+    centers = X[torch.randperm(n, device=X.device, generator=g)[:k]].contiguous().clone()
+    labels, _, _ = kmeans(X, centers, max_iter=iters, tol=0.0)
+    perm = torch.sort(labels.long(), stable=True).indices
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(n, device=X.device)
+    return perm, inv
