@@ -48,7 +48,12 @@ constexpr int STAGE_BYTES = 2 * ZA_BYTES + ZT_BYTES;  // 16 KB per J-step: B of 
 constexpr int G_PLANE = BT * BT * 2;                  // 32 KB: fp16 plane of one G tile (two 16 KB blocks of 64 columns)
 constexpr int G_BYTES = 2 * G_PLANE;                  // hi + lo
 constexpr int SMEM_BYTES = 2 * ZI_BYTES + STAGES * STAGE_BYTES + 2 * G_BYTES;   // 208 KB
-constexpr uint32_t TM_S = 0, TM_D1 = 256, TM_D2 = 320, TM_COLS = 512;   // S: 2×128, dZ_I: 2×32, dZ_J: 3×32
+constexpr uint32_t TM_S = 0, TM_D1 = 256, TM_D2 = 384, TM_COLS = 512;   // S: 2×128, dZ_I: 2 segments × 2 blocks × 32, dZ_J: 3×32
+// The tensor core adds into its fp32 accumulator with truncation, so a chain of k accumulations drifts by up to k·2^-24 (measured:
+// 6e-4 after the 125 000 accumulations of a 1 M-cell sweep).  dZ_I is therefore accumulated in SEGMENTS of SEG_STEPS J-steps
+// (≤ 128 accumulations), double-buffered in TMEM; the flush warps add each finished segment to global memory (round-to-nearest
+// atomics) while the next one accumulates.  dZ_J is flushed every step anyway.
+constexpr int SEG_STEPS = 8;
 constexpr float G_SCALE = 2048.f;
 constexpr int STAGGER_CYCLES = 1500;
 
@@ -182,8 +187,9 @@ gae_sym_kernel(const __grid_constant__ Params p) {
   const uint32_t g_empty = g_full + 16;                  // [2] D-MMA commit → elementwise group
   const uint32_t d2_full = g_empty + 16;                 // [3] D-MMA commit → flush warps
   const uint32_t d2_empty = d2_full + 24;                // [3] flush warps → MMA
-  const uint32_t d1_full = d2_empty + 24;                // 1
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bar_area + 192);
+  const uint32_t d1_full = d2_empty + 24;                // [2] last D-MMA of a segment → flush warps
+  const uint32_t d1_empty = d1_full + 16;                // [2] flush warps → MMA
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bar_area + 224);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Sweep sw(p.nb, p.sb_begin + blockIdx.x);
@@ -204,7 +210,7 @@ gae_sym_kernel(const __grid_constant__ Params p) {
       mbar_init(g_empty + 8 * b, 1);
     }
     for (int b = 0; b < 3; ++b) { mbar_init(d2_full + 8 * b, 1); mbar_init(d2_empty + 8 * b, FL_WARPS); }
-    mbar_init(d1_full, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(d1_full + 8 * b, 1); mbar_init(d1_empty + 8 * b, FL_WARPS); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), TM_COLS);
@@ -250,7 +256,8 @@ gae_sym_kernel(const __grid_constant__ Params p) {
       mbar_wait(zi_bar, 0);
       tc_fence_after();
       // per-group / per-buffer phase counters packed into scalars (dynamic indexing of local arrays would put them on the stack)
-      uint32_t cnt_s = 0, cnt_d = 0, use_d2 = 0, d1_started = 0;     // bit g / bit b3 = parity (or flag) of that slot
+      uint32_t cnt_s = 0, cnt_d = 0, use_d2 = 0, use_d1 = 0, d1_fresh = 0;   // bit q / b3 / segment parity = phase (or flag) of that slot
+      int cur_seg = -1;
       auto next_tile = [&](int& s, int& g) {              // advance to the next active tile (s == n_steps: end)
         do { if (++g == 2) { g = 0; ++s; } } while (s < sw.n_steps && !sw.active(g, s));
       };
@@ -280,16 +287,23 @@ gae_sym_kernel(const __grid_constant__ Params p) {
         tc_fence_after();
         const uint32_t g_hi = s_g + q * G_BYTES, g_lo = g_hi + G_PLANE;
         const uint32_t zt_j = s_ring + stage * STAGE_BYTES + 2 * ZA_BYTES;
-        const uint32_t d1 = tmem + TM_D1 + (uint32_t)(g * 2 * DW);
+        const int seg = s / SEG_STEPS, sp = seg & 1;
+        if (seg != cur_seg) {                    // first dZ_I product of a new segment: its TMEM buffers must have been drained
+          mbar_wait(d1_empty + 8 * sp, ((use_d1 >> sp) & 1u) ^ 1u);
+          tc_fence_after();
+          cur_seg = seg;
+          d1_fresh = 3u;                         // both blocks start the segment with accumulate = 0
+        }
+        const uint32_t d1 = tmem + TM_D1 + (uint32_t)((sp * 2 + g) * 2 * DW);
 #pragma unroll
         for (int ks = 0; ks < BT / 16; ++ks) {
           // K-major SWIZZLE_128B: 64 j per 128-byte row, 8-row groups 1 KB apart; k-step = 32 B inside the row, 64-column blocks 16 KB apart
           const uint32_t koff = (uint32_t)(ks >> 2) * (BT * 128) + (uint32_t)(ks & 3) * 32u;
           const uint64_t b = umma_desc(zt_j + (uint32_t)(ks >> 2) * (2 * ZT_BOX) + (uint32_t)(ks & 3) * 32u, 16, 1024, 2);
-          umma_f16(d1, umma_desc(g_hi + koff, 16, 1024, 2), b, idesc_d1, (((d1_started >> g) & 1u) || ks > 0) ? 1u : 0u);
+          umma_f16(d1, umma_desc(g_hi + koff, 16, 1024, 2), b, idesc_d1, (!((d1_fresh >> g) & 1u) || ks > 0) ? 1u : 0u);
           umma_f16(d1, umma_desc(g_lo + koff, 16, 1024, 2), b, idesc_d1, 1);
         }
-        d1_started |= 1u << g;
+        d1_fresh &= ~(1u << g);
         if (!sw.diag(g, s)) {
           const int b3 = s % 3;
           const bool first = (g == 0) || !(sw.active(0, s) && !sw.diag(0, s));     // first tile of this step that feeds dZ_J
@@ -313,6 +327,7 @@ gae_sym_kernel(const __grid_constant__ Params p) {
         if (sw.last_of_step(g, s)) {
           umma_commit(stage_free + 8 * stage);
           if (sw.has_d2(s)) { umma_commit(d2_full + 8 * (s % 3)); use_d2 ^= 1u << (s % 3); }
+          if (s % SEG_STEPS == SEG_STEPS - 1 || s == sw.n_steps - 1) { umma_commit(d1_full + 8 * sp); use_d1 ^= 1u << sp; }
         }
       };
       // S runs two tiles ahead of the D products (the tensor pipe executes in order; see gae_tch.cu)
@@ -326,7 +341,6 @@ gae_sym_kernel(const __grid_constant__ Params p) {
         ++dk;
         next_tile(ds, dg);
       }
-      umma_commit(d1_full);
     }
     __syncwarp();
   } else if (warp < 4 + EW_WARPS) {
@@ -441,17 +455,17 @@ gae_sym_kernel(const __grid_constant__ Params p) {
     double loss = (double)LN2 * (0.5 * (double)abs_w + (double)lg_w + 11.0 * 16.0 * (double)chunks_w);
     loss = warp_sum(loss);
     if (lane == 0 && loss != 0.0) atomicAdd(p.loss_acc, loss * (double)p.coef);
-    const int I_epi = sw.block(q);                // the half-0 warps of group q also drain the dZ accumulator of owned block q
-    if (half == 0 && I_epi >= 0) {
-      // dZ_I epilogue: [G·Z_hi | G·Z_lo] → global (atomic: other CTAs add their Gᵀ·Z contributions to the same rows)
-      mbar_wait(d1_full, 0);
-      tc_fence_after();
-      uint32_t a0[16], a1[16];
-      tmem_ld_32x32b_x16(tmem + lane_off + TM_D1 + (uint32_t)(q * 2 * DW), a0);
-      tmem_ld_32x32b_x16(tmem + lane_off + TM_D1 + (uint32_t)(q * 2 * DW + DW), a1);
-      const int gr = I_epi * BT + row;
+  } else {
+    // ===================== dZ_J flush warps =====================
+    setmaxnreg_dec<48>();
+    const int sub = warp & 3;
+    const uint32_t lane_off = (uint32_t)(sub * 32) << 16;
+    uint32_t fcnt = 0;                            // bit b3 = phase parity of dZ_J buffer b3
+    const float c2 = 2.f * p.coef * p.scale[2] * (1.f / G_SCALE);
+    uint32_t f1cnt = 0;                           // bit = phase parity of dZ_I segment buffer
+    auto add_rows = [&](int block, const uint32_t (&a0)[16], const uint32_t (&a1)[16]) {
+      const int gr = block * BT + sub * 32 + lane;
       if (gr < p.n) {
-        const float c2 = 2.f * p.coef * p.scale[2] * (1.f / G_SCALE);
         float* dst = p.dz + (size_t)gr * p.d;
         float o[16];
 #pragma unroll
@@ -464,39 +478,45 @@ gae_sym_kernel(const __grid_constant__ Params p) {
           for (int c = 0; c < 16; ++c) if (c < p.d) atomicAdd(dst + c, o[c]);
         }
       }
-    }
-  } else {
-    // ===================== dZ_J flush warps =====================
-    setmaxnreg_dec<48>();
-    const int sub = warp & 3;
-    const uint32_t lane_off = (uint32_t)(sub * 32) << 16;
-    uint32_t fcnt = 0;                            // bit b3 = phase parity of dZ_J buffer b3
-    const float c2 = 2.f * p.coef * p.scale[2] * (1.f / G_SCALE);
+    };
     for (int s = 0; s < sw.n_steps; ++s) {
-      if (!sw.has_d2(s)) continue;
-      const int b3 = s % 3;
-      mbar_wait(d2_full + 8 * b3, (fcnt >> b3) & 1u);
-      tc_fence_after();
-      uint32_t a0[16], a1[16];
-      tmem_ld_32x32b_x16(tmem + lane_off + TM_D2 + (uint32_t)(b3 * 2 * DW), a0);
-      tmem_ld_32x32b_x16(tmem + lane_off + TM_D2 + (uint32_t)(b3 * 2 * DW + DW), a1);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(d2_empty + 8 * b3);
-      fcnt ^= 1u << b3;
-      const int gr = sw.J(s) * BT + sub * 32 + lane;
-      if (gr < p.n) {
-        float* dst = p.dz + (size_t)gr * p.d;
-        float o[16];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) o[c] = c2 * (__uint_as_float(a0[c]) + __uint_as_float(a1[c]));
-        if (p.d == 16) {
-#pragma unroll
-          for (int c = 0; c < 16; c += 4) red_add_v4(dst + c, o[c], o[c + 1], o[c + 2], o[c + 3]);
-        } else {
-#pragma unroll
-          for (int c = 0; c < 16; ++c) if (c < p.d) atomicAdd(dst + c, o[c]);
+      if (sw.has_d2(s)) {
+        const int b3 = s % 3;
+        mbar_wait(d2_full + 8 * b3, (fcnt >> b3) & 1u);
+        tc_fence_after();
+        uint32_t a0[16], a1[16];
+        tmem_ld_32x32b_x16(tmem + lane_off + TM_D2 + (uint32_t)(b3 * 2 * DW), a0);
+        tmem_ld_32x32b_x16(tmem + lane_off + TM_D2 + (uint32_t)(b3 * 2 * DW + DW), a1);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d2_empty + 8 * b3);
+        fcnt ^= 1u << b3;
+        add_rows(sw.J(s), a0, a1);
+      }
+      if (s % SEG_STEPS == SEG_STEPS - 1 || s == sw.n_steps - 1) {
+        // a dZ_I segment is complete: [G·Z_hi | G·Z_lo] of both owned blocks → global (atomic: other CTAs add to the same rows)
+        const int seg = s / SEG_STEPS, sp = seg & 1;
+        mbar_wait(d1_full + 8 * sp, (f1cnt >> sp) & 1u);
+        tc_fence_after();
+        bool wrote0 = false, wrote1 = false;
+        for (int s2 = seg * SEG_STEPS; s2 <= s; ++s2) { wrote0 |= sw.active(0, s2); wrote1 |= sw.active(1, s2); }
+        {
+          uint32_t a0[16], a1[16];
+          if (wrote0) {
+            tmem_ld_32x32b_x16(tmem + lane_off + TM_D1 + (uint32_t)((sp * 2 + 0) * 2 * DW), a0);
+            tmem_ld_32x32b_x16(tmem + lane_off + TM_D1 + (uint32_t)((sp * 2 + 0) * 2 * DW + DW), a1);
+            add_rows(sw.I0, a0, a1);
+          }
+          if (wrote1) {
+            tmem_ld_32x32b_x16(tmem + lane_off + TM_D1 + (uint32_t)((sp * 2 + 1) * 2 * DW), a0);
+            tmem_ld_32x32b_x16(tmem + lane_off + TM_D1 + (uint32_t)((sp * 2 + 1) * 2 * DW + DW), a1);
+            add_rows(sw.I1, a0, a1);
+          }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d1_empty + 8 * sp);
+        f1cnt ^= 1u << sp;
       }
     }
   }

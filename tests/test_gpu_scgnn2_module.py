@@ -66,8 +66,12 @@ def test_scgnn2_fit_pre_em(cuda):
     model.fit(X)
     out = model.predict()
     assert out.shape == X.shape and np.isfinite(out).all()
-    with pytest.raises(NotImplementedError):
-        ScGNN2(_args(total_epoch=1), device="cuda", seed=0).fit(X)
+    # one EM iteration (the full loop is exercised in tests/test_gpu_em.py and through the example script)
+    em = ScGNN2(_args(total_epoch=1, clustering_louvain_only=False, clustering_embed="graph", clustering_method="KMeans", seed=0,
+                      cluster_AE_batch_size=12800, cluster_AE_epoch=2, cluster_AE_learning_rate=1e-3, cluster_AE_regu_strength=0.9,
+                      cluster_AE_dropout_prob=0), device="cuda", seed=0)
+    em.fit(X)
+    assert em.predict().shape == X.shape and np.isfinite(em.predict()).all() and len(em.cluster_labels) == 256
 
 
 def test_graph_ae_handler_locality_order_is_equivalent(cuda):
