@@ -642,7 +642,8 @@ def parity_checks(ops, gae, A, labels, norm, pos_weight, N, r0, n_loc, comm, dev
     b = gae._buffers(n_loc)
     z_loc = b["z"]
     z_all = gae._gather(z_loc, "z")
-    out = {}
+    out = {"z_finite": bool(torch.isfinite(z_all).all()), "z_absmax": float(z_all.abs().max()), "train_loss": float(gae.loss.item())}
+    assert out["z_finite"], f"Graph-AE embedding is not finite after the warm-up steps: {out}"
     g = torch.Generator(device=dev).manual_seed(7)
     rows_loc = torch.randint(0, n_loc, (96, ), device=dev, generator=g)
     dz = torch.empty(n_loc, z_loc.shape[1], dtype=torch.float32, device=dev)
@@ -656,6 +657,7 @@ def parity_checks(ops, gae, A, labels, norm, pos_weight, N, r0, n_loc, comm, dev
     if r0 + n_loc < N:
         rp_full[r0 + n_loc + 1:] = A.rowptr[-1]
     _, ref_rows = gae_reference_rows(z_all, rp_full, A.colidx, norm, pos_weight, rows_loc + r0)
+    out["dz_finite"] = bool(torch.isfinite(dz).all())
     err = float((dz[rows_loc].double() - ref_rows).norm() / ref_rows.norm())
     out["decoder_grad_rel_err_96_rows"] = err
     assert err < 2e-5, f"decoder gradient mismatch at full size: rel err {err}"
