@@ -20,6 +20,7 @@ _SIGNATURES = {
     "b2_version": (C.c_int, []),
     "b2_set_path": (C.c_int, [C.c_int, C.c_int]),
     "b2_get_path": (C.c_int, [C.c_int]),
+    "b2_set_tuning": (C.c_int, [C.c_int, C.c_int]),
     "b2_launch_count": (c_i64, []),
     "b2_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "b2_spmm_csr_f32": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32, C.c_int, C.c_int, c_vp, c_vp]),

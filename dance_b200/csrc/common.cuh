@@ -15,6 +15,7 @@ int cuda_fail(cudaError_t e, const char* what);
 int sm_count();
 const char* last_error();
 int path_mode(int which);          // b2_set_path selector value (0 = automatic)
+int tuning(int which);             // b2_set_tuning knob value
 extern long long g_launch_count;   // kernels launched by this library (process-wide; see b2_launch_count)
 
 #define B2_CHECK_CUDA(expr)                                   \

@@ -61,11 +61,12 @@ struct Params {
   CUtensorMap mA_hi, mA_lo;      // log2(e)·z [npad,16] halves, box {16,128} SWIZZLE_32B   (A of S)
   CUtensorMap mB_hi, mB_lo;      // z         [npad,16] halves, box {16,128} SWIZZLE_32B   (B of S)
   CUtensorMap mT_hi, mT_lo;      // 2^e·zᵀ    [16,npad] halves, box {64,16}  SWIZZLE_128B  (B of G·Z_J and of Gᵀ·Z_I)
-  const float* scale;            // scale[2] = 2^-e
+  const float* scale;            // [0] 2^e (ZT), [2] 2^-e, [3] 2^2f, [4] 2^-f, [5] f > 0 (see scale_kernel)
   float* dz;                     // [n, d], zero-initialised by the caller; every contribution is an atomic add
   double* loss_acc;
   int n, d, nb, sb_begin;
   float coef;
+  int stagger, late_gempty;      // b2_set_tuning knobs
 };
 
 // ---- sweep bookkeeping shared by all roles ----------------------------------------------------------------------------------
@@ -109,6 +110,15 @@ __global__ void scale_kernel(const uint32_t* __restrict__ maxbits, float* __rest
   scale[0] = ldexpf(1.f, e);
   scale[1] = ldexpf(1.f, -2 * e);
   scale[2] = ldexpf(1.f, -e);
+  // Operands of the S product are fp16 pairs: |log2(e)·z| must stay below 2^15.  Larger embeddings (an untrained Graph-AE at 1 M cells
+  // draws z = mu + eps·exp(logvar) with logvar ≈ 14) are scaled down by 2^-f on BOTH sides; the accumulator then holds 2^-2f·v and
+  // the elementwise warps multiply it back (SCALED kernel variant, one extra FMUL per logit; the unscaled variant runs otherwise).
+  int f = 0;
+  if (m > 0.f && isfinite(m)) { int ex; frexpf(m * 1.4426950408889634f, &ex); f = ex > 15 ? ex - 15 : 0; }
+  f = f > 60 ? 60 : f;
+  scale[3] = ldexpf(1.f, 2 * f);
+  scale[4] = ldexpf(1.f, -f);
+  scale[5] = f > 0 ? 1.f : 0.f;
 }
 
 // z [n,d] → fp16 hi/lo planes: za = log2(e)·z, zb = z (row-major, 16 wide, npad rows), zt = 2^e·zᵀ (row pitch npad); zero padding
@@ -117,7 +127,7 @@ split_kernel(const float* __restrict__ z, int64_t ldz, int32_t n, int32_t d, int
              __half* __restrict__ zah, __half* __restrict__ zal, __half* __restrict__ zbh, __half* __restrict__ zbl,
              __half* __restrict__ zth, __half* __restrict__ ztl) {
   const int64_t total = npad * DW;
-  const float s = scale[0];
+  const float s = scale[0], sd = scale[4];      // sd = 2^-f (1 unless the embedding is too large for fp16 operands)
   constexpr float LOG2E = 1.4426950408889634f;
   auto split = [](float v, __half& h, __half& l) { h = __float2half_rn(v); l = __float2half_rn(v - __half2float(h)); };
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -125,8 +135,8 @@ split_kernel(const float* __restrict__ z, int64_t ldz, int32_t n, int32_t d, int
     const int c = (int)(t % DW);
     const float v = (c < d && i < n) ? z[i * ldz + c] : 0.f;
     __half h, l;
-    split(v, h, l);          zbh[t] = h; zbl[t] = l;
-    split(v * LOG2E, h, l);  zah[t] = h; zal[t] = l;
+    split(v * sd, h, l);          zbh[t] = h; zbl[t] = l;
+    split(v * LOG2E * sd, h, l);  zah[t] = h; zal[t] = l;
     split(v * s, h, l);
     zth[(int64_t)c * npad + i] = h;
     ztl[(int64_t)c * npad + i] = l;
@@ -169,8 +179,12 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
+template <bool SCALED>
 __global__ void __launch_bounds__(THREADS, 1)
 gae_sym_kernel(const __grid_constant__ Params p) {
+  // both variants are launched back to back; the one that does not match the device-side scale flag returns at once (the host never
+  // reads the embedding's magnitude, so there is no synchronisation)
+  if ((p.scale[5] != 0.f) != SCALED) return;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t s_g = smem_u32(smem);                               // G planes first: 1024-byte aligned swizzle atoms
@@ -353,9 +367,10 @@ gae_sym_kernel(const __grid_constant__ Params p) {
     const int row = sub * 32 + lane;              // row inside the tile
     const uint32_t lane_off = (uint32_t)(sub * 32) << 16;
     constexpr float LN2 = 0.6931471805599453f;
+    const float vs = SCALED ? p.scale[3] : 1.f;   // 2^2f: undoes the operand scaling of the S product
     float abs_w = 0.f, lg_w = 0.f;
     int chunks_w = 0;                             // 16-logit chunks processed, weighted like the sums
-    if (q == 1) { const long long t0 = clock64(); while (clock64() - t0 < STAGGER_CYCLES) { } }
+    if (q == 1) { const long long t0 = clock64(); while (clock64() - t0 < p.stagger) { } }
     int ng = 0;                                   // tiles this group has processed (phase of its S / G buffers)
     const uint32_t g_hi = s_g + q * G_BYTES + (uint32_t)half * (BT * 128) + (uint32_t)row * 128u, g_lo = g_hi + G_PLANE;
     const uint32_t xr = (uint32_t)(row & 7);
@@ -374,7 +389,7 @@ gae_sym_kernel(const __grid_constant__ Params p) {
         const int col_end = (ragged && J == p.nb - 1) ? n_last : BT;       // valid columns of this tile
         mbar_wait(s_full + 8 * q, ng & 1);
         tc_fence_after();
-        mbar_wait(g_empty + 8 * q, (ng & 1) ^ 1);                          // the D-MMAs of this group's previous tile have read G
+        if (!p.late_gempty) mbar_wait(g_empty + 8 * q, (ng & 1) ^ 1);
         float abs_t = 0.f, lg_t = 0.f;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -394,7 +409,7 @@ gae_sym_kernel(const __grid_constant__ Params p) {
             float gg[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
-              const float x = __uint_as_float(v[c]);
+              const float x = SCALED ? __uint_as_float(v[c]) * vs : __uint_as_float(v[c]);
               const float e = ex2a(-fabsf(x));
               const float q = fmaf(e, 1.f / G_SCALE, 1.f / G_SCALE);
               const float r = rcpa(q);
@@ -429,6 +444,9 @@ gae_sym_kernel(const __grid_constant__ Params p) {
             chunk_math(std::false_type{}, v0, cofs, hi0, lo0);
             chunk_math(std::false_type{}, v1, cofs + 16, hi1, lo1);
           }
+          // G[q] may be overwritten once the D-MMAs of this group's previous tile have read it: waited for as late as possible
+          // (after the first half's math), so the group is not idle while the tensor pipe drains the previous tile
+          if (hh == 0 && p.late_gempty) mbar_wait(g_empty + 8 * q, (ng & 1) ^ 1);
           // 16-byte chunk c of this thread's 128-byte row holds columns 8c..8c+7; swizzle: chunk ^= row % 8
           const uint32_t cb = (uint32_t)hh * 4u;
           sts_v4(g_hi + (((cb + 0) ^ xr) << 4), hi0[0], hi0[1], hi0[2], hi0[3]);
@@ -596,16 +614,20 @@ int launch(const float* z, int64_t ldz, int32_t n, int32_t d, int32_t sb_begin, 
             make_tensor_map_f16_ex(&p.mT_hi, zth, (uint64_t)npad, DW, (uint64_t)npad, 64, DW, SW128) &&
             make_tensor_map_f16_ex(&p.mT_lo, ztl, (uint64_t)npad, DW, (uint64_t)npad, 64, DW, SW128);
   if (!ok) return B2_ERR_UNSUPPORTED;
+  p.stagger = tuning(B2_TUNE_GAE_STAGGER); p.late_gempty = tuning(B2_TUNE_GAE_LATE_GEMPTY);
   p.scale = scale; p.dz = dz; p.loss_acc = loss_acc; p.n = n; p.d = d; p.nb = (int)(npad / BT); p.sb_begin = sb_begin; p.coef = coef;
   if (sb_end <= sb_begin) return B2_OK;
   const size_t smem = SMEM_BYTES + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(gae_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2_CHECK_CUDA(cudaFuncSetAttribute(gae_sym_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2_CHECK_CUDA(cudaFuncSetAttribute(gae_sym_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  gae_sym_kernel<<<sb_end - sb_begin, THREADS, smem, st>>>(p);
+  gae_sym_kernel<false><<<sb_end - sb_begin, THREADS, smem, st>>>(p);
   B2_CHECK_LAUNCH("gae_sym_kernel");
+  gae_sym_kernel<true><<<sb_end - sb_begin, THREADS, smem, st>>>(p);      // no-op unless the embedding needed operand scaling
+  B2_CHECK_LAUNCH("gae_sym_kernel<scaled>");
   return B2_OK;
 }
 

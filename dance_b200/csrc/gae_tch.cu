@@ -76,6 +76,9 @@ __global__ void scale_kernel(const uint32_t* __restrict__ maxbits, float* __rest
   scale[0] = ldexpf(1.f, e);
   scale[1] = ldexpf(1.f, -2 * e);
   scale[2] = ldexpf(1.f, -e);
+  // the S-product operands are UNSCALED fp16 pairs of log2(e)·z: beyond 2^15 they overflow — this kernel then steps aside
+  // (scale[3] = 1) and b2_gae_loss_grad_f32 runs the fp32 CUDA-core kernel instead (device-side predicate, no host sync)
+  scale[3] = (m * 1.4426950408889634f >= 32768.f || !isfinite(m)) ? 1.f : 0.f;
 }
 
 // z [n,d] → fp16 hi/lo split of 2^e·z, as Z16 (row-major, padded to 16) and ZT (transposed, row pitch npad)
@@ -126,6 +129,7 @@ __device__ __forceinline__ float rcpa(float x) { float y; asm("rcp.approx.ftz.f3
 
 __global__ void __launch_bounds__(THREADS, 1)
 gae_allpairs_tch_kernel(const __grid_constant__ Params p) {
+  if (p.scale[3] != 0.f) return;                 // embedding too large for the fp16 operand format (see scale_kernel)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t s_zi_hi = smem_u32(smem), s_zi_lo = s_zi_hi + ZI_BYTES;
@@ -380,6 +384,8 @@ gae_allpairs_tch_kernel(const __grid_constant__ Params p) {
 }
 
 static int64_t padded_n(int32_t n) { return ((int64_t)n + 63) / 64 * 64; }
+
+const float* overflow_flag(const void* ws) { return reinterpret_cast<const float*>(reinterpret_cast<const char*>(ws) + 16) + 3; }
 
 size_t workspace_bytes(int32_t n) {
   return 256 + 32768 + 4 * align_up((size_t)n * DW * sizeof(__half), 256) + 2 * align_up((size_t)padded_n(n) * DW * sizeof(__half), 256);

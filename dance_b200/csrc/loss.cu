@@ -82,7 +82,11 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 template <int D>
 __global__ void __launch_bounds__(GL_THREADS)
 gae_allpairs_kernel(const float* __restrict__ z, int64_t ldz, int32_t n, int32_t row_begin, int32_t n_rows,
-                    int32_t j_chunk, float coef, float* __restrict__ dz, double* __restrict__ loss_acc) {
+                    int32_t j_chunk, float coef, float* __restrict__ dz, double* __restrict__ loss_acc,
+                    const float* __restrict__ only_if) {
+  // device-side predicate: the fp16-operand tensor-core kernel of gae_tch.cu steps aside (and raises this flag) when the embedding
+  // is too large for its operand format; this fp32 kernel then does the work, otherwise it returns at once
+  if (only_if && only_if[0] == 0.f) return;
   constexpr int GL_RPT = GaeCfg<D>::RPT, GL_ROWS = GaeCfg<D>::ROWS;
   __shared__ __align__(16) float zj[GL_JT][D];
   float2 zi[GL_RPT][D / 2], acc[GL_RPT][D / 2];   // feature pairs (d, d+1) packed for FFMA2
@@ -257,6 +261,7 @@ size_t workspace_bytes(int32_t n);
 bool eligible(int32_t n, int32_t d, int32_t n_rows);
 int launch(const float* z, int64_t ldz, int32_t n, int32_t d, int32_t row_begin, int32_t n_rows, float coef, float* dz,
            double* loss_acc, void* ws, size_t ws_bytes, cudaStream_t st);
+const float* overflow_flag(const void* ws);    // device flag: 1 when the embedding is too large for fp16 operands (kernel stepped aside)
 }  // namespace gtch
 
 namespace gsym {   // gae_sym.cu: symmetric (unordered block pairs) tcgen05 version — half the elementwise work of gae_tch.cu
@@ -282,8 +287,8 @@ static int launch_gae_edges(const float* z, int64_t ldz, const int32_t* rp, cons
 template <int D>
 static int launch_gae(const float* z, int64_t ldz, const int32_t* rp, const int32_t* ci, int32_t n, int32_t row_begin,
                       int32_t n_rows, float coef, float pw, int use_pw, float* dz, double* acc, bool skip_allpairs,
-                      cudaStream_t st) {
-  if (skip_allpairs) return launch_gae_edges<D>(z, ldz, rp, ci, row_begin, n_rows, coef, pw, use_pw, dz, acc, st);
+                      cudaStream_t st, const float* only_if = nullptr) {
+  if (skip_allpairs && !only_if) return launch_gae_edges<D>(z, ldz, rp, ci, row_begin, n_rows, coef, pw, use_pw, dz, acc, st);
   const int row_blocks = ceil_div(n_rows, GaeCfg<D>::ROWS);
   // split the j range so that small graphs still fill the machine
   int j_splits = 1;
@@ -294,7 +299,7 @@ static int launch_gae(const float* z, int64_t ldz, const int32_t* rp, const int3
   int j_chunk = ceil_div(ceil_div(n, j_splits), GL_JT) * GL_JT;
   j_splits = ceil_div(n, j_chunk);
   dim3 grid(row_blocks, j_splits);
-  gae_allpairs_kernel<D><<<grid, GL_THREADS, 0, st>>>(z, ldz, n, row_begin, n_rows, j_chunk, coef, dz, acc);
+  gae_allpairs_kernel<D><<<grid, GL_THREADS, 0, st>>>(z, ldz, n, row_begin, n_rows, j_chunk, coef, dz, acc, only_if);
   B2_CHECK_LAUNCH("gae_allpairs_kernel");
   return launch_gae_edges<D>(z, ldz, rp, ci, row_begin, n_rows, coef, pw, use_pw, dz, acc, st);
 }
@@ -345,6 +350,7 @@ extern "C" int b2_gae_loss_grad_f32(const float* z, int64_t ldz, const float* mu
   int rc;
   // large problems: the all-pairs part runs on tcgen05 (gae_tc.cu); the CUDA-core kernel serves small graphs
   bool tc_done = false;
+  const float* fallback_flag = nullptr;          // set when the chosen tensor-core kernel may step aside on the device
   // full row range: the symmetric kernel evaluates every unordered block pair once (gae_sym.cu); a row shard of a multi-GPU run
   // goes through b2_gae_loss_grad_sym_f32 instead (super-block ranges + all-reduce of dz), or falls through to the row-sweep kernel
   if (row_begin == 0 && n_rows == n && gsym::eligible(n, d) && workspace_bytes >= 256 + gsym::workspace_bytes(n)) {
@@ -354,7 +360,7 @@ extern "C" int b2_gae_loss_grad_f32(const float* z, int64_t ldz, const float* mu
   }
   if (!tc_done && gtch::eligible(n, d, n_rows) && workspace_bytes >= 256 + gtch::workspace_bytes(n)) {
     rc = gtch::launch(z, ldz, n, d, row_begin, n_rows, coef, dz, acc, reinterpret_cast<char*>(workspace) + 256, workspace_bytes - 256, st);
-    if (rc == B2_OK) tc_done = true;
+    if (rc == B2_OK) { tc_done = true; fallback_flag = gtch::overflow_flag(reinterpret_cast<char*>(workspace) + 256); }
     else if (rc != B2_ERR_UNSUPPORTED) return rc;
   }
   if (!tc_done && gtc::eligible(n, d, n_rows) && workspace_bytes >= 256 + gtc::workspace_bytes(n)) {
@@ -363,10 +369,10 @@ extern "C" int b2_gae_loss_grad_f32(const float* z, int64_t ldz, const float* mu
     else if (rc != B2_ERR_UNSUPPORTED) return rc;
   }
   switch (d) {
-    case 8: rc = launch_gae<8>(z, ldz, lab_rowptr, lab_colidx, n, row_begin, n_rows, coef, pos_weight, use_pos_weight, dz, acc, tc_done, st); break;
-    case 16: rc = launch_gae<16>(z, ldz, lab_rowptr, lab_colidx, n, row_begin, n_rows, coef, pos_weight, use_pos_weight, dz, acc, tc_done, st); break;
-    case 32: rc = launch_gae<32>(z, ldz, lab_rowptr, lab_colidx, n, row_begin, n_rows, coef, pos_weight, use_pos_weight, dz, acc, tc_done, st); break;
-    case 64: rc = launch_gae<64>(z, ldz, lab_rowptr, lab_colidx, n, row_begin, n_rows, coef, pos_weight, use_pos_weight, dz, acc, tc_done, st); break;
+    case 8: rc = launch_gae<8>(z, ldz, lab_rowptr, lab_colidx, n, row_begin, n_rows, coef, pos_weight, use_pos_weight, dz, acc, tc_done, st, fallback_flag); break;
+    case 16: rc = launch_gae<16>(z, ldz, lab_rowptr, lab_colidx, n, row_begin, n_rows, coef, pos_weight, use_pos_weight, dz, acc, tc_done, st, fallback_flag); break;
+    case 32: rc = launch_gae<32>(z, ldz, lab_rowptr, lab_colidx, n, row_begin, n_rows, coef, pos_weight, use_pos_weight, dz, acc, tc_done, st, fallback_flag); break;
+    case 64: rc = launch_gae<64>(z, ldz, lab_rowptr, lab_colidx, n, row_begin, n_rows, coef, pos_weight, use_pos_weight, dz, acc, tc_done, st, fallback_flag); break;
     default:
       set_error("b2_gae_loss_grad_f32: embedding size %d unsupported (8, 16, 32, 64)", d);
       return B2_ERR_UNSUPPORTED;

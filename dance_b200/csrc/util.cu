@@ -39,6 +39,10 @@ const char* last_error() { return g_err; }
 static int g_path[B2_PATH_COUNT] = {0, 0};
 int path_mode(int which) { return (which >= 0 && which < B2_PATH_COUNT) ? g_path[which] : 0; }
 
+// scheduling knobs of the tensor-core decoder (b2_set_tuning): they move work in time, never change a result
+static int g_tune[B2_TUNE_COUNT] = {1500, 1};
+int tuning(int which) { return (which >= 0 && which < B2_TUNE_COUNT) ? g_tune[which] : 0; }
+
 }  // namespace b2
 
 extern "C" {
@@ -57,6 +61,13 @@ int b2_set_path(int which, int mode) {
 }
 
 int b2_get_path(int which) { return b2::path_mode(which); }
+
+int b2_set_tuning(int which, int value) {
+  B2_REQUIRE(which >= 0 && which < B2_TUNE_COUNT, "b2_set_tuning: unknown knob %d", which);
+  B2_REQUIRE(value >= 0 && value <= 1000000, "b2_set_tuning: value %d out of range", value);
+  b2::g_tune[which] = value;
+  return B2_OK;
+}
 
 int b2_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;

@@ -135,6 +135,11 @@ def set_path(which: str, mode: str = "auto") -> None:
     check(lib().b2_set_path(sel, modes[mode]), "b2_set_path")
 
 
+def set_tuning(knob: str, value: int) -> None:
+    """Scheduling knobs of the symmetric decoder ("gae_stagger" cycles, "gae_late_gempty" 0/1): timing experiments only."""
+    check(lib().b2_set_tuning({"gae_stagger": 0, "gae_late_gempty": 1}[knob], int(value)), "b2_set_tuning")
+
+
 def get_path(which: str) -> str:
     sel, modes = _PATHS[which]
     v = lib().b2_get_path(sel)

@@ -422,6 +422,28 @@ def test_gae_symmetric_decoder_small_graphs(cuda, n, d):
     assert rel_err(dz, dz_r) < 2e-5 and abs(loss.item() - loss_r.item()) < 2e-6 * abs(ref_loss)
 
 
+@pytest.mark.parametrize("n,path,scale", [(4500, "sym", 3.0e4), (4500, "sym", 40.0), (3000, "f16", 3.0e4), (3000, "cuda", 3.0e4)])
+def test_gae_decoder_large_embedding(cuda, n, path, scale):
+    """Embeddings far beyond the fp16 operand range (an untrained Graph-AE at 1 M cells draws z = mu + eps·exp(logvar) with logvar ≈ 14,
+    |z| ~ 1e6): the symmetric kernel switches to its scaled-operand variant, the row-sweep kernel steps aside for the fp32 kernel —
+    finite and equal to the fp64 closed form either way (the reference's BCE-with-logits is finite for any logit)."""
+    from dance_b200 import ops
+    gen = torch.Generator(device=cuda).manual_seed(n)
+    z = (torch.randn(n, 16, device=cuda, generator=gen) * scale).contiguous()
+    idx = torch.randint(0, n, (n, 5), device=cuda, dtype=torch.int32, generator=gen)
+    A = ops.knn_graph_build(idx.contiguous())
+    L = ops.CSR(A.rowptr, A.colidx, None, A.shape)
+    ref_loss, ref_dz = gae_reference_rows(z, A.rowptr, A.colidx, 0.5, 50.0, torch.arange(n, device=cuda))
+    ops.set_path("gae", path)
+    try:
+        loss, dz, _, _ = ops.gae_loss_grad(z, L, 0.5, 50.0)
+    finally:
+        ops.set_path("gae", "auto")
+    assert bool(torch.isfinite(dz).all()) and np.isfinite(loss.item())
+    assert abs(loss.item() - ref_loss) < 5e-6 * abs(ref_loss), (loss.item(), ref_loss)
+    assert rel_err(dz, ref_dz) < 5e-5
+
+
 @pytest.mark.parametrize("n,parts", [(5000, 2), (19_333, 3)])
 def test_gae_symmetric_decoder_pair_sharded(cuda, n, parts):
     """b2_gae_loss_grad_sym_f32: contiguous super-block ranges + row ranges of the label terms; the summed partial gradients and
