@@ -54,7 +54,7 @@ int b2_set_path(int which, int mode);
 int b2_get_path(int which);
 /* Scheduling knobs of the symmetric decoder (timing experiments; results do not depend on them). */
 #define B2_TUNE_GAE_STAGGER 0     /* initial delay (cycles) of the second elementwise group, default 1500 */
-#define B2_TUNE_GAE_LATE_GEMPTY 1 /* 1 (default): wait for the G buffer after the first half's math; 0: before loading S */
+#define B2_TUNE_GAE_LATE_GEMPTY 1 /* 0 (default, measured faster): wait for the G buffer before loading S; 1: after the first half's math */
 #define B2_TUNE_COUNT 2
 int b2_set_tuning(int which, int value);
 
