@@ -551,15 +551,17 @@ def main():
         # the exact N×N decoder is SFU/issue-bound; report it on the tensor roofline with its matmul flops (2·d per logit, S and G·Z)
         dec_flops = 2.0 * 2 * EMB * float(n_loc) * N
         ach = dec_flops / (dec_total * 1e-3) / 1e12 if dec_total else 0.0
-        roofline = {"kernel": "gae decoder (matrix-free z·zᵀ BCE: tcgen05 kind::f16 hi/lo split, S in TMEM)",
+        roofline = {"kernel": "gae_sym_kernel (matrix-free symmetric z·zᵀ BCE decoder: tcgen05 kind::f16 hi/lo split, S / dZ in TMEM, each "
+                              "unordered 128×128 tile computed once and used for both gradient blocks)",
                     "bound": "tensor", "achieved": ach,
                     "peak": peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"], "unit": "TFLOP/s",
-                    "frac": ach / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]), "traffic": traffic_from_profiles("gae_allpairs"),
+                    "frac": ach / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]), "traffic": traffic_from_profiles("gae_sym_kernel"),
                     "launches": dec_n, "ms_total": dec_total, "peak_source": peaks["source"],
                     "logits_per_s": float(n_loc) * N / (dec_total * 1e-3) if dec_total else None,
                     "note": "dominant kernel of the step; algorithmic flops = the two K=16 products per logit (S and G·Z) over ALL N² ordered "
-                            "pairs. Its real ceiling is the per-logit elementwise work (2 MUFU + ~9 ALU instructions), not the tensor pipe or "
-                            "HBM — see DESIGN.md §decoder and profiles/; roofline_spmm / roofline_gemm are the HBM- and tensor-bound kernels"}
+                            "pairs (the symmetric kernel evaluates each unordered pair once). Its real ceiling is the per-logit elementwise work "
+                            "(2 MUFU + ~11 ALU instructions per unordered logit), not the tensor pipe or HBM — see DESIGN.md §4.1 and "
+                            "profiles/r02_ncu_gae_sym.md; roofline_spmm / roofline_gemm are the HBM- and tensor-bound kernels"}
 
     cpu_baseline, matched = None, None
     if not args.no_cpu_baseline and world == 1:

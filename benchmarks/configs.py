@@ -74,10 +74,14 @@ def config3(args):
     sample = Data(AnnDataLite(X[:20000].cpu().numpy()))
     FeatureFeatureGraph(threshold=0.05, normalize_edges=True)(sample)
     graph = sample.data.uns["FeatureFeatureGraph"]
+    graph.ndata["feat"] = X.t().contiguous()       # node features of the gene graph = (log-)expression of ALL cells ([G, N], graphsci.py:126)
+    del sample
     model = GraphSCI(num_cells=N, num_genes=G, dataset="synthetic", dropout=0.1, gpu=0, seed=0, precision="tf32")
-    mask = torch.ones(N, G, dtype=torch.bool, device=dev)
     model._bind_graph(graph)
-    tm = mask.view(torch.uint8)
+    n_counts = Xraw.sum(1)
+    model.size_factors = (n_counts / torch.median(n_counts)).contiguous()      # what fit() sets up (graphsci.py:270-276)
+    model.lr, model.weight_decay = 1e-3, 1e-5
+    tm = torch.ones(N, G, dtype=torch.uint8, device=dev)
     for _ in range(2):
         model.train(X, Xraw, graph, tm, tm, le=1, la=1e-9, ke=1e2, ka=1)
     torch.cuda.synchronize()
