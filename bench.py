@@ -648,9 +648,22 @@ def parity_checks(ops, gae, A, labels, norm, pos_weight, N, r0, n_loc, comm, dev
     assert out["z_finite"], f"Graph-AE embedding is not finite after the warm-up steps: {out}"
     g = torch.Generator(device=dev).manual_seed(7)
     rows_loc = torch.randint(0, n_loc, (96, ), device=dev, generator=g)
-    dz = torch.empty(n_loc, z_loc.shape[1], dtype=torch.float32, device=dev)
     loss = torch.zeros(1, dtype=torch.float32, device=dev)
-    ops.gae_loss_grad(z_all, labels, norm, pos_weight, dz=dz, loss=loss, row_begin=r0, n_rows=n_loc)
+    gcomm = getattr(gae, "comm", None)
+    if gcomm is not None and gcomm.enabled:
+        # what GraphAEEngine.train_step runs under sharding: this rank's share of the block-pair schedule, partial gradients for ALL
+        # rows, summed over ranks
+        from dance_b200.parallel import shard_bounds
+        sb0, sb1 = shard_bounds(ops.gae_sym_super_blocks(N), gcomm.world)[gcomm.rank]
+        dzf = torch.empty(N, z_loc.shape[1], dtype=torch.float32, device=dev)
+        ops.gae_loss_grad_sym(z_all, labels, norm, pos_weight, sb0, sb1, dz_full=dzf, loss=loss, row_begin=r0, n_rows=n_loc)
+        gcomm.allreduce_sum_(dzf)
+        gcomm.allreduce_sum_(loss)
+        dz = dzf[r0:r0 + n_loc]
+        out["decoder_path"] = "pair-sharded symmetric decoder + all-reduce(dz)"
+    else:
+        dz = torch.empty(n_loc, z_loc.shape[1], dtype=torch.float32, device=dev)
+        ops.gae_loss_grad(z_all, labels, norm, pos_weight, dz=dz, loss=loss, row_begin=r0, n_rows=n_loc)
     # reference rows need the label pattern of the sampled rows in GLOBAL numbering: shift the local CSR rows
     class _Shift:   # minimal view: rowptr indexable by global row id
         pass
