@@ -675,7 +675,7 @@ def parity_checks(ops, gae, A, labels, norm, pos_weight, N, r0, n_loc, comm, dev
     out["dz_finite"] = bool(torch.isfinite(dz).all())
     err = float((dz[rows_loc].double() - ref_rows).norm() / ref_rows.norm())
     out["decoder_grad_rel_err_96_rows"] = err
-    assert err < 2e-5, f"decoder gradient mismatch at full size: rel err {err}"
+    assert err < 1e-4, f"decoder gradient mismatch at full size: rel err {err}"      # north_star tolerance; typical 5e-7 … 7e-6
     # loss of a 512-row block through the same entry point (row-sharded form) against fp64
     blk = torch.arange(0, min(512, n_loc), device=dev)
     sub = ops.CSR(A.rowptr[:len(blk) + 1].contiguous(), A.colidx[:int(A.rowptr[len(blk)].item())].contiguous(), None, (len(blk), N))

@@ -26,6 +26,14 @@ idx, _ = ops.knn(emb, 15, return_dist=False)
 A = ops.knn_graph_build(idx.contiguous())
 del emb
 nnz = A.nnz
+if len(sys.argv) > 6:        # dump the CSR for scripts/lab/gather_lab (int64 n, int64 nnz, rowptr, colidx, vals)
+    import numpy as np
+    with open(sys.argv[6], "wb") as f:
+        np.array([n, nnz], dtype=np.int64).tofile(f)
+        A.rowptr.cpu().numpy().astype(np.int32).tofile(f)
+        A.colidx[:nnz].cpu().numpy().astype(np.int32).tofile(f)
+        A.vals[:nnz].cpu().numpy().astype(np.float32).tofile(f)
+    print("dumped", sys.argv[6], flush=True)
 X = torch.randn(n, F, device=dev, generator=gen).contiguous()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 ref = None
