@@ -66,7 +66,7 @@ struct Params {
   double* loss_acc;
   int n, d, nb, sb_begin;
   float coef;
-  int stagger, late_gempty;      // b2_set_tuning knobs
+  int stagger, late_gempty, inorder_issue;      // b2_set_tuning knobs
 };
 
 // ---- sweep bookkeeping shared by all roles ----------------------------------------------------------------------------------
@@ -344,16 +344,55 @@ gae_sym_kernel(const __grid_constant__ Params p) {
           if (s % SEG_STEPS == SEG_STEPS - 1 || s == sw.n_steps - 1) { umma_commit(d1_full + 8 * sp); use_d1 ^= 1u << sp; }
         }
       };
-      // S runs two tiles ahead of the D products (the tensor pipe executes in order; see gae_tch.cu)
+      // Event-driven issue order.  S(k) only needs its S buffer back (the group has pulled S(k-2) into registers) and the Z_J stage;
+      // D(k) needs G(k) written and, at segment / step starts, drained accumulators.  A fixed program order (S(k+2), D(k), S(k+3), …)
+      // lets one not-yet-satisfied wait hold up work whose inputs are ready — measured: the elementwise warps spent 25 % of their
+      // time waiting for S and 11 % for their G buffer, both groups at once (profiles/r02_ncu_gae_sym.md) — so the issuer probes the
+      // barriers of both queues and issues whatever can go.  The tensor pipe still executes in issue order; every commit covers all
+      // earlier MMAs, which is conservative for both queues.
+      auto s_ready = [&](int s, int q) {
+        return mbar_test(s_empty + 8 * q, ((cnt_s >> q) & 1u) ^ 1u) && mbar_test(full_bar + 8 * (s % STAGES), (s / STAGES) & 1);
+      };
+      auto d_ready = [&](int s, int g, int q) {
+        if (!mbar_test(g_full + 8 * q, (cnt_d >> q) & 1u)) return false;
+        const int seg = s / SEG_STEPS, sp = seg & 1;
+        if (seg != cur_seg && !mbar_test(d1_empty + 8 * sp, ((use_d1 >> sp) & 1u) ^ 1u)) return false;
+        if (!sw.diag(g, s)) {
+          const int b3 = s % 3;
+          const bool first = (g == 0) || !(sw.active(0, s) && !sw.diag(0, s));
+          if (first && !mbar_test(d2_empty + 8 * b3, ((use_d2 >> b3) & 1u) ^ 1u)) return false;
+        }
+        return true;
+      };
       int ss = 0, sg = -1, sk = 0, ds = 0, dg = -1, dk = 0;     // (step, block, sequence index) of the next S / D tile
       next_tile(ss, sg);
       next_tile(ds, dg);
-      for (int pre = 0; pre < 2 && ss < sw.n_steps; ++pre) { issue_s(ss, sg, sk & 1); ++sk; next_tile(ss, sg); }
-      while (ds < sw.n_steps) {
-        if (ss < sw.n_steps) { issue_s(ss, sg, sk & 1); ++sk; next_tile(ss, sg); }
-        issue_d(ds, dg, dk & 1);
-        ++dk;
-        next_tile(ds, dg);
+      if (p.inorder_issue) {
+        // S two tiles ahead of the D products, fixed order (kept for A/B timing)
+        for (int pre = 0; pre < 2 && ss < sw.n_steps; ++pre) { issue_s(ss, sg, sk & 1); ++sk; next_tile(ss, sg); }
+        while (ds < sw.n_steps) {
+          if (ss < sw.n_steps) { issue_s(ss, sg, sk & 1); ++sk; next_tile(ss, sg); }
+          issue_d(ds, dg, dk & 1);
+          ++dk;
+          next_tile(ds, dg);
+        }
+      } else {
+        while (ds < sw.n_steps) {
+          bool did = false;
+          if (ss < sw.n_steps && sk - dk < 3 && s_ready(ss, sk & 1)) {
+            issue_s(ss, sg, sk & 1);
+            ++sk;
+            next_tile(ss, sg);
+            did = true;
+          }
+          if (d_ready(ds, dg, dk & 1)) {
+            issue_d(ds, dg, dk & 1);
+            ++dk;
+            next_tile(ds, dg);
+            did = true;
+          }
+          if (!did) __nanosleep(20);
+        }
       }
     }
     __syncwarp();
@@ -615,6 +654,7 @@ int launch(const float* z, int64_t ldz, int32_t n, int32_t d, int32_t sb_begin, 
             make_tensor_map_f16_ex(&p.mT_lo, ztl, (uint64_t)npad, DW, (uint64_t)npad, 64, DW, SW128);
   if (!ok) return B2_ERR_UNSUPPORTED;
   p.stagger = tuning(B2_TUNE_GAE_STAGGER); p.late_gempty = tuning(B2_TUNE_GAE_LATE_GEMPTY);
+  p.inorder_issue = tuning(B2_TUNE_GAE_INORDER_ISSUE);
   p.scale = scale; p.dz = dz; p.loss_acc = loss_acc; p.n = n; p.d = d; p.nb = (int)(npad / BT); p.sb_begin = sb_begin; p.coef = coef;
   if (sb_end <= sb_begin) return B2_OK;
   const size_t smem = SMEM_BYTES + 1024 + 256;
