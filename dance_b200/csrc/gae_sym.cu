@@ -67,7 +67,23 @@ struct Params {
   int n, d, nb, sb_begin;
   float coef;
   int stagger, late_gempty, inorder_issue;      // b2_set_tuning knobs
+#ifdef B2_GAE_TRACE
+  unsigned long long* trace;     // lab build only (scripts/lab/build_trace.sh): clock64 stamps of CTA 0's roles
+  int trace_tiles;
+#endif
 };
+
+#ifdef B2_GAE_TRACE
+// agent: 0/1 elementwise group, 2 S issue, 3 D issue, 4 dZ_J flush;  8 stamps per (agent, index)
+#define B2_TRACE(agent, idx, field)                                                                          \
+  do {                                                                                                       \
+    if (p.trace && blockIdx.x == 0 && (idx) < p.trace_tiles) p.trace[((agent) * p.trace_tiles + (idx)) * 8 + (field)] = clock64(); \
+  } while (0)
+unsigned long long* g_trace = nullptr;
+int g_trace_tiles = 0;
+#else
+#define B2_TRACE(agent, idx, field) do { } while (0)
+#endif
 
 // ---- sweep bookkeeping shared by all roles ----------------------------------------------------------------------------------
 struct Sweep {
@@ -272,6 +288,7 @@ gae_sym_kernel(const __grid_constant__ Params p) {
       // per-group / per-buffer phase counters packed into scalars (dynamic indexing of local arrays would put them on the stack)
       uint32_t cnt_s = 0, cnt_d = 0, use_d2 = 0, use_d1 = 0, d1_fresh = 0;   // bit q / b3 / segment parity = phase (or flag) of that slot
       int cur_seg = -1;
+      int ss = 0, sg = -1, sk = 0, ds = 0, dg = -1, dk = 0;     // (step, block, sequence index) of the next S / D tile
       auto next_tile = [&](int& s, int& g) {              // advance to the next active tile (s == n_steps: end)
         do { if (++g == 2) { g = 0; ++s; } } while (s < sw.n_steps && !sw.active(g, s));
       };
@@ -281,9 +298,12 @@ gae_sym_kernel(const __grid_constant__ Params p) {
       // read S(t+1), which waits for G's buffer, which waits for D(t) — queued behind S(t+2)).
       auto issue_s = [&](int s, int g, int q) {
         const int stage = s % STAGES;
+        B2_TRACE(2, sk, 0);
         mbar_wait(s_empty + 8 * q, ((cnt_s >> q) & 1u) ^ 1u);
+        B2_TRACE(2, sk, 1);
         mbar_wait(full_bar + 8 * stage, (s / STAGES) & 1);
         tc_fence_after();
+        B2_TRACE(2, sk, 2);
         const uint32_t st = s_ring + stage * STAGE_BYTES, zi = s_zi + g * ZI_BYTES;
         const uint32_t d_s = tmem + TM_S + (uint32_t)(q * BT);
         // SWIZZLE_32B K-major: 32-byte rows (the whole K = 16), 8-row groups 256 B apart — one k-step
@@ -297,8 +317,10 @@ gae_sym_kernel(const __grid_constant__ Params p) {
       };
       auto issue_d = [&](int s, int g, int q) {
         const int stage = s % STAGES;
+        B2_TRACE(3, dk, 0);
         mbar_wait(g_full + 8 * q, (cnt_d >> q) & 1u);
         tc_fence_after();
+        B2_TRACE(3, dk, 1);
         const uint32_t g_hi = s_g + q * G_BYTES, g_lo = g_hi + G_PLANE;
         const uint32_t zt_j = s_ring + stage * STAGE_BYTES + 2 * ZA_BYTES;
         const int seg = s / SEG_STEPS, sp = seg & 1;
@@ -337,6 +359,7 @@ gae_sym_kernel(const __grid_constant__ Params p) {
           }
         }
         umma_commit(g_empty + 8 * q);
+        B2_TRACE(3, dk, 2);
         cnt_d ^= 1u << q;
         if (sw.last_of_step(g, s)) {
           umma_commit(stage_free + 8 * stage);
@@ -364,7 +387,6 @@ gae_sym_kernel(const __grid_constant__ Params p) {
         }
         return true;
       };
-      int ss = 0, sg = -1, sk = 0, ds = 0, dg = -1, dk = 0;     // (step, block, sequence index) of the next S / D tile
       next_tile(ss, sg);
       next_tile(ds, dg);
       if (p.inorder_issue) {
@@ -426,9 +448,13 @@ gae_sym_kernel(const __grid_constant__ Params p) {
         const bool masked = ragged && (I == p.nb - 1 || J == p.nb - 1);
         const bool row_ok = !(ragged && I == p.nb - 1 && row >= n_last);
         const int col_end = (ragged && J == p.nb - 1) ? n_last : BT;       // valid columns of this tile
+        const bool tr = (sub == 0 && half == 0 && lane == 0);
+        if (tr) B2_TRACE(q, ng, 0);
         mbar_wait(s_full + 8 * q, ng & 1);
         tc_fence_after();
+        if (tr) B2_TRACE(q, ng, 1);
         if (!p.late_gempty) mbar_wait(g_empty + 8 * q, (ng & 1) ^ 1);
+        if (tr) B2_TRACE(q, ng, 2);
         float abs_t = 0.f, lg_t = 0.f;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -486,6 +512,7 @@ gae_sym_kernel(const __grid_constant__ Params p) {
           // G[q] may be overwritten once the D-MMAs of this group's previous tile have read it: waited for as late as possible
           // (after the first half's math), so the group is not idle while the tensor pipe drains the previous tile
           if (hh == 0 && p.late_gempty) mbar_wait(g_empty + 8 * q, (ng & 1) ^ 1);
+          if (tr) B2_TRACE(q, ng, 3 + hh);
           // 16-byte chunk c of this thread's 128-byte row holds columns 8c..8c+7; swizzle: chunk ^= row % 8
           const uint32_t cb = (uint32_t)hh * 4u;
           sts_v4(g_hi + (((cb + 0) ^ xr) << 4), hi0[0], hi0[1], hi0[2], hi0[3]);
@@ -500,6 +527,7 @@ gae_sym_kernel(const __grid_constant__ Params p) {
         fence_proxy_async();                                               // generic-proxy stores → visible to the tensor core's async proxy
         __syncwarp();
         if (lane == 0) mbar_arrive(g_full + 8 * q);
+        if (tr) B2_TRACE(q, ng, 5);
         abs_w += (float)wgt * abs_t;
         lg_w += (float)wgt * lg_t;
         chunks_w += wgt * 4;
@@ -539,8 +567,10 @@ gae_sym_kernel(const __grid_constant__ Params p) {
     for (int s = 0; s < sw.n_steps; ++s) {
       if (sw.has_d2(s)) {
         const int b3 = s % 3;
+        if (sub == 0 && lane == 0) B2_TRACE(4, s, 0);
         mbar_wait(d2_full + 8 * b3, (fcnt >> b3) & 1u);
         tc_fence_after();
+        if (sub == 0 && lane == 0) B2_TRACE(4, s, 1);
         uint32_t a0[16], a1[16];
         tmem_ld_32x32b_x16(tmem + lane_off + TM_D2 + (uint32_t)(b3 * 2 * DW), a0);
         tmem_ld_32x32b_x16(tmem + lane_off + TM_D2 + (uint32_t)(b3 * 2 * DW + DW), a1);
@@ -549,6 +579,7 @@ gae_sym_kernel(const __grid_constant__ Params p) {
         if (lane == 0) mbar_arrive(d2_empty + 8 * b3);
         fcnt ^= 1u << b3;
         add_rows(sw.J(s), a0, a1);
+        if (sub == 0 && lane == 0) B2_TRACE(4, s, 2);
       }
       if (s % SEG_STEPS == SEG_STEPS - 1 || s == sw.n_steps - 1) {
         // a dZ_I segment is complete: [G·Z_hi | G·Z_lo] of both owned blocks → global (atomic: other CTAs add to the same rows)
@@ -656,6 +687,9 @@ int launch(const float* z, int64_t ldz, int32_t n, int32_t d, int32_t sb_begin, 
   p.stagger = tuning(B2_TUNE_GAE_STAGGER); p.late_gempty = tuning(B2_TUNE_GAE_LATE_GEMPTY);
   p.inorder_issue = tuning(B2_TUNE_GAE_INORDER_ISSUE);
   p.scale = scale; p.dz = dz; p.loss_acc = loss_acc; p.n = n; p.d = d; p.nb = (int)(npad / BT); p.sb_begin = sb_begin; p.coef = coef;
+#ifdef B2_GAE_TRACE
+  p.trace = g_trace; p.trace_tiles = g_trace_tiles;
+#endif
   if (sb_end <= sb_begin) return B2_OK;
   const size_t smem = SMEM_BYTES + 1024 + 256;
   static bool attr_set = false;
@@ -673,3 +707,11 @@ int launch(const float* z, int64_t ldz, int32_t n, int32_t d, int32_t sb_begin, 
 
 }  // namespace gsym
 }  // namespace b2
+
+#ifdef B2_GAE_TRACE
+extern "C" int b2_debug_gae_sym_trace(unsigned long long* buf, int tiles) {
+  b2::gsym::g_trace = buf;
+  b2::gsym::g_trace_tiles = tiles;
+  return 0;
+}
+#endif
