@@ -66,7 +66,7 @@ struct Params {
   double* loss_acc;
   int n, d, nb, sb_begin;
   float coef;
-  int stagger, late_gempty, inorder_issue;      // b2_set_tuning knobs
+  int stagger, late_gempty;      // b2_set_tuning knobs
 #ifdef B2_GAE_TRACE
   unsigned long long* trace;     // lab build only (scripts/lab/build_trace.sh): clock64 stamps of CTA 0's roles
   int trace_tiles;
@@ -278,8 +278,12 @@ gae_sym_kernel(const __grid_constant__ Params p) {
           tma_load_2d(st + 2 * ZA_BYTES + jb * 2 * ZT_BOX + ZT_BOX, &p.mT_lo, fb, c0 + jb * 64, 0);
         }
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
       // ===================== MMA issuer =====================
+      // The WHOLE warp runs this role (waits and bookkeeping are warp-uniform); tcgen05.mma / commit are issued by one elected lane
+      // inside the asm.  Issued from a divergent `lane == 0` branch, every MMA cost ~14 SASS instructions (an ELECT / BRA.U.ANY loop
+      // plus descriptor arithmetic): the 32 gradient MMAs of a tile took 2 500 cycles to ISSUE — the elementwise warps spent 48 % of
+      // their time waiting for the issuer (clock64 trace, profiles/r02_sym_trace.md), not for the tensor pipe.
       const uint32_t idesc_s = umma_idesc_f16(BT, BT, 0, 0);        // S    = Z_I (K-major, K = 16) · Z_J (K-major)
       const uint32_t idesc_d1 = umma_idesc_f16(BT, 2 * DW, 0, 0);   // dZ_I = G  (K-major A,  K = j) · [Z_hi | Z_lo]_J
       const uint32_t idesc_d2 = umma_idesc_f16(BT, 2 * DW, 1, 0);   // dZ_J = Gᵀ (MN-major A, K = i) · [Z_hi | Z_lo]_I
@@ -292,36 +296,38 @@ gae_sym_kernel(const __grid_constant__ Params p) {
       auto next_tile = [&](int& s, int& g) {              // advance to the next active tile (s == n_steps: end)
         do { if (++g == 2) { g = 0; ++s; } } while (s < sw.n_steps && !sw.active(g, s));
       };
+      // A descriptor's start-address field counts 16-byte units in its low 14 bits and shared memory is < 256 KB, so a byte offset is
+      // added to a base descriptor as (offset >> 4) without touching the other fields.
+      auto adv = [](uint64_t desc, uint32_t byte_off) { return desc + (uint64_t)(byte_off >> 4); };
       // g = which owned block the tile belongs to (operands, dZ_I accumulator); q = parity of the tile in the CTA's tile sequence =
       // elementwise group / S buffer / G buffer.  Alternating by SEQUENCE (not by block) guarantees that consecutive tiles never
       // share a group: with two tiles of one group in a row the S-two-ahead order would deadlock (S(t+2) needs the group to have
       // read S(t+1), which waits for G's buffer, which waits for D(t) — queued behind S(t+2)).
       auto issue_s = [&](int s, int g, int q) {
         const int stage = s % STAGES;
-        B2_TRACE(2, sk, 0);
+        if (lane == 0) B2_TRACE(2, sk, 0);
         mbar_wait(s_empty + 8 * q, ((cnt_s >> q) & 1u) ^ 1u);
-        B2_TRACE(2, sk, 1);
+        if (lane == 0) B2_TRACE(2, sk, 1);
         mbar_wait(full_bar + 8 * stage, (s / STAGES) & 1);
         tc_fence_after();
-        B2_TRACE(2, sk, 2);
+        if (lane == 0) B2_TRACE(2, sk, 2);
         const uint32_t st = s_ring + stage * STAGE_BYTES, zi = s_zi + g * ZI_BYTES;
         const uint32_t d_s = tmem + TM_S + (uint32_t)(q * BT);
         // SWIZZLE_32B K-major: 32-byte rows (the whole K = 16), 8-row groups 256 B apart — one k-step
-        const uint64_t a_hi = umma_desc(zi, 16, 256, 6), a_lo = umma_desc(zi + ZA_BYTES, 16, 256, 6);
-        const uint64_t b_hi = umma_desc(st, 16, 256, 6), b_lo = umma_desc(st + ZA_BYTES, 16, 256, 6);
-        umma_f16(d_s, a_lo, b_hi, idesc_s, 0);
-        umma_f16(d_s, a_hi, b_lo, idesc_s, 1);
-        umma_f16(d_s, a_hi, b_hi, idesc_s, 1);
-        umma_commit(s_full + 8 * q);
+        const uint64_t a_hi = umma_desc(zi, 16, 256, 6), a_lo = adv(a_hi, ZA_BYTES);
+        const uint64_t b_hi = umma_desc(st, 16, 256, 6), b_lo = adv(b_hi, ZA_BYTES);
+        umma_f16_elect(d_s, a_lo, b_hi, idesc_s, 0);
+        umma_f16_elect(d_s, a_hi, b_lo, idesc_s, 1);
+        umma_f16_elect(d_s, a_hi, b_hi, idesc_s, 1);
+        umma_commit_elect(s_full + 8 * q);
         cnt_s ^= 1u << q;
       };
       auto issue_d = [&](int s, int g, int q) {
         const int stage = s % STAGES;
-        B2_TRACE(3, dk, 0);
+        if (lane == 0) B2_TRACE(3, dk, 0);
         mbar_wait(g_full + 8 * q, (cnt_d >> q) & 1u);
         tc_fence_after();
-        B2_TRACE(3, dk, 1);
-        const uint32_t g_hi = s_g + q * G_BYTES, g_lo = g_hi + G_PLANE;
+        if (lane == 0) B2_TRACE(3, dk, 1);
         const uint32_t zt_j = s_ring + stage * STAGE_BYTES + 2 * ZA_BYTES;
         const int seg = s / SEG_STEPS, sp = seg & 1;
         if (seg != cur_seg) {                    // first dZ_I product of a new segment: its TMEM buffers must have been drained
@@ -331,13 +337,16 @@ gae_sym_kernel(const __grid_constant__ Params p) {
           d1_fresh = 3u;                         // both blocks start the segment with accumulate = 0
         }
         const uint32_t d1 = tmem + TM_D1 + (uint32_t)((sp * 2 + g) * 2 * DW);
+        // K-major SWIZZLE_128B view of G: 64 j per 128-byte row, 8-row groups 1 KB apart; k-step = 32 B inside the row, 64-column blocks
+        // 16 KB apart.  [Z_hi | Z_lo]_J (N = 32): same layout, 64-column blocks 2·ZT_BOX apart.
+        const uint64_t ga_hi = umma_desc(s_g + q * G_BYTES, 16, 1024, 2), ga_lo = adv(ga_hi, G_PLANE);
+        const uint64_t zb_j = umma_desc(zt_j, 16, 1024, 2);
 #pragma unroll
         for (int ks = 0; ks < BT / 16; ++ks) {
-          // K-major SWIZZLE_128B: 64 j per 128-byte row, 8-row groups 1 KB apart; k-step = 32 B inside the row, 64-column blocks 16 KB apart
           const uint32_t koff = (uint32_t)(ks >> 2) * (BT * 128) + (uint32_t)(ks & 3) * 32u;
-          const uint64_t b = umma_desc(zt_j + (uint32_t)(ks >> 2) * (2 * ZT_BOX) + (uint32_t)(ks & 3) * 32u, 16, 1024, 2);
-          umma_f16(d1, umma_desc(g_hi + koff, 16, 1024, 2), b, idesc_d1, (!((d1_fresh >> g) & 1u) || ks > 0) ? 1u : 0u);
-          umma_f16(d1, umma_desc(g_lo + koff, 16, 1024, 2), b, idesc_d1, 1);
+          const uint64_t b = adv(zb_j, (uint32_t)(ks >> 2) * (2 * ZT_BOX) + (uint32_t)(ks & 3) * 32u);
+          umma_f16_elect(d1, adv(ga_hi, koff), b, idesc_d1, (!((d1_fresh >> g) & 1u) || ks > 0) ? 1u : 0u);
+          umma_f16_elect(d1, adv(ga_lo, koff), b, idesc_d1, 1);
         }
         d1_fresh &= ~(1u << g);
         if (!sw.diag(g, s)) {
@@ -348,73 +357,36 @@ gae_sym_kernel(const __grid_constant__ Params p) {
             tc_fence_after();
           }
           const uint32_t d2 = tmem + TM_D2 + (uint32_t)(b3 * 2 * DW);
-          const uint32_t zt_i = s_zi + g * ZI_BYTES + 2 * ZA_BYTES;
+          // MN-major SWIZZLE_128B over the SAME bytes of G: 64 j (M) contiguous per 128-byte row, k-step = 16 rows (i) = 2 KB,
+          // 8-row groups (SBO) 1 KB apart, the second 64-j block (LBO) 16 KB further
+          const uint64_t gt_hi = umma_desc(s_g + q * G_BYTES, BT * 128, 1024, 2), gt_lo = adv(gt_hi, G_PLANE);
+          const uint64_t zb_i = umma_desc(s_zi + g * ZI_BYTES + 2 * ZA_BYTES, 16, 1024, 2);
 #pragma unroll
           for (int ks = 0; ks < BT / 16; ++ks) {
-            // MN-major SWIZZLE_128B over the SAME bytes: 64 j (M) contiguous per 128-byte row, k-step = 16 rows (i) = 2 KB,
-            // 8-row groups (SBO) 1 KB apart, the second 64-j block (LBO) 16 KB further
-            const uint64_t b = umma_desc(zt_i + (uint32_t)(ks >> 2) * (2 * ZT_BOX) + (uint32_t)(ks & 3) * 32u, 16, 1024, 2);
-            umma_f16(d2, umma_desc(g_hi + (uint32_t)ks * 2048u, BT * 128, 1024, 2), b, idesc_d2, (!first || ks > 0) ? 1u : 0u);
-            umma_f16(d2, umma_desc(g_lo + (uint32_t)ks * 2048u, BT * 128, 1024, 2), b, idesc_d2, 1);
+            const uint64_t b = adv(zb_i, (uint32_t)(ks >> 2) * (2 * ZT_BOX) + (uint32_t)(ks & 3) * 32u);
+            umma_f16_elect(d2, adv(gt_hi, (uint32_t)ks * 2048u), b, idesc_d2, (!first || ks > 0) ? 1u : 0u);
+            umma_f16_elect(d2, adv(gt_lo, (uint32_t)ks * 2048u), b, idesc_d2, 1);
           }
         }
-        umma_commit(g_empty + 8 * q);
-        B2_TRACE(3, dk, 2);
+        umma_commit_elect(g_empty + 8 * q);
+        if (lane == 0) B2_TRACE(3, dk, 2);
         cnt_d ^= 1u << q;
         if (sw.last_of_step(g, s)) {
-          umma_commit(stage_free + 8 * stage);
-          if (sw.has_d2(s)) { umma_commit(d2_full + 8 * (s % 3)); use_d2 ^= 1u << (s % 3); }
-          if (s % SEG_STEPS == SEG_STEPS - 1 || s == sw.n_steps - 1) { umma_commit(d1_full + 8 * sp); use_d1 ^= 1u << sp; }
+          umma_commit_elect(stage_free + 8 * stage);
+          if (sw.has_d2(s)) { umma_commit_elect(d2_full + 8 * (s % 3)); use_d2 ^= 1u << (s % 3); }
+          if (s % SEG_STEPS == SEG_STEPS - 1 || s == sw.n_steps - 1) { umma_commit_elect(d1_full + 8 * sp); use_d1 ^= 1u << sp; }
         }
       };
-      // Event-driven issue order.  S(k) only needs its S buffer back (the group has pulled S(k-2) into registers) and the Z_J stage;
-      // D(k) needs G(k) written and, at segment / step starts, drained accumulators.  A fixed program order (S(k+2), D(k), S(k+3), …)
-      // lets one not-yet-satisfied wait hold up work whose inputs are ready — measured: the elementwise warps spent 25 % of their
-      // time waiting for S and 11 % for their G buffer, both groups at once (profiles/r02_ncu_gae_sym.md) — so the issuer probes the
-      // barriers of both queues and issues whatever can go.  The tensor pipe still executes in issue order; every commit covers all
-      // earlier MMAs, which is conservative for both queues.
-      auto s_ready = [&](int s, int q) {
-        return mbar_test(s_empty + 8 * q, ((cnt_s >> q) & 1u) ^ 1u) && mbar_test(full_bar + 8 * (s % STAGES), (s / STAGES) & 1);
-      };
-      auto d_ready = [&](int s, int g, int q) {
-        if (!mbar_test(g_full + 8 * q, (cnt_d >> q) & 1u)) return false;
-        const int seg = s / SEG_STEPS, sp = seg & 1;
-        if (seg != cur_seg && !mbar_test(d1_empty + 8 * sp, ((use_d1 >> sp) & 1u) ^ 1u)) return false;
-        if (!sw.diag(g, s)) {
-          const int b3 = s % 3;
-          const bool first = (g == 0) || !(sw.active(0, s) && !sw.diag(0, s));
-          if (first && !mbar_test(d2_empty + 8 * b3, ((use_d2 >> b3) & 1u) ^ 1u)) return false;
-        }
-        return true;
-      };
+      // S runs two tiles ahead of the gradient products (the tensor pipe executes in order).  An event-driven order — issue whichever
+      // queue has its inputs ready — was measured 7 % slower (the probes cost the issuer more than head-of-line blocking does).
       next_tile(ss, sg);
       next_tile(ds, dg);
-      if (p.inorder_issue) {
-        // S two tiles ahead of the D products, fixed order (kept for A/B timing)
-        for (int pre = 0; pre < 2 && ss < sw.n_steps; ++pre) { issue_s(ss, sg, sk & 1); ++sk; next_tile(ss, sg); }
-        while (ds < sw.n_steps) {
-          if (ss < sw.n_steps) { issue_s(ss, sg, sk & 1); ++sk; next_tile(ss, sg); }
-          issue_d(ds, dg, dk & 1);
-          ++dk;
-          next_tile(ds, dg);
-        }
-      } else {
-        while (ds < sw.n_steps) {
-          bool did = false;
-          if (ss < sw.n_steps && sk - dk < 3 && s_ready(ss, sk & 1)) {
-            issue_s(ss, sg, sk & 1);
-            ++sk;
-            next_tile(ss, sg);
-            did = true;
-          }
-          if (d_ready(ds, dg, dk & 1)) {
-            issue_d(ds, dg, dk & 1);
-            ++dk;
-            next_tile(ds, dg);
-            did = true;
-          }
-          if (!did) __nanosleep(20);
-        }
+      for (int pre = 0; pre < 2 && ss < sw.n_steps; ++pre) { issue_s(ss, sg, sk & 1); ++sk; next_tile(ss, sg); }
+      while (ds < sw.n_steps) {
+        if (ss < sw.n_steps) { issue_s(ss, sg, sk & 1); ++sk; next_tile(ss, sg); }
+        issue_d(ds, dg, dk & 1);
+        ++dk;
+        next_tile(ds, dg);
       }
     }
     __syncwarp();
@@ -685,7 +657,6 @@ int launch(const float* z, int64_t ldz, int32_t n, int32_t d, int32_t sb_begin, 
             make_tensor_map_f16_ex(&p.mT_lo, ztl, (uint64_t)npad, DW, (uint64_t)npad, 64, DW, SW128);
   if (!ok) return B2_ERR_UNSUPPORTED;
   p.stagger = tuning(B2_TUNE_GAE_STAGGER); p.late_gempty = tuning(B2_TUNE_GAE_LATE_GEMPTY);
-  p.inorder_issue = tuning(B2_TUNE_GAE_INORDER_ISSUE);
   p.scale = scale; p.dz = dz; p.loss_acc = loss_acc; p.n = n; p.d = d; p.nb = (int)(npad / BT); p.sb_begin = sb_begin; p.coef = coef;
 #ifdef B2_GAE_TRACE
   p.trace = g_trace; p.trace_tiles = g_trace_tiles;

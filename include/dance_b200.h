@@ -55,8 +55,7 @@ int b2_get_path(int which);
 /* Scheduling knobs of the symmetric decoder (timing experiments; results do not depend on them). */
 #define B2_TUNE_GAE_STAGGER 0     /* initial delay (cycles) of the second elementwise group, default 1500 */
 #define B2_TUNE_GAE_LATE_GEMPTY 1 /* 0 (default, measured faster): wait for the G buffer before loading S; 1: after the first half's math */
-#define B2_TUNE_GAE_INORDER_ISSUE 2 /* 0 (default): the MMA issuer issues whichever of its two queues (S products, gradient products) is ready; 1: fixed order */
-#define B2_TUNE_COUNT 3
+#define B2_TUNE_COUNT 2
 int b2_set_tuning(int which, int value);
 
 const char* b2_last_error(void);

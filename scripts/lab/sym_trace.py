@@ -27,8 +27,7 @@ h.b2_debug_gae_sym_trace.restype = C.c_int
 h.b2_debug_gae_sym_trace.argtypes = [C.c_void_p, C.c_int]
 buf = torch.zeros(5 * T * 8, dtype=torch.int64, device=dev)
 (ROOT / "gpurun_out").mkdir(exist_ok=True)
-for mode, knobs in (("inorder", {"gae_inorder_issue": 1, "gae_late_gempty": 0}), ("event", {"gae_inorder_issue": 0, "gae_late_gempty": 0}),
-                    ("inorder_late", {"gae_inorder_issue": 1, "gae_late_gempty": 1})):
+for mode, knobs in (("early_gwait", {"gae_late_gempty": 0}), ("late_gwait", {"gae_late_gempty": 1})):
     for k, v in knobs.items():
         ops.set_tuning(k, v)
     ops.gae_loss_grad(z, L, 0.5, 100.0)

@@ -28,14 +28,11 @@ def t():
     return s.elapsed_time(e) / 3
 
 
-for inorder in (1, 0):
-    ops.set_tuning("gae_inorder_issue", inorder)
-    for late in (0, 1):
-        ops.set_tuning("gae_late_gempty", late)
-        for stag in (0, 1500):
-            ops.set_tuning("gae_stagger", stag)
-            print(f"n={n} inorder_issue={inorder} late_gempty={late} stagger={stag}: {t():.2f} ms", flush=True)
-ops.set_tuning("gae_inorder_issue", 0)
+for late in (0, 1):
+    ops.set_tuning("gae_late_gempty", late)
+    for stag in (0, 1500):
+        ops.set_tuning("gae_stagger", stag)
+        print(f"n={n} late_gempty={late} stagger={stag}: {t():.2f} ms", flush=True)
 ops.set_tuning("gae_late_gempty", 0)
 ops.set_tuning("gae_stagger", 1500)
 # large-magnitude embedding: the scaled-operand variant
