@@ -278,21 +278,17 @@ gae_sym_kernel(const __grid_constant__ Params p) {
           tma_load_2d(st + 2 * ZA_BYTES + jb * 2 * ZT_BOX + ZT_BOX, &p.mT_lo, fb, c0 + jb * 64, 0);
         }
       }
-    } else if (warp == 1) {
-      // ===================== MMA issuer =====================
-      // The WHOLE warp runs this role (waits and bookkeeping are warp-uniform); tcgen05.mma / commit are issued by one elected lane
-      // inside the asm.  Issued from a divergent `lane == 0` branch, every MMA cost ~14 SASS instructions (an ELECT / BRA.U.ANY loop
-      // plus descriptor arithmetic): the 32 gradient MMAs of a tile took 2 500 cycles to ISSUE — the elementwise warps spent 48 % of
-      // their time waiting for the issuer (clock64 trace, profiles/r02_sym_trace.md), not for the tensor pipe.
-      const uint32_t idesc_s = umma_idesc_f16(BT, BT, 0, 0);        // S    = Z_I (K-major, K = 16) · Z_J (K-major)
-      const uint32_t idesc_d1 = umma_idesc_f16(BT, 2 * DW, 0, 0);   // dZ_I = G  (K-major A,  K = j) · [Z_hi | Z_lo]_J
-      const uint32_t idesc_d2 = umma_idesc_f16(BT, 2 * DW, 1, 0);   // dZ_J = Gᵀ (MN-major A, K = i) · [Z_hi | Z_lo]_I
+    } else if (warp == 1 || warp == 3) {
+      // ===================== MMA issuers: warp 1 issues the S products, warp 3 the gradient products =====================
+      // Each WHOLE warp runs its role (waits and bookkeeping are warp-uniform); tcgen05.mma / commit are issued by one elected lane
+      // inside the asm.  History (clock64 traces, profiles/r02_sym_trace.md): one thread issuing everything from a divergent
+      // `lane == 0` branch spent 2 500 cycles ISSUING the 32 gradient MMAs of a tile (~14 SASS instructions per MMA: an ELECT /
+      // BRA.U.ANY loop plus descriptor arithmetic), the elementwise warps waited 48 % of the time; warp-uniform issue: 1 850 cycles —
+      // the issuer shares its scheduler with four busy elementwise warps and gets roughly every fifth issue slot — and it was still
+      // the busiest role (S + gradient products + bookkeeping = the whole tile period).  The two queues are independent (different
+      // TMEM regions and shared-memory buffers, every hand-over is an mbarrier), so they run on two warps of two schedulers.
       mbar_wait(zi_bar, 0);
       tc_fence_after();
-      // per-group / per-buffer phase counters packed into scalars (dynamic indexing of local arrays would put them on the stack)
-      uint32_t cnt_s = 0, cnt_d = 0, use_d2 = 0, use_d1 = 0, d1_fresh = 0;   // bit q / b3 / segment parity = phase (or flag) of that slot
-      int cur_seg = -1;
-      int ss = 0, sg = -1, sk = 0, ds = 0, dg = -1, dk = 0;     // (step, block, sequence index) of the next S / D tile
       auto next_tile = [&](int& s, int& g) {              // advance to the next active tile (s == n_steps: end)
         do { if (++g == 2) { g = 0; ++s; } } while (s < sw.n_steps && !sw.active(g, s));
       };
@@ -300,93 +296,96 @@ gae_sym_kernel(const __grid_constant__ Params p) {
       // added to a base descriptor as (offset >> 4) without touching the other fields.
       auto adv = [](uint64_t desc, uint32_t byte_off) { return desc + (uint64_t)(byte_off >> 4); };
       // g = which owned block the tile belongs to (operands, dZ_I accumulator); q = parity of the tile in the CTA's tile sequence =
-      // elementwise group / S buffer / G buffer.  Alternating by SEQUENCE (not by block) guarantees that consecutive tiles never
-      // share a group: with two tiles of one group in a row the S-two-ahead order would deadlock (S(t+2) needs the group to have
-      // read S(t+1), which waits for G's buffer, which waits for D(t) — queued behind S(t+2)).
-      auto issue_s = [&](int s, int g, int q) {
-        const int stage = s % STAGES;
-        if (lane == 0) B2_TRACE(2, sk, 0);
-        mbar_wait(s_empty + 8 * q, ((cnt_s >> q) & 1u) ^ 1u);
-        if (lane == 0) B2_TRACE(2, sk, 1);
-        mbar_wait(full_bar + 8 * stage, (s / STAGES) & 1);
-        tc_fence_after();
-        if (lane == 0) B2_TRACE(2, sk, 2);
-        const uint32_t st = s_ring + stage * STAGE_BYTES, zi = s_zi + g * ZI_BYTES;
-        const uint32_t d_s = tmem + TM_S + (uint32_t)(q * BT);
-        // SWIZZLE_32B K-major: 32-byte rows (the whole K = 16), 8-row groups 256 B apart — one k-step
-        const uint64_t a_hi = umma_desc(zi, 16, 256, 6), a_lo = adv(a_hi, ZA_BYTES);
-        const uint64_t b_hi = umma_desc(st, 16, 256, 6), b_lo = adv(b_hi, ZA_BYTES);
-        umma_f16_elect(d_s, a_lo, b_hi, idesc_s, 0);
-        umma_f16_elect(d_s, a_hi, b_lo, idesc_s, 1);
-        umma_f16_elect(d_s, a_hi, b_hi, idesc_s, 1);
-        umma_commit_elect(s_full + 8 * q);
-        cnt_s ^= 1u << q;
-      };
-      auto issue_d = [&](int s, int g, int q) {
-        const int stage = s % STAGES;
-        if (lane == 0) B2_TRACE(3, dk, 0);
-        mbar_wait(g_full + 8 * q, (cnt_d >> q) & 1u);
-        tc_fence_after();
-        if (lane == 0) B2_TRACE(3, dk, 1);
-        const uint32_t zt_j = s_ring + stage * STAGE_BYTES + 2 * ZA_BYTES;
-        const int seg = s / SEG_STEPS, sp = seg & 1;
-        if (seg != cur_seg) {                    // first dZ_I product of a new segment: its TMEM buffers must have been drained
-          mbar_wait(d1_empty + 8 * sp, ((use_d1 >> sp) & 1u) ^ 1u);
+      // elementwise group / S buffer / G buffer (alternating by SEQUENCE, not by block: consecutive tiles never share a group).
+      if (warp == 1) {
+        const uint32_t idesc_s = umma_idesc_f16(BT, BT, 0, 0);        // S = Z_I (K-major, K = 16) · Z_J (K-major)
+        uint32_t cnt_s = 0;                                           // bit q = phase of S buffer q
+        int s = 0, g = -1, k = 0;
+        for (next_tile(s, g); s < sw.n_steps; next_tile(s, g), ++k) {
+          const int q = k & 1, stage = s % STAGES;
+          if (lane == 0) B2_TRACE(2, k, 0);
+          mbar_wait(s_empty + 8 * q, ((cnt_s >> q) & 1u) ^ 1u);       // the group has pulled S(k-2) into registers
+          if (lane == 0) B2_TRACE(2, k, 1);
+          mbar_wait(full_bar + 8 * stage, (s / STAGES) & 1);
           tc_fence_after();
-          cur_seg = seg;
-          d1_fresh = 3u;                         // both blocks start the segment with accumulate = 0
+          if (lane == 0) B2_TRACE(2, k, 2);
+          const uint32_t st = s_ring + stage * STAGE_BYTES, zi = s_zi + g * ZI_BYTES;
+          const uint32_t d_s = tmem + TM_S + (uint32_t)(q * BT);
+          // SWIZZLE_32B K-major: 32-byte rows (the whole K = 16), 8-row groups 256 B apart — one k-step
+          const uint64_t a_hi = umma_desc(zi, 16, 256, 6), a_lo = adv(a_hi, ZA_BYTES);
+          const uint64_t b_hi = umma_desc(st, 16, 256, 6), b_lo = adv(b_hi, ZA_BYTES);
+          umma_f16_elect(d_s, a_lo, b_hi, idesc_s, 0);
+          umma_f16_elect(d_s, a_hi, b_lo, idesc_s, 1);
+          umma_f16_elect(d_s, a_hi, b_hi, idesc_s, 1);
+          umma_commit_elect(s_full + 8 * q);
+          if (lane == 0) B2_TRACE(2, k, 3);
+          cnt_s ^= 1u << q;
         }
-        const uint32_t d1 = tmem + TM_D1 + (uint32_t)((sp * 2 + g) * 2 * DW);
-        // K-major SWIZZLE_128B view of G: 64 j per 128-byte row, 8-row groups 1 KB apart; k-step = 32 B inside the row, 64-column blocks
-        // 16 KB apart.  [Z_hi | Z_lo]_J (N = 32): same layout, 64-column blocks 2·ZT_BOX apart.
-        const uint64_t ga_hi = umma_desc(s_g + q * G_BYTES, 16, 1024, 2), ga_lo = adv(ga_hi, G_PLANE);
-        const uint64_t zb_j = umma_desc(zt_j, 16, 1024, 2);
-#pragma unroll
-        for (int ks = 0; ks < BT / 16; ++ks) {
-          const uint32_t koff = (uint32_t)(ks >> 2) * (BT * 128) + (uint32_t)(ks & 3) * 32u;
-          const uint64_t b = adv(zb_j, (uint32_t)(ks >> 2) * (2 * ZT_BOX) + (uint32_t)(ks & 3) * 32u);
-          umma_f16_elect(d1, adv(ga_hi, koff), b, idesc_d1, (!((d1_fresh >> g) & 1u) || ks > 0) ? 1u : 0u);
-          umma_f16_elect(d1, adv(ga_lo, koff), b, idesc_d1, 1);
-        }
-        d1_fresh &= ~(1u << g);
-        if (!sw.diag(g, s)) {
-          const int b3 = s % 3;
-          const bool first = (g == 0) || !(sw.active(0, s) && !sw.diag(0, s));     // first tile of this step that feeds dZ_J
-          if (first) {
-            mbar_wait(d2_empty + 8 * b3, ((use_d2 >> b3) & 1u) ^ 1u);
+      } else {
+        const uint32_t idesc_d1 = umma_idesc_f16(BT, 2 * DW, 0, 0);   // dZ_I = G  (K-major A,  K = j) · [Z_hi | Z_lo]_J
+        const uint32_t idesc_d2 = umma_idesc_f16(BT, 2 * DW, 1, 0);   // dZ_J = Gᵀ (MN-major A, K = i) · [Z_hi | Z_lo]_I
+        // per-buffer phase counters packed into scalars (dynamic indexing of local arrays would put them on the stack)
+        uint32_t cnt_d = 0, use_d2 = 0, use_d1 = 0, d1_fresh = 0;     // bit q / b3 / segment parity = phase (or flag) of that slot
+        int cur_seg = -1;
+        int s = 0, g = -1, k = 0;
+        for (next_tile(s, g); s < sw.n_steps; next_tile(s, g), ++k) {
+          const int q = k & 1, stage = s % STAGES;
+          if (lane == 0) B2_TRACE(3, k, 0);
+          mbar_wait(g_full + 8 * q, (cnt_d >> q) & 1u);               // G(k) written
+          mbar_wait(full_bar + 8 * stage, (s / STAGES) & 1);          // (complete long ago: the TMA writes of Z_J made visible to this thread)
+          tc_fence_after();
+          if (lane == 0) B2_TRACE(3, k, 1);
+          const uint32_t zt_j = s_ring + stage * STAGE_BYTES + 2 * ZA_BYTES;
+          const int seg = s / SEG_STEPS, sp = seg & 1;
+          if (seg != cur_seg) {                    // first dZ_I product of a new segment: its TMEM buffers must have been drained
+            mbar_wait(d1_empty + 8 * sp, ((use_d1 >> sp) & 1u) ^ 1u);
             tc_fence_after();
+            cur_seg = seg;
+            d1_fresh = 3u;                         // both blocks start the segment with accumulate = 0
           }
-          const uint32_t d2 = tmem + TM_D2 + (uint32_t)(b3 * 2 * DW);
-          // MN-major SWIZZLE_128B over the SAME bytes of G: 64 j (M) contiguous per 128-byte row, k-step = 16 rows (i) = 2 KB,
-          // 8-row groups (SBO) 1 KB apart, the second 64-j block (LBO) 16 KB further
-          const uint64_t gt_hi = umma_desc(s_g + q * G_BYTES, BT * 128, 1024, 2), gt_lo = adv(gt_hi, G_PLANE);
-          const uint64_t zb_i = umma_desc(s_zi + g * ZI_BYTES + 2 * ZA_BYTES, 16, 1024, 2);
+          const uint32_t d1 = tmem + TM_D1 + (uint32_t)((sp * 2 + g) * 2 * DW);
+          // K-major SWIZZLE_128B view of G: 64 j per 128-byte row, 8-row groups 1 KB apart; k-step = 32 B inside the row, 64-column
+          // blocks 16 KB apart.  [Z_hi | Z_lo]_J (N = 32): same layout, 64-column blocks 2·ZT_BOX apart.
+          const uint64_t ga_hi = umma_desc(s_g + q * G_BYTES, 16, 1024, 2), ga_lo = adv(ga_hi, G_PLANE);
+          const uint64_t zb_j = umma_desc(zt_j, 16, 1024, 2);
 #pragma unroll
           for (int ks = 0; ks < BT / 16; ++ks) {
-            const uint64_t b = adv(zb_i, (uint32_t)(ks >> 2) * (2 * ZT_BOX) + (uint32_t)(ks & 3) * 32u);
-            umma_f16_elect(d2, adv(gt_hi, (uint32_t)ks * 2048u), b, idesc_d2, (!first || ks > 0) ? 1u : 0u);
-            umma_f16_elect(d2, adv(gt_lo, (uint32_t)ks * 2048u), b, idesc_d2, 1);
+            const uint32_t koff = (uint32_t)(ks >> 2) * (BT * 128) + (uint32_t)(ks & 3) * 32u;
+            const uint64_t bd = adv(zb_j, (uint32_t)(ks >> 2) * (2 * ZT_BOX) + (uint32_t)(ks & 3) * 32u);
+            umma_f16_elect(d1, adv(ga_hi, koff), bd, idesc_d1, (!((d1_fresh >> g) & 1u) || ks > 0) ? 1u : 0u);
+            umma_f16_elect(d1, adv(ga_lo, koff), bd, idesc_d1, 1);
           }
+          d1_fresh &= ~(1u << g);
+          if (!sw.diag(g, s)) {
+            const int b3 = s % 3;
+            const bool first = (g == 0) || !(sw.active(0, s) && !sw.diag(0, s));     // first tile of this step that feeds dZ_J
+            if (first) {
+              mbar_wait(d2_empty + 8 * b3, ((use_d2 >> b3) & 1u) ^ 1u);
+              tc_fence_after();
+            }
+            const uint32_t d2 = tmem + TM_D2 + (uint32_t)(b3 * 2 * DW);
+            // MN-major SWIZZLE_128B over the SAME bytes of G: 64 j (M) contiguous per 128-byte row, k-step = 16 rows (i) = 2 KB,
+            // 8-row groups (SBO) 1 KB apart, the second 64-j block (LBO) 16 KB further
+            const uint64_t gt_hi = umma_desc(s_g + q * G_BYTES, BT * 128, 1024, 2), gt_lo = adv(gt_hi, G_PLANE);
+            const uint64_t zb_i = umma_desc(s_zi + g * ZI_BYTES + 2 * ZA_BYTES, 16, 1024, 2);
+#pragma unroll
+            for (int ks = 0; ks < BT / 16; ++ks) {
+              const uint64_t bd = adv(zb_i, (uint32_t)(ks >> 2) * (2 * ZT_BOX) + (uint32_t)(ks & 3) * 32u);
+              umma_f16_elect(d2, adv(gt_hi, (uint32_t)ks * 2048u), bd, idesc_d2, (!first || ks > 0) ? 1u : 0u);
+              umma_f16_elect(d2, adv(gt_lo, (uint32_t)ks * 2048u), bd, idesc_d2, 1);
+            }
+          }
+          umma_commit_elect(g_empty + 8 * q);
+          if (lane == 0) B2_TRACE(3, k, 2);
+          cnt_d ^= 1u << q;
+          if (sw.last_of_step(g, s)) {
+            // the S products of this step finished before its elementwise passes started, so the gradient products are the last readers
+            umma_commit_elect(stage_free + 8 * stage);
+            if (sw.has_d2(s)) { umma_commit_elect(d2_full + 8 * (s % 3)); use_d2 ^= 1u << (s % 3); }
+            if (s % SEG_STEPS == SEG_STEPS - 1 || s == sw.n_steps - 1) { umma_commit_elect(d1_full + 8 * sp); use_d1 ^= 1u << sp; }
+          }
+          if (lane == 0) B2_TRACE(3, k, 3);
         }
-        umma_commit_elect(g_empty + 8 * q);
-        if (lane == 0) B2_TRACE(3, dk, 2);
-        cnt_d ^= 1u << q;
-        if (sw.last_of_step(g, s)) {
-          umma_commit_elect(stage_free + 8 * stage);
-          if (sw.has_d2(s)) { umma_commit_elect(d2_full + 8 * (s % 3)); use_d2 ^= 1u << (s % 3); }
-          if (s % SEG_STEPS == SEG_STEPS - 1 || s == sw.n_steps - 1) { umma_commit_elect(d1_full + 8 * sp); use_d1 ^= 1u << sp; }
-        }
-      };
-      // S runs two tiles ahead of the gradient products (the tensor pipe executes in order).  An event-driven order — issue whichever
-      // queue has its inputs ready — was measured 7 % slower (the probes cost the issuer more than head-of-line blocking does).
-      next_tile(ss, sg);
-      next_tile(ds, dg);
-      for (int pre = 0; pre < 2 && ss < sw.n_steps; ++pre) { issue_s(ss, sg, sk & 1); ++sk; next_tile(ss, sg); }
-      while (ds < sw.n_steps) {
-        if (ss < sw.n_steps) { issue_s(ss, sg, sk & 1); ++sk; next_tile(ss, sg); }
-        issue_d(ds, dg, dk & 1);
-        ++dk;
-        next_tile(ds, dg);
       }
     }
     __syncwarp();

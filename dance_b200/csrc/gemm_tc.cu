@@ -163,7 +163,9 @@ gemm_tc_kernel(const __grid_constant__ Params p) {
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // the whole warp runs the role; tcgen05.mma / commit are issued by one elected lane inside the asm (tc_common.cuh: issued from a
+    // divergent `lane == 0` branch each MMA costs an ELECT / BRA.U.ANY loop plus per-instruction descriptor arithmetic)
+    {
       const uint32_t idesc = umma_idesc(BM, p.BN, p.a_mn, p.b_mn);
       const uint32_t a_lbo = p.a_mn ? p.mn_lbo : 16, b_lbo = p.b_mn ? p.mn_lbo : 16;
       const uint32_t a_kstep = p.a_mn ? 1024u : (uint32_t)(UK * 4), b_kstep = p.b_mn ? 1024u : (uint32_t)(UK * 4);
@@ -184,28 +186,31 @@ gemm_tc_kernel(const __grid_constant__ Params p) {
           mbar_wait((p.x3 ? split_bar : full_bar) + 8 * stage, phase);
           tc_fence_after();
           const uint32_t st = smem_base + stage * L.stage_bytes;
+          // start-address field = 16-byte units in the low 14 bits (shared memory < 256 KB): a k-step advances it by kstep / 16
+          const uint64_t a_hi0 = umma_desc(st + L.a_hi, a_lbo, a_sbo, a_lay), b_hi0 = umma_desc(st + L.b_hi, b_lbo, b_sbo, b_lay);
+          const uint64_t a_lo0 = umma_desc(st + L.a_lo, a_lbo, a_sbo, a_lay), b_lo0 = umma_desc(st + L.b_lo, b_lbo, b_sbo, b_lay);
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
-            const uint64_t a_hi = umma_desc(st + L.a_hi + k * a_kstep, a_lbo, a_sbo, a_lay);
-            const uint64_t b_hi = umma_desc(st + L.b_hi + k * b_kstep, b_lbo, b_sbo, b_lay);
+            const uint64_t a_hi = a_hi0 + (uint64_t)((k * a_kstep) >> 4);
+            const uint64_t b_hi = b_hi0 + (uint64_t)((k * b_kstep) >> 4);
             if (p.x3) {
-              const uint64_t a_lo = umma_desc(st + L.a_lo + k * a_kstep, a_lbo, a_sbo, a_lay);
-              const uint64_t b_lo = umma_desc(st + L.b_lo + k * b_kstep, b_lbo, b_sbo, b_lay);
+              const uint64_t a_lo = a_lo0 + (uint64_t)((k * a_kstep) >> 4);
+              const uint64_t b_lo = b_lo0 + (uint64_t)((k * b_kstep) >> 4);
               // The TMEM accumulate truncates (measured: error grows linearly with the number of accumulations),
               // so the two small cross terms go to their own accumulator: the big one sees 1/3 of the additions
               // and the small one's truncation is ~2^-11 smaller in absolute terms.  Summed (RN) in the epilogue.
-              umma_tf32(d_small, a_lo, b_hi, idesc, accumulate);
-              umma_tf32(d_small, a_hi, b_lo, idesc, 1);
-              umma_tf32(d_tmem, a_hi, b_hi, idesc, accumulate);
+              umma_tf32_elect(d_small, a_lo, b_hi, idesc, accumulate);
+              umma_tf32_elect(d_small, a_hi, b_lo, idesc, 1);
+              umma_tf32_elect(d_tmem, a_hi, b_hi, idesc, accumulate);
             } else {
-              umma_tf32(d_tmem, a_hi, b_hi, idesc, accumulate);
+              umma_tf32_elect(d_tmem, a_hi, b_hi, idesc, accumulate);
             }
             accumulate = 1;
           }
-          umma_commit(empty_bar + 8 * stage);   // frees the smem stage once these MMAs have read it
+          umma_commit_elect(empty_bar + 8 * stage);   // frees the smem stage once these MMAs have read it
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar + 8 * acc);       // accumulator complete → epilogue
+        umma_commit_elect(tfull_bar + 8 * acc);       // accumulator complete → epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

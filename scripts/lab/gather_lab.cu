@@ -62,6 +62,22 @@ __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void cp_async_16_hint(uint32_t dst, const void* src, uint64_t pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async_4_hint(uint32_t dst, const void* src, uint64_t pol) {
+  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -588,6 +604,183 @@ stream2_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ c
   }
 }
 
+template <int DT, int CB, int NG, int WARPS, int HINT>
+__global__ void __launch_bounds__(WARPS * 32)
+stream3_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const float* __restrict__ vals,
+               const uint8_t* __restrict__ X, int64_t ldxb, float* __restrict__ Y, int n_rows, int row_begin, int row_end) {
+  constexpr int ESZ = DT == 2 ? 4 : 2;
+  constexpr int RB = F * ESZ;
+  constexpr int BLK = 32;
+  constexpr int LPR = RB / 16;
+  constexpr int RPI = 32 / LPR;
+  constexpr int LPRC = RB / CB;
+  constexpr int NPI = 32 / LPRC;
+  constexpr int NV = CB / ESZ;
+  constexpr int NC = 2 * NG;           // blocks of (col, val) pairs resident per warp
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* ring = smem + (size_t)warp * (NG * BLK * RB);
+  int32_t* cring = reinterpret_cast<int32_t*>(smem + (size_t)WARPS * NG * BLK * RB) + warp * (NC * BLK);
+  float* vring = reinterpret_cast<float*>(smem + (size_t)WARPS * NG * BLK * RB + (size_t)WARPS * NC * BLK * 4) + warp * (NC * BLK);
+  const uint32_t ring_s = smem_u32(ring), cring_s = smem_u32(cring), vring_s = smem_u32(vring);
+  const int W = gridDim.x * WARPS, w = blockIdx.x * WARPS + warp;
+  // this launch covers rows [row_begin, row_end) (one slab); the slab's non-zeros are split evenly over the warps
+  const int64_t s0 = __ldg(rowptr + row_begin), s1 = __ldg(rowptr + row_end);
+  const int64_t t0 = s0 + (int64_t)w * (s1 - s0) / W, t1 = s0 + (int64_t)(w + 1) * (s1 - s0) / W;
+  const int R0 = (w == 0) ? row_begin : max(row_begin, min(row_end, warp_lower_bound(rowptr, n_rows, t0, lane)));
+  const int R1 = (w == W - 1) ? row_end : max(row_begin, min(row_end, warp_lower_bound(rowptr, n_rows, t1, lane)));
+  const uint64_t pol_x = policy_evict_last(), pol_s = policy_evict_first();
+  if (R0 >= R1) return;
+  const int E0 = __ldg(rowptr + R0), E1 = __ldg(rowptr + R1);
+  const int nblk = (E1 - E0 + BLK - 1) / BLK;
+
+  int rb = R0;
+  int rpv = __ldg(rowptr + min(rb + 1 + lane, n_rows));
+  int rpn = __ldg(rowptr + min(rb + 33 + lane, n_rows));
+  int r = R0, rend = __shfl_sync(FULL, rpv, 0);
+  const int subc = lane / LPRC, glc = lane % LPRC;
+  float acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+
+  auto issue_pairs = [&](int blk_i, int cs) {     // (col, val) of block blk_i → pair-ring slot cs
+    const int e = E0 + blk_i * BLK + lane;
+    if (blk_i < nblk && e < E1) {
+      if (HINT) {
+        cp_async_4_hint(cring_s + (cs * BLK + lane) * 4, colidx + e, pol_s);
+        cp_async_4_hint(vring_s + (cs * BLK + lane) * 4, vals + e, pol_s);
+      } else {
+        cp_async_4(cring_s + (cs * BLK + lane) * 4, colidx + e);
+        cp_async_4(vring_s + (cs * BLK + lane) * 4, vals + e);
+      }
+    } else {
+      cring[cs * BLK + lane] = -1;
+    }
+  };
+  // prologue: pairs of blocks 0 .. NG-1
+#pragma unroll
+  for (int j = 0; j < NG; ++j) issue_pairs(j, j);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncwarp();
+
+  int st_i = 0, cs_i = 0;      // row-ring stage / pair-ring slot of the block being issued
+  int st_c = 0, cs_c = 0;      // … of the block being consumed
+  int cs_p = NG;               // pair-ring slot receiving block b + NG
+  for (int b = 0; b < nblk + NG - 1; ++b) {
+    if (b < nblk) {
+      const int c = cring[cs_i * BLK + lane];
+#pragma unroll
+      for (int i = 0; i < LPR; ++i) {
+        const int idx = i * RPI + lane / LPR;
+        const int cc = __shfl_sync(FULL, c, idx);
+        if (cc >= 0) {
+          if (HINT) cp_async_16_hint(ring_s + (st_i * BLK + idx) * RB + (lane % LPR) * 16, X + (int64_t)cc * ldxb + (lane % LPR) * 16, pol_x);
+          else cp_async_16(ring_s + (st_i * BLK + idx) * RB + (lane % LPR) * 16, X + (int64_t)cc * ldxb + (lane % LPR) * 16);
+        }
+      }
+      issue_pairs(b + NG, cs_p);
+      st_i = (st_i + 1 == NG) ? 0 : st_i + 1;
+      cs_i = (cs_i + 1 == NC) ? 0 : cs_i + 1;
+      cs_p = (cs_p + 1 == NC) ? 0 : cs_p + 1;
+    }
+    cp_async_commit();
+    if (b >= NG - 1) {
+      const int bc = b - (NG - 1);
+      cp_async_wait<NG - 1>();
+      __syncwarp();
+      const int eb = E0 + bc * BLK;
+      const int eend = min(E1, eb + BLK);
+      const uint8_t* blk = ring + (size_t)st_c * BLK * RB;
+      const float* vb = vring + cs_c * BLK;
+      int e = eb;
+      while (true) {
+        while (r < R1 && rend <= e) {
+#pragma unroll
+          for (int o = LPRC; o < 32; o <<= 1) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) acc[i] += __shfl_xor_sync(FULL, acc[i], o);
+          }
+          if (lane < LPRC) {
+            float* y = Y + (int64_t)r * F + lane * NV;
+            if (NV == 1) stg_cs(y, acc[0]);
+            else if (NV == 2) stg_cs2(y, acc[0], acc[1 % NV]);
+            else if (NV == 4) stg_cs4(y, acc[0], acc[1 % NV], acc[2 % NV], acc[3 % NV]);
+            else { stg_cs4(y, acc[0], acc[1 % NV], acc[2 % NV], acc[3 % NV]); stg_cs4(y + 4, acc[4 % NV], acc[5 % NV], acc[6 % NV], acc[7 % NV]); }
+          }
+#pragma unroll
+          for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+          ++r;
+          int j = r - rb;
+          if (j == 32) {
+            rb += 32;
+            rpv = rpn;
+            rpn = __ldg(rowptr + min(rb + 33 + lane, n_rows));
+            j = 0;
+          }
+          rend = __shfl_sync(FULL, rpv, j);
+        }
+        if (e >= eend || r >= R1) break;
+        const int run_end = min(rend, eend);
+#pragma unroll 4
+        for (int k = e + subc; k < run_end; k += NPI) {
+          const int slot = k - eb;
+          const float wv = vb[slot];
+          const uint8_t* src = blk + slot * RB + glc * CB;
+          if (DT == 2) {
+            if (NV == 1) {
+              acc[0] = fmaf(wv, *reinterpret_cast<const float*>(src), acc[0]);
+            } else if (NV == 2) {
+              const float2 x = *reinterpret_cast<const float2*>(src);
+              acc[0] = fmaf(wv, x.x, acc[0]); acc[1 % NV] = fmaf(wv, x.y, acc[1 % NV]);
+            } else {
+              const float4 x = *reinterpret_cast<const float4*>(src);
+              acc[0] = fmaf(wv, x.x, acc[0]); acc[1 % NV] = fmaf(wv, x.y, acc[1 % NV]);
+              acc[2 % NV] = fmaf(wv, x.z, acc[2 % NV]); acc[3 % NV] = fmaf(wv, x.w, acc[3 % NV]);
+            }
+          } else {
+            float a, bb;
+            if (NV == 2) {
+              unpack2<0>(*reinterpret_cast<const uint32_t*>(src), a, bb);
+              acc[0] = fmaf(wv, a, acc[0]); acc[1 % NV] = fmaf(wv, bb, acc[1 % NV]);
+            } else if (NV == 4) {
+              const uint2 x = *reinterpret_cast<const uint2*>(src);
+              unpack2<0>(x.x, a, bb); acc[0] = fmaf(wv, a, acc[0]); acc[1 % NV] = fmaf(wv, bb, acc[1 % NV]);
+              unpack2<0>(x.y, a, bb); acc[2 % NV] = fmaf(wv, a, acc[2 % NV]); acc[3 % NV] = fmaf(wv, bb, acc[3 % NV]);
+            } else {
+              const uint4 x = *reinterpret_cast<const uint4*>(src);
+              unpack2<0>(x.x, a, bb); acc[0] = fmaf(wv, a, acc[0]); acc[1 % NV] = fmaf(wv, bb, acc[1 % NV]);
+              unpack2<0>(x.y, a, bb); acc[2 % NV] = fmaf(wv, a, acc[2 % NV]); acc[3 % NV] = fmaf(wv, bb, acc[3 % NV]);
+              unpack2<0>(x.z, a, bb); acc[4 % NV] = fmaf(wv, a, acc[4 % NV]); acc[5 % NV] = fmaf(wv, bb, acc[5 % NV]);
+              unpack2<0>(x.w, a, bb); acc[6 % NV] = fmaf(wv, a, acc[6 % NV]); acc[7 % NV] = fmaf(wv, bb, acc[7 % NV]);
+            }
+          }
+        }
+        e = run_end;
+      }
+      st_c = (st_c + 1 == NG) ? 0 : st_c + 1;
+      cs_c = (cs_c + 1 == NC) ? 0 : cs_c + 1;
+    }
+  }
+  while (r < R1) {
+#pragma unroll
+    for (int o = LPRC; o < 32; o <<= 1) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) acc[i] += __shfl_xor_sync(FULL, acc[i], o);
+    }
+    if (lane < LPRC) {
+      float* y = Y + (int64_t)r * F + lane * NV;
+      if (NV == 1) stg_cs(y, acc[0]);
+      else if (NV == 2) stg_cs2(y, acc[0], acc[1 % NV]);
+      else if (NV == 4) stg_cs4(y, acc[0], acc[1 % NV], acc[2 % NV], acc[3 % NV]);
+      else { stg_cs4(y, acc[0], acc[1 % NV], acc[2 % NV], acc[3 % NV]); stg_cs4(y + 4, acc[4 % NV], acc[5 % NV], acc[6 % NV], acc[7 % NV]); }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+    ++r;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -653,6 +846,25 @@ static void launch_stream2(const Ctx& c, const CUtensorMap&, cudaStream_t st) {
   kern<<<c.sms * per_sm, WARPS * 32, smem, st>>>(c.rowptr, c.colidx, c.vals, X, (int64_t)RB, c.Y, c.n, c.nnz);
 }
 
+template <int DT, int CB, int NG, int WARPS, int HINT, int SLABS>
+static void launch_stream3(const Ctx& c, const CUtensorMap&, cudaStream_t st) {
+  constexpr int RB = F * (DT == 2 ? 4 : 2);
+  const size_t smem = (size_t)WARPS * NG * 32 * RB + (size_t)WARPS * 2 * NG * 32 * 8 + 128;
+  static bool once = false;
+  auto kern = stream3_kernel<DT, CB, NG, WARPS, HINT>;
+  if (!once) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    once = true;
+  }
+  int per_sm = (int)std::min<size_t>((227 * 1024) / (smem + 1024), 2048 / (WARPS * 32));
+  if (per_sm < 1) per_sm = 1;
+  const uint8_t* X = DT == 2 ? reinterpret_cast<const uint8_t*>(c.X) : reinterpret_cast<const uint8_t*>(c.Xb);
+  for (int sl = 0; sl < SLABS; ++sl) {
+    const int r0 = (int)((int64_t)c.n * sl / SLABS), r1 = (int)((int64_t)c.n * (sl + 1) / SLABS);
+    kern<<<c.sms * per_sm, WARPS * 32, smem, st>>>(c.rowptr, c.colidx, c.vals, X, (int64_t)RB, c.Y, c.n, r0, r1);
+  }
+}
+
 template <int DT, int TCH>
 static void launch_rg(const Ctx& c, cudaStream_t st) {
   constexpr int G = (DT == 2 ? F * 4 : F * 2) / 16;
@@ -692,6 +904,13 @@ static std::vector<Variant> variants() {
   S2("f32", 2, 16, 2, 4);  S2("f32", 2, 16, 3, 4);  S2("f32", 2, 16, 2, 16);
   S2("bf16", 0, 4, 2, 8);  S2("bf16", 0, 4, 3, 8);  S2("bf16", 0, 4, 4, 8);  S2("bf16", 0, 4, 6, 8);  S2("bf16", 0, 4, 8, 8);  S2("bf16", 0, 8, 4, 8);
   S2("bf16", 0, 16, 4, 8); S2("bf16", 0, 4, 4, 16);
+#define S3(DTN, DT, CB, NG, WP, HINT, SLABS) \
+  v.push_back({std::string("s3:") + DTN + ":" #CB ":" #NG ":" #WP ":h" #HINT ":s" #SLABS, DT, 0, launch_stream3<DT, CB, NG, WP, HINT, SLABS>})
+  S3("f32", 2, 16, 2, 8, 0, 1);  S3("f32", 2, 16, 2, 8, 1, 1);  S3("f32", 2, 16, 2, 8, 0, 10); S3("f32", 2, 16, 2, 8, 1, 10);
+  S3("f32", 2, 16, 2, 8, 1, 5);  S3("f32", 2, 16, 2, 8, 1, 20); S3("f32", 2, 16, 2, 8, 1, 40); S3("f32", 2, 16, 3, 8, 1, 10);
+  S3("f32", 2, 16, 3, 4, 1, 10); S3("f32", 2, 16, 4, 8, 1, 10);
+  S3("bf16", 0, 4, 2, 8, 0, 1);  S3("bf16", 0, 4, 2, 8, 1, 1);  S3("bf16", 0, 4, 2, 8, 1, 10); S3("bf16", 0, 4, 2, 8, 1, 20);
+  S3("bf16", 0, 4, 3, 8, 1, 10); S3("bf16", 0, 4, 4, 8, 1, 10); S3("bf16", 0, 4, 2, 8, 0, 10);
   return v;
 }
 

@@ -51,9 +51,10 @@ for mode, knobs in (("early_gwait", {"gae_late_gempty": 0}), ("late_gwait", {"ga
               f"first half {np.mean(e[:, 3] - e[:, 2]):7.0f} | second half {np.mean(e[:, 4] - e[:, 3]):7.0f} | fence+arrive {np.mean(e[:, 5] - e[:, 4]):6.0f}")
     s_ = rel[2, 2 * lo:2 * hi]
     d_ = rel[3, 2 * lo:2 * hi]
-    print(f"  issuer S: wait s_empty {np.mean(s_[:, 1] - s_[:, 0]):7.0f} | wait Z stage {np.mean(s_[:, 2] - s_[:, 1]):6.0f}   "
-          f"D: wait g_full {np.mean(d_[:, 1] - d_[:, 0]):7.0f} | accumulator waits + issue {np.mean(d_[:, 2] - d_[:, 1]):6.0f} | "
-          f"tile period {np.diff(d_[:, 2]).mean():7.0f}")
+    print(f"  issuer S: wait s_empty {np.mean(s_[:, 1] - s_[:, 0]):7.0f} | wait Z stage {np.mean(s_[:, 2] - s_[:, 1]):6.0f} | issue {np.mean(s_[:, 3] - s_[:, 2]):6.0f} | "
+          f"bookkeeping {np.mean(s_[1:, 0] - s_[:-1, 3]):6.0f}")
+    print(f"  issuer D: wait g_full {np.mean(d_[:, 1] - d_[:, 0]):7.0f} | accumulator waits + issue {np.mean(d_[:, 2] - d_[:, 1]):6.0f} | commits {np.mean(d_[:, 3] - d_[:, 2]):6.0f} | "
+          f"bookkeeping {np.mean(d_[1:, 0] - d_[:-1, 3]):6.0f} | tile period {np.diff(d_[:, 2]).mean():7.0f}")
     # lag between EW(k) end and D(k) issue complete; and between D(k) issued and the group's next g_empty pass
     k = np.arange(2 * lo, 2 * hi)
     ew_end = np.array([rel[kk & 1, kk >> 1, 5] for kk in k])
@@ -64,4 +65,4 @@ for mode, knobs in (("early_gwait", {"gae_late_gempty": 0}), ("late_gwait", {"ga
     # first 12 tiles, raw
     for kk in range(24, 36):
         q, i = kk & 1, kk >> 1
-        print(f"   tile {kk:3d} g{q}: EW {rel[q, i, :6].tolist()}  S {rel[2, kk, :3].tolist()}  D {rel[3, kk, :3].tolist()}")
+        print(f"   tile {kk:3d} g{q}: EW {rel[q, i, :6].tolist()}  S {rel[2, kk, :4].tolist()}  D {rel[3, kk, :4].tolist()}")
