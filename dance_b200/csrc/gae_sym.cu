@@ -311,13 +311,17 @@ gae_sym_kernel(const __grid_constant__ Params p) {
           if (lane == 0) B2_TRACE(2, k, 2);
           const uint32_t st = s_ring + stage * STAGE_BYTES, zi = s_zi + g * ZI_BYTES;
           const uint32_t d_s = tmem + TM_S + (uint32_t)(q * BT);
-          // SWIZZLE_32B K-major: 32-byte rows (the whole K = 16), 8-row groups 256 B apart — one k-step
-          const uint64_t a_hi = umma_desc(zi, 16, 256, 6), a_lo = adv(a_hi, ZA_BYTES);
-          const uint64_t b_hi = umma_desc(st, 16, 256, 6), b_lo = adv(b_hi, ZA_BYTES);
-          umma_f16_elect(d_s, a_lo, b_hi, idesc_s, 0);
-          umma_f16_elect(d_s, a_hi, b_lo, idesc_s, 1);
-          umma_f16_elect(d_s, a_hi, b_hi, idesc_s, 1);
-          umma_commit_elect(s_full + 8 * q);
+          if (elect_one_pred()) {
+            // SWIZZLE_32B K-major: 32-byte rows (the whole K = 16), 8-row groups 256 B apart — one k-step
+            constexpr uint32_t HI = umma_desc_hi(256, 6);
+            const uint32_t a_hi = umma_desc_lo(zi, 16), a_lo = a_hi + (ZA_BYTES >> 4);
+            const uint32_t b_hi = umma_desc_lo(st, 16), b_lo = b_hi + (ZA_BYTES >> 4);
+            umma_f16_lo<HI, HI>(d_s, a_lo, b_hi, idesc_s, 0);
+            umma_f16_lo<HI, HI>(d_s, a_hi, b_lo, idesc_s, 1);
+            umma_f16_lo<HI, HI>(d_s, a_hi, b_hi, idesc_s, 1);
+            umma_commit(s_full + 8 * q);
+          }
+          __syncwarp();
           if (lane == 0) B2_TRACE(2, k, 3);
           cnt_s ^= 1u << q;
         }
@@ -344,45 +348,58 @@ gae_sym_kernel(const __grid_constant__ Params p) {
             d1_fresh = 3u;                         // both blocks start the segment with accumulate = 0
           }
           const uint32_t d1 = tmem + TM_D1 + (uint32_t)((sp * 2 + g) * 2 * DW);
-          // K-major SWIZZLE_128B view of G: 64 j per 128-byte row, 8-row groups 1 KB apart; k-step = 32 B inside the row, 64-column
-          // blocks 16 KB apart.  [Z_hi | Z_lo]_J (N = 32): same layout, 64-column blocks 2·ZT_BOX apart.
-          const uint64_t ga_hi = umma_desc(s_g + q * G_BYTES, 16, 1024, 2), ga_lo = adv(ga_hi, G_PLANE);
-          const uint64_t zb_j = umma_desc(zt_j, 16, 1024, 2);
-#pragma unroll
-          for (int ks = 0; ks < BT / 16; ++ks) {
-            const uint32_t koff = (uint32_t)(ks >> 2) * (BT * 128) + (uint32_t)(ks & 3) * 32u;
-            const uint64_t bd = adv(zb_j, (uint32_t)(ks >> 2) * (2 * ZT_BOX) + (uint32_t)(ks & 3) * 32u);
-            umma_f16_elect(d1, adv(ga_hi, koff), bd, idesc_d1, (!((d1_fresh >> g) & 1u) || ks > 0) ? 1u : 0u);
-            umma_f16_elect(d1, adv(ga_lo, koff), bd, idesc_d1, 1);
+          const bool off_diag = !sw.diag(g, s);
+          const int b3 = s % 3;
+          const bool first = (g == 0) || !(sw.active(0, s) && !sw.diag(0, s));     // first tile of this step that feeds dZ_J
+          if (off_diag && first) {
+            mbar_wait(d2_empty + 8 * b3, ((use_d2 >> b3) & 1u) ^ 1u);
+            tc_fence_after();
           }
-          d1_fresh &= ~(1u << g);
-          if (!sw.diag(g, s)) {
-            const int b3 = s % 3;
-            const bool first = (g == 0) || !(sw.active(0, s) && !sw.diag(0, s));     // first tile of this step that feeds dZ_J
-            if (first) {
-              mbar_wait(d2_empty + 8 * b3, ((use_d2 >> b3) & 1u) ^ 1u);
-              tc_fence_after();
-            }
-            const uint32_t d2 = tmem + TM_D2 + (uint32_t)(b3 * 2 * DW);
-            // MN-major SWIZZLE_128B over the SAME bytes of G: 64 j (M) contiguous per 128-byte row, k-step = 16 rows (i) = 2 KB,
-            // 8-row groups (SBO) 1 KB apart, the second 64-j block (LBO) 16 KB further
-            const uint64_t gt_hi = umma_desc(s_g + q * G_BYTES, BT * 128, 1024, 2), gt_lo = adv(gt_hi, G_PLANE);
-            const uint64_t zb_i = umma_desc(s_zi + g * ZI_BYTES + 2 * ZA_BYTES, 16, 1024, 2);
+          const bool last = sw.last_of_step(g, s);
+          const bool seg_done = (s % SEG_STEPS == SEG_STEPS - 1 || s == sw.n_steps - 1);
+          if (elect_one_pred()) {
+            constexpr uint32_t HI = umma_desc_hi(1024, 2);           // SWIZZLE_128B, 8-row groups 1 KB apart (all four operand views)
+            // K-major SWIZZLE_128B view of G: 64 j per 128-byte row; k-step = 32 B inside the row, 64-column blocks 16 KB apart.
+            // [Z_hi | Z_lo]_J (N = 32): same layout, 64-column blocks 2·ZT_BOX apart.
+            const uint32_t ga_hi = umma_desc_lo(s_g + q * G_BYTES, 16), ga_lo = ga_hi + (G_PLANE >> 4);
+            const uint32_t zb_j = umma_desc_lo(zt_j, 16);
+            const uint32_t acc0 = ((d1_fresh >> g) & 1u) ? 0u : 1u;
 #pragma unroll
             for (int ks = 0; ks < BT / 16; ++ks) {
-              const uint64_t bd = adv(zb_i, (uint32_t)(ks >> 2) * (2 * ZT_BOX) + (uint32_t)(ks & 3) * 32u);
-              umma_f16_elect(d2, adv(gt_hi, (uint32_t)ks * 2048u), bd, idesc_d2, (!first || ks > 0) ? 1u : 0u);
-              umma_f16_elect(d2, adv(gt_lo, (uint32_t)ks * 2048u), bd, idesc_d2, 1);
+              const uint32_t koff = ((uint32_t)(ks >> 2) * (BT * 128) + (uint32_t)(ks & 3) * 32u) >> 4;
+              const uint32_t bd = zb_j + (((uint32_t)(ks >> 2) * (2 * ZT_BOX) + (uint32_t)(ks & 3) * 32u) >> 4);
+              umma_f16_lo<HI, HI>(d1, ga_hi + koff, bd, idesc_d1, ks > 0 ? 1u : acc0);
+              umma_f16_lo<HI, HI>(d1, ga_lo + koff, bd, idesc_d1, 1);
+            }
+            if (off_diag) {
+              const uint32_t d2 = tmem + TM_D2 + (uint32_t)(b3 * 2 * DW);
+              // MN-major SWIZZLE_128B over the SAME bytes of G: 64 j (M) contiguous per 128-byte row, k-step = 16 rows (i) = 2 KB,
+              // the second 64-j block (LBO) 16 KB further
+              const uint32_t gt_hi = umma_desc_lo(s_g + q * G_BYTES, BT * 128), gt_lo = gt_hi + (G_PLANE >> 4);
+              const uint32_t zb_i = umma_desc_lo(s_zi + g * ZI_BYTES + 2 * ZA_BYTES, 16);
+              const uint32_t acc2 = first ? 0u : 1u;
+#pragma unroll
+              for (int ks = 0; ks < BT / 16; ++ks) {
+                const uint32_t bd = zb_i + (((uint32_t)(ks >> 2) * (2 * ZT_BOX) + (uint32_t)(ks & 3) * 32u) >> 4);
+                umma_f16_lo<HI, HI>(d2, gt_hi + (((uint32_t)ks * 2048u) >> 4), bd, idesc_d2, ks > 0 ? 1u : acc2);
+                umma_f16_lo<HI, HI>(d2, gt_lo + (((uint32_t)ks * 2048u) >> 4), bd, idesc_d2, 1);
+              }
+            }
+            umma_commit(g_empty + 8 * q);
+            if (last) {
+              // the S products of this step finished before its elementwise passes started, so the gradient products are the last readers
+              umma_commit(stage_free + 8 * stage);
+              if (sw.has_d2(s)) umma_commit(d2_full + 8 * b3);
+              if (seg_done) umma_commit(d1_full + 8 * sp);
             }
           }
-          umma_commit_elect(g_empty + 8 * q);
+          __syncwarp();
           if (lane == 0) B2_TRACE(3, k, 2);
+          d1_fresh &= ~(1u << g);
           cnt_d ^= 1u << q;
-          if (sw.last_of_step(g, s)) {
-            // the S products of this step finished before its elementwise passes started, so the gradient products are the last readers
-            umma_commit_elect(stage_free + 8 * stage);
-            if (sw.has_d2(s)) { umma_commit_elect(d2_full + 8 * (s % 3)); use_d2 ^= 1u << (s % 3); }
-            if (s % SEG_STEPS == SEG_STEPS - 1 || s == sw.n_steps - 1) { umma_commit_elect(d1_full + 8 * sp); use_d1 ^= 1u << sp; }
+          if (last) {
+            if (sw.has_d2(s)) use_d2 ^= 1u << b3;
+            if (seg_done) use_d1 ^= 1u << sp;
           }
           if (lane == 0) B2_TRACE(3, k, 3);
         }

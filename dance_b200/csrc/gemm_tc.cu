@@ -163,7 +163,7 @@ gemm_tc_kernel(const __grid_constant__ Params p) {
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // the whole warp runs the role; tcgen05.mma / commit are issued by one elected lane inside the asm (tc_common.cuh: issued from a
+    // the whole warp runs the role; each k-block's MMAs and commits are one single-thread issue region (tc_common.cuh: issued from a
     // divergent `lane == 0` branch each MMA costs an ELECT / BRA.U.ANY loop plus per-instruction descriptor arithmetic)
     {
       const uint32_t idesc = umma_idesc(BM, p.BN, p.a_mn, p.b_mn);
@@ -171,6 +171,7 @@ gemm_tc_kernel(const __grid_constant__ Params p) {
       const uint32_t a_kstep = p.a_mn ? 1024u : (uint32_t)(UK * 4), b_kstep = p.b_mn ? 1024u : (uint32_t)(UK * 4);
       const uint32_t a_sbo = p.a_mn ? p.mn_sbo : 1024u, b_sbo = p.b_mn ? p.mn_sbo : 1024u;
       const uint32_t a_lay = p.a_mn ? p.mn_layout : 2u, b_lay = p.b_mn ? p.mn_layout : 2u;
+      const uint32_t a_hiw = umma_desc_hi(a_sbo, a_lay), b_hiw = umma_desc_hi(b_sbo, b_lay);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -186,31 +187,38 @@ gemm_tc_kernel(const __grid_constant__ Params p) {
           mbar_wait((p.x3 ? split_bar : full_bar) + 8 * stage, phase);
           tc_fence_after();
           const uint32_t st = smem_base + stage * L.stage_bytes;
-          // start-address field = 16-byte units in the low 14 bits (shared memory < 256 KB): a k-step advances it by kstep / 16
-          const uint64_t a_hi0 = umma_desc(st + L.a_hi, a_lbo, a_sbo, a_lay), b_hi0 = umma_desc(st + L.b_hi, b_lbo, b_sbo, b_lay);
-          const uint64_t a_lo0 = umma_desc(st + L.a_lo, a_lbo, a_sbo, a_lay), b_lo0 = umma_desc(st + L.b_lo, b_lbo, b_sbo, b_lay);
+          if (elect_one_pred()) {
+            // single-thread issue region (tc_common.cuh): 32-bit descriptor words; the start-address field counts 16-byte units in
+            // the low 14 bits (shared memory < 256 KB), so a k-step advances the low word by kstep / 16
+            const uint32_t a_hi0 = umma_desc_lo(st + L.a_hi, a_lbo), b_hi0 = umma_desc_lo(st + L.b_hi, b_lbo);
+            const uint32_t a_lo0 = umma_desc_lo(st + L.a_lo, a_lbo), b_lo0 = umma_desc_lo(st + L.b_lo, b_lbo);
+            uint32_t accf = accumulate;
 #pragma unroll
-          for (int k = 0; k < BK / UK; ++k) {
-            const uint64_t a_hi = a_hi0 + (uint64_t)((k * a_kstep) >> 4);
-            const uint64_t b_hi = b_hi0 + (uint64_t)((k * b_kstep) >> 4);
-            if (p.x3) {
-              const uint64_t a_lo = a_lo0 + (uint64_t)((k * a_kstep) >> 4);
-              const uint64_t b_lo = b_lo0 + (uint64_t)((k * b_kstep) >> 4);
-              // The TMEM accumulate truncates (measured: error grows linearly with the number of accumulations),
-              // so the two small cross terms go to their own accumulator: the big one sees 1/3 of the additions
-              // and the small one's truncation is ~2^-11 smaller in absolute terms.  Summed (RN) in the epilogue.
-              umma_tf32_elect(d_small, a_lo, b_hi, idesc, accumulate);
-              umma_tf32_elect(d_small, a_hi, b_lo, idesc, 1);
-              umma_tf32_elect(d_tmem, a_hi, b_hi, idesc, accumulate);
-            } else {
-              umma_tf32_elect(d_tmem, a_hi, b_hi, idesc, accumulate);
+            for (int k = 0; k < BK / UK; ++k) {
+              const uint32_t ak = (k * a_kstep) >> 4, bk = (k * b_kstep) >> 4;
+              if (p.x3) {
+                // The TMEM accumulate truncates (measured: error grows linearly with the number of accumulations),
+                // so the two small cross terms go to their own accumulator: the big one sees 1/3 of the additions
+                // and the small one's truncation is ~2^-11 smaller in absolute terms.  Summed (RN) in the epilogue.
+                umma_tf32_lo(d_small, a_lo0 + ak, a_hiw, b_hi0 + bk, b_hiw, idesc, accf);
+                umma_tf32_lo(d_small, a_hi0 + ak, a_hiw, b_lo0 + bk, b_hiw, idesc, 1);
+                umma_tf32_lo(d_tmem, a_hi0 + ak, a_hiw, b_hi0 + bk, b_hiw, idesc, accf);
+              } else {
+                umma_tf32_lo(d_tmem, a_hi0 + ak, a_hiw, b_hi0 + bk, b_hiw, idesc, accf);
+              }
+              accf = 1;
             }
-            accumulate = 1;
+            umma_commit(empty_bar + 8 * stage);                        // frees the smem stage once these MMAs have read it
+            if (kb == kb1 - 1) umma_commit(tfull_bar + 8 * acc);       // accumulator complete → epilogue
           }
-          umma_commit_elect(empty_bar + 8 * stage);   // frees the smem stage once these MMAs have read it
+          __syncwarp();
+          accumulate = 1;
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit_elect(tfull_bar + 8 * acc);       // accumulator complete → epilogue
+        if (kb1 <= kb0) {                                // empty K range: nothing was issued, the epilogue still expects the hand-over
+          if (elect_one_pred()) umma_commit(tfull_bar + 8 * acc);
+          __syncwarp();
+        }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

@@ -197,6 +197,11 @@ static int launch_spmm(const int32_t* rowptr, const int32_t* colidx, const float
   return B2_OK;
 }
 
+// spmm_stream.cu: nnz-stream kernel for operand rows of 32 / 64 / 128 bytes; returns 1 when it does not take the shape
+int spmm_stream_dispatch(int dtype, const int32_t* rowptr, const int32_t* colidx, const float* vals, const void* X, int64_t ldx, float* Y,
+                         int64_t ldy, void* Y16, int64_t ldy16, int32_t n_rows, int32_t F, int reduce, int act, const float* bias,
+                         cudaStream_t st);
+
 }  // namespace b2
 
 extern "C" int b2_spmm_csr_f32(const int32_t* rowptr, const int32_t* colidx, const float* vals,
@@ -215,6 +220,10 @@ extern "C" int b2_spmm_csr_f32(const int32_t* rowptr, const int32_t* colidx, con
   B2_REQUIRE(!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "b2_spmm_csr_f32: bias must be 16-byte aligned");
   if (n_rows == 0) return B2_OK;
   cudaStream_t st = as_stream(stream);
+  {
+    const int rc = spmm_stream_dispatch(2, rowptr, colidx, vals, X, ldx, Y, ldy, nullptr, 0, n_rows, F, reduce, act, bias, st);
+    if (rc != 1) return rc;
+  }
   const int F4 = F / 4;
 #define B2_SPMM_CASE(G, VPL) return launch_spmm<G, VPL>(rowptr, colidx, vals, X, ldx, Y, ldy, n_rows, F, reduce, act, bias, st)
   if (F4 <= 2) B2_SPMM_CASE(2, 1);

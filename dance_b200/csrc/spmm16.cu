@@ -15,6 +15,9 @@
 #include <cuda_fp16.h>
 
 namespace b2 {
+int spmm_stream_dispatch(int dtype, const int32_t* rowptr, const int32_t* colidx, const float* vals, const void* X, int64_t ldx, float* Y,
+                         int64_t ldy, void* Y16, int64_t ldy16, int32_t n_rows, int32_t F, int reduce, int act, const float* bias,
+                         cudaStream_t st);
 namespace {
 
 template <int DT> struct X16;
@@ -155,6 +158,10 @@ int dispatch_x16(const char* name, const int32_t* rowptr, const int32_t* colidx,
   B2_REQUIRE(reduce == 0 || reduce == 1, "%s: reduce must be 0 (sum) or 1 (mean)", name);
   if (n_rows == 0) return B2_OK;
   cudaStream_t st = as_stream(stream);
+  {
+    const int rc = spmm_stream_dispatch(DT, rowptr, colidx, vals, X, ldx, Y, ldy, Y16, ldy16, n_rows, F, reduce, act, bias, st);
+    if (rc != 1) return rc;
+  }
   const int F8 = F / 8;
 #define B2_X16_CASE(G) return launch_x16<G, DT>(rowptr, colidx, vals, X, ldx, Y, ldy, Y16, ldy16, n_rows, F, reduce, act, bias, st)
   if (F8 <= 1) B2_X16_CASE(1);

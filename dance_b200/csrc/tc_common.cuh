@@ -205,6 +205,44 @@ __device__ __forceinline__ void umma_f16_elect(uint32_t d_tmem, uint64_t adesc, 
       "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Single-thread issue region: `if (elect_one_pred()) { umma_*_lo(...) …; umma_commit(bar); } __syncwarp();` inside warp-uniform code.
+// Descriptors are passed as their 32-bit LOW word (start address >> 4 | LBO field) with the HIGH word (SBO, version, layout) as an
+// immediate: ptxas converts each base to a uniform register once per region and advances it with one UIADD3 per MMA (≈ 3 SASS
+// instructions per tcgen05.mma; 64-bit descriptors elected per instruction cost ≈ 12, issued under `lane == 0` ≈ 14 plus a loop).
+__device__ __forceinline__ bool elect_one_pred() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t@e mov.u32 %0, 1;\n\t}\n" : "+r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes, uint32_t layout) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29); }
+template <uint32_t A_HI, uint32_t B_HI>
+__device__ __forceinline__ void umma_f16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %6};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "n"(A_HI), "n"(B_HI) : "memory");
+}
+// kind::tf32 with run-time high words (the GEMM's operands can be K- or MN-major)
+__device__ __forceinline__ void umma_tf32_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
   asm volatile(
       "{\n\t"

@@ -36,11 +36,11 @@ int sm_count() {
 const char* last_error() { return g_err; }
 
 // kernel-path selectors (b2_set_path): every selectable path computes the same result, the switch exists for A/B tests
-static int g_path[B2_PATH_COUNT] = {0, 0};
+static int g_path[B2_PATH_COUNT] = {0, 0, 0};
 int path_mode(int which) { return (which >= 0 && which < B2_PATH_COUNT) ? g_path[which] : 0; }
 
 // scheduling knobs of the tensor-core decoder (b2_set_tuning): they move work in time, never change a result
-static int g_tune[B2_TUNE_COUNT] = {1500, 0};
+static int g_tune[B2_TUNE_COUNT] = {1500, 1};
 int tuning(int which) { return (which >= 0 && which < B2_TUNE_COUNT) ? g_tune[which] : 0; }
 
 }  // namespace b2

@@ -49,12 +49,13 @@ extern "C" {
  * rounding for the decoder); mode 0 = automatic choice by problem size. */
 #define B2_PATH_GAE_DECODER 0 /* 1 CUDA cores · 2 tcgen05 tf32 split · 3 tcgen05 fp16 row sweep · 4 tcgen05 fp16 symmetric */
 #define B2_PATH_KNN_FILTER 1  /* 1 SIMT candidate filter */
-#define B2_PATH_COUNT 2
+#define B2_PATH_SPMM 2        /* 1 row-per-lane-group kernels for every shape (default: the nnz-stream kernel where it applies) */
+#define B2_PATH_COUNT 3
 int b2_set_path(int which, int mode);
 int b2_get_path(int which);
 /* Scheduling knobs of the symmetric decoder (timing experiments; results do not depend on them). */
 #define B2_TUNE_GAE_STAGGER 0     /* initial delay (cycles) of the second elementwise group, default 1500 */
-#define B2_TUNE_GAE_LATE_GEMPTY 1 /* 0 (default, measured faster): wait for the G buffer before loading S; 1: after the first half's math */
+#define B2_TUNE_GAE_LATE_GEMPTY 1 /* 1 (default): the elementwise group waits for its G buffer after the first half's math; 0: before loading S */
 #define B2_TUNE_COUNT 2
 int b2_set_tuning(int which, int value);
 

@@ -102,6 +102,53 @@ def test_spmm_16bit_operand(cuda, dtype, F, reduce):
     assert np.all(Yu[1].cpu().numpy() == 0)   # empty row
 
 
+@pytest.mark.parametrize("F,dtype", [(8, torch.float32), (16, torch.float32), (32, torch.float32), (16, torch.bfloat16), (32, torch.bfloat16),
+                                     (64, torch.float16)])
+def test_spmm_stream_kernel_against_rowgroup_and_fp64(cuda, F, dtype):
+    """The nnz-stream aggregate (operand rows of 32 / 64 / 128 bytes: spmm_stream.cu) on a graph with every row shape it has to
+    handle — runs of empty rows longer than its 32-row pointer window, hub rows spanning hundreds of 32-entry blocks, rows ending
+    exactly on block boundaries, an empty tail — against fp64 and against the row-per-lane-group kernels (ops.set_path)."""
+    from dance_b200 import ops
+    rng = np.random.default_rng(F)
+    n, c = 20_011, 15_000
+    deg = rng.integers(0, 60, n)
+    deg[100:180] = 0                      # > 2 pointer windows of empty rows
+    deg[500] = 7000; deg[501] = 0; deg[502] = 3333
+    deg[1000:1064] = 32                   # rows ending exactly on block boundaries
+    deg[-700:] = 0                        # empty tail
+    rows = np.repeat(np.arange(n), deg)
+    cols = rng.integers(0, c, rows.size)
+    m = sp.csr_matrix((rng.normal(size=rows.size).astype(np.float32), (rows, cols)), shape=(n, c))
+    m.sum_duplicates(); m.sort_indices()
+    X = torch.from_numpy(rng.normal(size=(c, F)).astype(np.float32)).to(cuda)
+    Xop = X if dtype == torch.float32 else ops.to_x16(X, dtype)
+    bias = torch.randn(F, device=cuda)
+    A = ops.CSR.from_scipy(m, cuda)
+    ref = m.astype(np.float64) @ Xop.double().cpu().numpy()
+    for reduce in ("sum", "mean"):
+        r = ref / np.maximum(np.diff(m.indptr), 1)[:, None] if reduce == "mean" else ref
+        r = np.maximum(r + bias.double().cpu().numpy(), 0)
+        ops.set_path("spmm", "auto")
+        Y = ops.spmm(A, Xop, reduce=reduce, act="relu", bias=bias)
+        try:
+            ops.set_path("spmm", "rowgroup")
+            Yg = ops.spmm(A, Xop, reduce=reduce, act="relu", bias=bias)
+        finally:
+            ops.set_path("spmm", "auto")
+        assert rel_err(Y, r) < 1e-6 and rel_err(Yg, r) < 1e-6
+        assert rel_err(Y, Yg.cpu().numpy()) < 1e-6
+        assert torch.all(Y[100:180] == torch.relu(bias)) and torch.all(Y[-700:] == torch.relu(bias))
+    # unit weights, padded leading dimension, one-row and all-empty matrices
+    Au = ops.CSR.from_scipy(m, cuda, with_values=False)
+    wide = torch.zeros(c, F + 8, dtype=Xop.dtype, device=cuda)
+    wide[:, :F] = Xop
+    ones = m.copy(); ones.data[:] = 1
+    assert rel_err(ops.spmm(Au, wide[:, :F]), ones.astype(np.float64) @ Xop.double().cpu().numpy()) < 1e-6
+    one = sp.csr_matrix((np.ones(3, np.float32), ([0, 0, 0], [1, 5, 7])), shape=(1, c))
+    assert rel_err(ops.spmm(ops.CSR.from_scipy(one, cuda), Xop), Xop[[1, 5, 7]].double().sum(0, keepdim=True).cpu().numpy()) < 1e-6
+    assert torch.all(ops.spmm(ops.CSR.from_scipy(sp.csr_matrix((37, c), dtype=np.float32), cuda), Xop) == 0)
+
+
 def test_spmm_empty_matrix(cuda):
     from dance_b200 import ops
     m = sp.csr_matrix((10, 10), dtype=np.float32)
