@@ -456,25 +456,34 @@ gae_sym_kernel(const __grid_constant__ Params p) {
             if (lane == 0) mbar_arrive(s_empty + 8 * q);                   // S[q] is in registers
           }
           uint32_t hi0[8], lo0[8], hi1[8], lo1[8];
+          // G = σ(x) leaves this lambda as two fp16 planes of 2^11·σ (hi: the top 11 significant bits, lo: the next 11) WITHOUT a
+          // float→half conversion: F2FP runs on the XU pipe (half the MUFU rate), and with 2 MUFU per logit that pipe is the
+          // kernel's bound (82 % busy once the MMA issue was fixed).  σ is produced at the scale 2^-5 — g = 2^-5·σ ∈ [2^-29, 2^-5] after
+          // clamping σ at 2^-24 — so its fp32 exponent field E satisfies E mod 32 = (fp16 exponent field of 2^11·σ): bits 13..28 of the
+          // fp32 word ARE the fp16 word.  Two shifts and a byte permute per pair replace the conversion; the residual g − hi goes the
+          // same way (values below 2^-31, i.e. 2^-26 of the largest σ, saturate there).
           auto chunk_math = [&](auto full_tag, const uint32_t (&v)[16], int c0, uint32_t (&hi)[8], uint32_t (&lo)[8]) {
             constexpr bool FULL = decltype(full_tag)::value;
+            constexpr float QS = 32.f;                 // q = 2^5·(1 + e)
+            constexpr float G_MIN = 1.862645149e-9f;   // 2^-29
+            constexpr float L_MIN = 4.656612873e-10f;  // 2^-31
             float prod0 = 1.f, prod1 = 1.f;
             float gg[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
               const float x = SCALED ? __uint_as_float(v[c]) * vs : __uint_as_float(v[c]);
               const float e = ex2a(-fabsf(x));
-              const float q = fmaf(e, 1.f / G_SCALE, 1.f / G_SCALE);
+              const float q = fmaf(e, QS, QS);
               const float r = rcpa(q);
               const float er = e * r;
-              float gc = x >= 0.f ? r : er;
+              float gc = fmaxf(x >= 0.f ? r : er, G_MIN);
               if (FULL) {
                 abs_t += fabsf(x);
                 if (c & 1) prod1 *= q; else prod0 *= q;
               } else {
                 const bool valid = row_ok && (c0 + c < col_end);
                 abs_t += valid ? fabsf(x) : 0.f;
-                const float f = valid ? q : 1.f / G_SCALE;
+                const float f = valid ? q : QS;
                 if (c & 1) prod1 *= f; else prod0 *= f;
                 gc = valid ? gc : 0.f;
               }
@@ -482,11 +491,17 @@ gae_sym_kernel(const __grid_constant__ Params p) {
             }
 #pragma unroll
             for (int c = 0; c < 16; c += 2) {
-              const float h0 = __uint_as_float(__float_as_uint(gg[c]) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(gg[c + 1]) & 0xFFFFE000u);
-              const __half2 h2 = __floats2half2_rn(h0, h1);
-              const __half2 l2 = __floats2half2_rn(gg[c] - h0, gg[c + 1] - h1);
-              hi[c >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
-              lo[c >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+              const uint32_t b0 = __float_as_uint(gg[c]), b1 = __float_as_uint(gg[c + 1]);
+              hi[c >> 1] = __byte_perm(b0 << 3, b1 << 3, 0x7632);
+              float l0 = gg[c] - __uint_as_float(b0 & 0xFFFFE000u), l1 = gg[c + 1] - __uint_as_float(b1 & 0xFFFFE000u);
+              if (FULL) {
+                l0 = fmaxf(l0, L_MIN);
+                l1 = fmaxf(l1, L_MIN);
+              } else {
+                l0 = b0 ? fmaxf(l0, L_MIN) : 0.f;      // masked entries stay exactly zero
+                l1 = b1 ? fmaxf(l1, L_MIN) : 0.f;
+              }
+              lo[c >> 1] = __byte_perm(__float_as_uint(l0) << 3, __float_as_uint(l1) << 3, 0x7632);
             }
             lg_t += lg2a(prod0) + lg2a(prod1);
           };
@@ -524,8 +539,8 @@ gae_sym_kernel(const __grid_constant__ Params p) {
       }
     }
     // Σ softplus over this thread's logits (both orientations of off-diagonal tiles) = ln2·[½Σ|v| + Σlog2(1+e)], the ½Σv half is
-    // added in closed form by linear_term_kernel; every logit carried a 2^-11 factor inside the products
-    double loss = (double)LN2 * (0.5 * (double)abs_w + (double)lg_w + 11.0 * 16.0 * (double)chunks_w);
+    // added in closed form by linear_term_kernel; every logit carried a 2^5 factor inside the products
+    double loss = (double)LN2 * (0.5 * (double)abs_w + (double)lg_w - 5.0 * 16.0 * (double)chunks_w);
     loss = warp_sum(loss);
     if (lane == 0 && loss != 0.0) atomicAdd(p.loss_acc, loss * (double)p.coef);
   } else {

@@ -116,7 +116,9 @@ struct StreamArgs {
 };
 
 // DT: 2 = fp32 operand, 0 = bf16, 1 = fp16.  RB = bytes per operand row (F · element size).  CB = bytes per lane at consumption.
-template <int DT, int RB, int CB>
+// EPI = false compiles the epilogue away (plain sum, no bias / activation / 16-bit copy): the aggregate's inner loop is issue-bound
+// enough (≈ 70 % issue-active) that the extra per-row instructions cost 25 %.
+template <int DT, int RB, int CB, bool EPI>
 __global__ void __launch_bounds__(SS_WARPS * 32)
 spmm_stream_kernel(const StreamArgs a) {
   constexpr int ESZ = DT == 2 ? 4 : 2;
@@ -173,13 +175,18 @@ spmm_stream_kernel(const StreamArgs a) {
       for (int i = 0; i < NV; ++i) acc[i] += __shfl_xor_sync(FULL, acc[i], o);
     }
     if (lane < LPRC) {
-      const float scale = (a.reduce == 1 && rend > rbeg) ? 1.f / (float)(rend - rbeg) : 1.f;   // DGL fn.mean divides by the in-degree
       float o[NV];
+      if (EPI) {
+        const float scale = (a.reduce == 1 && rend > rbeg) ? 1.f / (float)(rend - rbeg) : 1.f;   // DGL fn.mean divides by the in-degree
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        float v = acc[i] * scale;
-        if (a.bias) v += __ldg(a.bias + lane * NV + i);
-        o[i] = apply_act(v, a.act);
+        for (int i = 0; i < NV; ++i) {
+          float v = acc[i] * scale;
+          if (a.bias) v += __ldg(a.bias + lane * NV + i);
+          o[i] = apply_act(v, a.act);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) o[i] = acc[i];
       }
       if (a.Y) {
         float* y = a.Y + (int64_t)r * a.ldy + lane * NV;
@@ -192,7 +199,7 @@ spmm_stream_kernel(const StreamArgs a) {
                          "f"(o[(i + 3) % NV]) : "memory");
         }
       }
-      if (DT != 2 && a.Y16) {
+      if (EPI && DT != 2 && a.Y16) {
         uint8_t* y = a.Y16 + (int64_t)r * a.ldy16b + lane * NV * 2;
         if (NV == 2) {
           *reinterpret_cast<uint32_t*>(y) = pack2<DT>(o[0], o[1 % NV]);
@@ -299,10 +306,10 @@ spmm_stream_kernel(const StreamArgs a) {
   while (r < R1) emit_row();   // rows that end exactly at E1 and trailing empty rows of this warp's range
 }
 
-template <int DT, int RB, int CB>
-int launch_stream(const StreamArgs& a, cudaStream_t st) {
+template <int DT, int RB, int CB, bool EPI>
+int launch_stream_epi(const StreamArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)SS_WARPS * SS_NG * SS_BLK * RB + (size_t)SS_WARPS * 2 * SS_NG * SS_BLK * 8 + 128;
-  auto kern = spmm_stream_kernel<DT, RB, CB>;
+  auto kern = spmm_stream_kernel<DT, RB, CB, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -318,6 +325,12 @@ int launch_stream(const StreamArgs& a, cudaStream_t st) {
   kern<<<(unsigned)blocks, SS_WARPS * 32, smem, st>>>(a);
   B2_CHECK_LAUNCH("spmm_stream_kernel");
   return B2_OK;
+}
+
+template <int DT, int RB, int CB>
+int launch_stream(const StreamArgs& a, cudaStream_t st) {
+  const bool plain = a.reduce == 0 && a.act == B2_ACT_NONE && !a.bias && !a.Y16 && a.Y;
+  return plain ? launch_stream_epi<DT, RB, CB, false>(a, st) : launch_stream_epi<DT, RB, CB, true>(a, st);
 }
 
 }  // namespace
