@@ -54,7 +54,7 @@ constexpr uint32_t TM_S = 0, TM_D1 = 256, TM_D2 = 384, TM_COLS = 512;   // S: 2Ã
 // (â‰¤ 128 accumulations), double-buffered in TMEM; the flush warps add each finished segment to global memory (round-to-nearest
 // atomics) while the next one accumulates.  dZ_J is flushed every step anyway.
 constexpr int SEG_STEPS = 8;
-constexpr float G_SCALE = 2048.f;
+constexpr float G_SCALE = 32768.f;        // the MMAs see G = 2^15Â·Ïƒ (fp16 planes; see chunk_math)
 constexpr int STAGGER_CYCLES = 1500;
 
 struct Params {
@@ -67,6 +67,7 @@ struct Params {
   int n, d, nb, sb_begin;
   float coef;
   int stagger, late_gempty;      // b2_set_tuning knobs
+  int splits;                    // CTAs per super-block (step ranges)
 #ifdef B2_GAE_TRACE
   unsigned long long* trace;     // lab build only (scripts/lab/build_trace.sh): clock64 stamps of CTA 0's roles
   int trace_tiles;
@@ -88,10 +89,14 @@ int g_trace_tiles = 0;
 // ---- sweep bookkeeping shared by all roles ----------------------------------------------------------------------------------
 struct Sweep {
   int nb, h, I0, I1, n_steps;
+  int s0, s1;                                  // this CTA's share [s0, s1) of the super-block's J-steps (part `part` of `splits`)
   bool even;
-  __device__ Sweep(int nb_, int sb) : nb(nb_), h(nb_ / 2), I0(2 * sb), I1(2 * sb + 1 < nb_ ? 2 * sb + 1 : -1), even((nb_ & 1) == 0) {
+  __device__ Sweep(int nb_, int sb, int part, int splits)
+      : nb(nb_), h(nb_ / 2), I0(2 * sb), I1(2 * sb + 1 < nb_ ? 2 * sb + 1 : -1), even((nb_ & 1) == 0) {
     n_steps = 0;
     for (int s = h + 1; s >= 0; --s) if (active(0, s) || active(1, s)) { n_steps = s + 1; break; }   // dead steps form a suffix
+    s0 = (int)((long long)n_steps * part / splits);
+    s1 = (int)((long long)n_steps * (part + 1) / splits);
   }
   __device__ int J(int s) const { return (I0 + s) % nb; }
   __device__ int block(int g) const { return g ? I1 : I0; }
@@ -222,7 +227,9 @@ gae_sym_kernel(const __grid_constant__ Params p) {
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bar_area + 224);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const Sweep sw(p.nb, p.sb_begin + blockIdx.x);
+  // a super-block's sweep can be cut into `splits` step ranges (one CTA each) so that the grid fills whole waves of 148 SMs under
+  // sharding; every accumulator is flushed with atomic adds, so the parts are independent
+  const Sweep sw(p.nb, p.sb_begin + (int)blockIdx.x / p.splits, (int)blockIdx.x % p.splits, p.splits);
   const int n_last = p.n - (p.nb - 1) * BT;              // valid rows of the last block (1..128)
   const bool ragged = n_last < BT;
 
@@ -265,9 +272,9 @@ gae_sym_kernel(const __grid_constant__ Params p) {
           tma_load_2d(zi + 2 * ZA_BYTES + jb * 2 * ZT_BOX + ZT_BOX, &p.mT_lo, zi_bar, r0 + jb * 64, 0);
         }
       }
-      for (int s = 0; s < sw.n_steps; ++s) {
-        const int stage = s % STAGES;
-        mbar_wait(stage_free + 8 * stage, ((s / STAGES) & 1) ^ 1);
+      for (int s = sw.s0; s < sw.s1; ++s) {
+        const int ls = s - sw.s0, stage = ls % STAGES;
+        mbar_wait(stage_free + 8 * stage, ((ls / STAGES) & 1) ^ 1);
         const uint32_t fb = full_bar + 8 * stage, st = s_ring + stage * STAGE_BYTES;
         const int c0 = sw.J(s) * BT;
         mbar_expect_tx(fb, STAGE_BYTES);
@@ -290,7 +297,7 @@ gae_sym_kernel(const __grid_constant__ Params p) {
       mbar_wait(zi_bar, 0);
       tc_fence_after();
       auto next_tile = [&](int& s, int& g) {              // advance to the next active tile (s == n_steps: end)
-        do { if (++g == 2) { g = 0; ++s; } } while (s < sw.n_steps && !sw.active(g, s));
+        do { if (++g == 2) { g = 0; ++s; } } while (s < sw.s1 && !sw.active(g, s));
       };
       // A descriptor's start-address field counts 16-byte units in its low 14 bits and shared memory is < 256 KB, so a byte offset is
       // added to a base descriptor as (offset >> 4) without touching the other fields.
@@ -300,13 +307,14 @@ gae_sym_kernel(const __grid_constant__ Params p) {
       if (warp == 1) {
         const uint32_t idesc_s = umma_idesc_f16(BT, BT, 0, 0);        // S = Z_I (K-major, K = 16) Â· Z_J (K-major)
         uint32_t cnt_s = 0;                                           // bit q = phase of S buffer q
-        int s = 0, g = -1, k = 0;
-        for (next_tile(s, g); s < sw.n_steps; next_tile(s, g), ++k) {
-          const int q = k & 1, stage = s % STAGES;
+        int s = sw.s0, g = -1, k = 0;
+        for (next_tile(s, g); s < sw.s1; next_tile(s, g), ++k) {
+          const int ls = s - sw.s0;
+          const int q = k & 1, stage = ls % STAGES;
           if (lane == 0) B2_TRACE(2, k, 0);
           mbar_wait(s_empty + 8 * q, ((cnt_s >> q) & 1u) ^ 1u);       // the group has pulled S(k-2) into registers
           if (lane == 0) B2_TRACE(2, k, 1);
-          mbar_wait(full_bar + 8 * stage, (s / STAGES) & 1);
+          mbar_wait(full_bar + 8 * stage, (ls / STAGES) & 1);
           tc_fence_after();
           if (lane == 0) B2_TRACE(2, k, 2);
           const uint32_t st = s_ring + stage * STAGE_BYTES, zi = s_zi + g * ZI_BYTES;
@@ -331,16 +339,17 @@ gae_sym_kernel(const __grid_constant__ Params p) {
         // per-buffer phase counters packed into scalars (dynamic indexing of local arrays would put them on the stack)
         uint32_t cnt_d = 0, use_d2 = 0, use_d1 = 0, d1_fresh = 0;     // bit q / b3 / segment parity = phase (or flag) of that slot
         int cur_seg = -1;
-        int s = 0, g = -1, k = 0;
-        for (next_tile(s, g); s < sw.n_steps; next_tile(s, g), ++k) {
-          const int q = k & 1, stage = s % STAGES;
+        int s = sw.s0, g = -1, k = 0;
+        for (next_tile(s, g); s < sw.s1; next_tile(s, g), ++k) {
+          const int ls = s - sw.s0;
+          const int q = k & 1, stage = ls % STAGES;
           if (lane == 0) B2_TRACE(3, k, 0);
           mbar_wait(g_full + 8 * q, (cnt_d >> q) & 1u);               // G(k) written
-          mbar_wait(full_bar + 8 * stage, (s / STAGES) & 1);          // (complete long ago: the TMA writes of Z_J made visible to this thread)
+          mbar_wait(full_bar + 8 * stage, (ls / STAGES) & 1);         // (complete long ago: the TMA writes of Z_J made visible to this thread)
           tc_fence_after();
           if (lane == 0) B2_TRACE(3, k, 1);
           const uint32_t zt_j = s_ring + stage * STAGE_BYTES + 2 * ZA_BYTES;
-          const int seg = s / SEG_STEPS, sp = seg & 1;
+          const int seg = ls / SEG_STEPS, sp = seg & 1;
           if (seg != cur_seg) {                    // first dZ_I product of a new segment: its TMEM buffers must have been drained
             mbar_wait(d1_empty + 8 * sp, ((use_d1 >> sp) & 1u) ^ 1u);
             tc_fence_after();
@@ -349,14 +358,14 @@ gae_sym_kernel(const __grid_constant__ Params p) {
           }
           const uint32_t d1 = tmem + TM_D1 + (uint32_t)((sp * 2 + g) * 2 * DW);
           const bool off_diag = !sw.diag(g, s);
-          const int b3 = s % 3;
+          const int b3 = ls % 3;
           const bool first = (g == 0) || !(sw.active(0, s) && !sw.diag(0, s));     // first tile of this step that feeds dZ_J
           if (off_diag && first) {
             mbar_wait(d2_empty + 8 * b3, ((use_d2 >> b3) & 1u) ^ 1u);
             tc_fence_after();
           }
           const bool last = sw.last_of_step(g, s);
-          const bool seg_done = (s % SEG_STEPS == SEG_STEPS - 1 || s == sw.n_steps - 1);
+          const bool seg_done = (ls % SEG_STEPS == SEG_STEPS - 1 || s == sw.s1 - 1);
           if (elect_one_pred()) {
             constexpr uint32_t HI = umma_desc_hi(1024, 2);           // SWIZZLE_128B, 8-row groups 1 KB apart (all four operand views)
             // K-major SWIZZLE_128B view of G: 64 j per 128-byte row; k-step = 32 B inside the row, 64-column blocks 16 KB apart.
@@ -425,7 +434,7 @@ gae_sym_kernel(const __grid_constant__ Params p) {
     const uint32_t xr = (uint32_t)(row & 7);
     {
       int seq = -1;                               // index of the tile in the CTA's tile sequence (same enumeration as the MMA issuer)
-      for (int s = 0; s < sw.n_steps; ++s) {
+      for (int s = sw.s0; s < sw.s1; ++s) {
        for (int g = 0; g < 2; ++g) {
         if (!sw.active(g, s)) continue;
         ++seq;
@@ -456,18 +465,20 @@ gae_sym_kernel(const __grid_constant__ Params p) {
             if (lane == 0) mbar_arrive(s_empty + 8 * q);                   // S[q] is in registers
           }
           uint32_t hi0[8], lo0[8], hi1[8], lo1[8];
-          // G = Ïƒ(x) leaves this lambda as two fp16 planes of 2^11Â·Ïƒ (hi: the top 11 significant bits, lo: the next 11) WITHOUT a
+          // G = Ïƒ(x) leaves this lambda as two fp16 planes of 2^15Â·Ïƒ (hi: the top 11 significant bits, lo: the next 11) WITHOUT a
           // floatâ†’half conversion: F2FP runs on the XU pipe (half the MUFU rate), and with 2 MUFU per logit that pipe is the
-          // kernel's bound (82 % busy once the MMA issue was fixed).  Ïƒ is produced at the scale 2^-5 â€” g = 2^-5Â·Ïƒ âˆˆ [2^-29, 2^-5] after
-          // clamping Ïƒ at 2^-24 â€” so its fp32 exponent field E satisfies E mod 32 = (fp16 exponent field of 2^11Â·Ïƒ): bits 13..28 of the
-          // fp32 word ARE the fp16 word.  Two shifts and a byte permute per pair replace the conversion; the residual g âˆ’ hi goes the
-          // same way (values below 2^-31, i.e. 2^-26 of the largest Ïƒ, saturate there).
+          // kernel's bound (82 % busy once the MMA issue was fixed).  Ïƒ is produced at the scale 2^31 â€” g = 2^31Â·Ïƒ âˆˆ [2^2, 2^31] after
+          // clamping Ïƒ at 2^-29 â€” so that its fp32 exponent field E âˆˆ [129, 158] has bit 5 clear and E mod 32 âˆˆ [1, 30] = the fp16
+          // exponent field of 2^15Â·Ïƒ: bits 13..28 of the fp32 word ARE the fp16 word (sign 0, 5 exponent bits, 10 mantissa bits).
+          // Two shifts and a byte permute per pair replace the conversion; the residual g âˆ’ hi goes the same way (residuals below
+          // 2^2, i.e. 2^-29 of the largest Ïƒ, saturate there â€” exponent field 0 would read as an fp16 subnormal).  Per entry both
+          // clamps move Ïƒ by < 2e-9.
           auto chunk_math = [&](auto full_tag, const uint32_t (&v)[16], int c0, uint32_t (&hi)[8], uint32_t (&lo)[8]) {
             constexpr bool FULL = decltype(full_tag)::value;
-            constexpr float QS = 32.f;                 // q = 2^5Â·(1 + e)
-            constexpr float G_MIN = 1.862645149e-9f;   // 2^-29
-            constexpr float L_MIN = 4.656612873e-10f;  // 2^-31
-            float prod0 = 1.f, prod1 = 1.f;
+            constexpr float QS = 4.656612873e-10f;     // 2^-31: q = 2^-31Â·(1 + e), r = 1 / q = 2^31Â·Ïƒ(|x|)
+            constexpr float G_MIN = 4.f;               // 2^31 Â· 2^-29
+            constexpr float L_MIN = 4.f;
+            float prod[4] = {1.f, 1.f, 1.f, 1.f};      // four factors each: â‰¥ 2^-124 (normal)
             float gg[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
@@ -479,12 +490,11 @@ gae_sym_kernel(const __grid_constant__ Params p) {
               float gc = fmaxf(x >= 0.f ? r : er, G_MIN);
               if (FULL) {
                 abs_t += fabsf(x);
-                if (c & 1) prod1 *= q; else prod0 *= q;
+                prod[c & 3] *= q;
               } else {
                 const bool valid = row_ok && (c0 + c < col_end);
                 abs_t += valid ? fabsf(x) : 0.f;
-                const float f = valid ? q : QS;
-                if (c & 1) prod1 *= f; else prod0 *= f;
+                prod[c & 3] *= valid ? q : QS;
                 gc = valid ? gc : 0.f;
               }
               gg[c] = gc;
@@ -503,7 +513,7 @@ gae_sym_kernel(const __grid_constant__ Params p) {
               }
               lo[c >> 1] = __byte_perm(__float_as_uint(l0) << 3, __float_as_uint(l1) << 3, 0x7632);
             }
-            lg_t += lg2a(prod0) + lg2a(prod1);
+            lg_t += (lg2a(prod[0]) + lg2a(prod[1])) + (lg2a(prod[2]) + lg2a(prod[3]));
           };
           if (!masked) {
             chunk_math(std::true_type{}, v0, cofs, hi0, lo0);
@@ -539,8 +549,8 @@ gae_sym_kernel(const __grid_constant__ Params p) {
       }
     }
     // Î£ softplus over this thread's logits (both orientations of off-diagonal tiles) = ln2Â·[Â½Î£|v| + Î£log2(1+e)], the Â½Î£v half is
-    // added in closed form by linear_term_kernel; every logit carried a 2^5 factor inside the products
-    double loss = (double)LN2 * (0.5 * (double)abs_w + (double)lg_w - 5.0 * 16.0 * (double)chunks_w);
+    // added in closed form by linear_term_kernel; every logit carried a 2^-31 factor inside the products
+    double loss = (double)LN2 * (0.5 * (double)abs_w + (double)lg_w + 31.0 * 16.0 * (double)chunks_w);
     loss = warp_sum(loss);
     if (lane == 0 && loss != 0.0) atomicAdd(p.loss_acc, loss * (double)p.coef);
   } else {
@@ -567,13 +577,14 @@ gae_sym_kernel(const __grid_constant__ Params p) {
         }
       }
     };
-    for (int s = 0; s < sw.n_steps; ++s) {
+    for (int s = sw.s0; s < sw.s1; ++s) {
+      const int ls = s - sw.s0;
       if (sw.has_d2(s)) {
-        const int b3 = s % 3;
-        if (sub == 0 && lane == 0) B2_TRACE(4, s, 0);
+        const int b3 = ls % 3;
+        if (sub == 0 && lane == 0) B2_TRACE(4, ls, 0);
         mbar_wait(d2_full + 8 * b3, (fcnt >> b3) & 1u);
         tc_fence_after();
-        if (sub == 0 && lane == 0) B2_TRACE(4, s, 1);
+        if (sub == 0 && lane == 0) B2_TRACE(4, ls, 1);
         uint32_t a0[16], a1[16];
         tmem_ld_32x32b_x16(tmem + lane_off + TM_D2 + (uint32_t)(b3 * 2 * DW), a0);
         tmem_ld_32x32b_x16(tmem + lane_off + TM_D2 + (uint32_t)(b3 * 2 * DW + DW), a1);
@@ -582,15 +593,15 @@ gae_sym_kernel(const __grid_constant__ Params p) {
         if (lane == 0) mbar_arrive(d2_empty + 8 * b3);
         fcnt ^= 1u << b3;
         add_rows(sw.J(s), a0, a1);
-        if (sub == 0 && lane == 0) B2_TRACE(4, s, 2);
+        if (sub == 0 && lane == 0) B2_TRACE(4, ls, 2);
       }
-      if (s % SEG_STEPS == SEG_STEPS - 1 || s == sw.n_steps - 1) {
+      if (ls % SEG_STEPS == SEG_STEPS - 1 || s == sw.s1 - 1) {
         // a dZ_I segment is complete: [GÂ·Z_hi | GÂ·Z_lo] of both owned blocks â†’ global (atomic: other CTAs add to the same rows)
-        const int seg = s / SEG_STEPS, sp = seg & 1;
+        const int seg = ls / SEG_STEPS, sp = seg & 1;
         mbar_wait(d1_full + 8 * sp, (f1cnt >> sp) & 1u);
         tc_fence_after();
         bool wrote0 = false, wrote1 = false;
-        for (int s2 = seg * SEG_STEPS; s2 <= s; ++s2) { wrote0 |= sw.active(0, s2); wrote1 |= sw.active(1, s2); }
+        for (int s2 = sw.s0 + seg * SEG_STEPS; s2 <= s; ++s2) { wrote0 |= sw.active(0, s2); wrote1 |= sw.active(1, s2); }
         {
           uint32_t a0[16], a1[16];
           if (wrote0) {
@@ -700,9 +711,26 @@ int launch(const float* z, int64_t ldz, int32_t n, int32_t d, int32_t sb_begin, 
     B2_CHECK_CUDA(cudaFuncSetAttribute(gae_sym_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  gae_sym_kernel<false><<<sb_end - sb_begin, THREADS, smem, st>>>(p);
+  // CTAs per super-block: whole waves of SMs.  A rank's share of the super-blocks (e.g. 489 of 3 907 at 8 GPUs = 3.3 waves of 148)
+  // would idle a large part of the last wave; cutting every sweep into 2â€“8 step ranges makes the grid many small waves.
+  const int n_sb = sb_end - sb_begin, n_steps_min = p.nb / 2;
+  int splits = tuning(B2_TUNE_GAE_SPLITS);
+  if (splits <= 0) {
+    splits = 1;
+    double best = 0.0;
+    const int cand[6] = {1, 2, 3, 4, 6, 8};
+    for (int c = 0; c < 6; ++c) {
+      if (cand[c] > 1 && n_steps_min / cand[c] < 4 * SEG_STEPS) break;
+      const double waves = (double)n_sb * cand[c] / sm_count();
+      const double eff = waves / ceil(waves);
+      if (eff > best + 0.015) { best = eff; splits = cand[c]; }
+    }
+  }
+  if (splits > 1 && n_steps_min / splits < 1) splits = 1;
+  p.splits = splits;
+  gae_sym_kernel<false><<<n_sb * splits, THREADS, smem, st>>>(p);
   B2_CHECK_LAUNCH("gae_sym_kernel");
-  gae_sym_kernel<true><<<sb_end - sb_begin, THREADS, smem, st>>>(p);      // no-op unless the embedding needed operand scaling
+  gae_sym_kernel<true><<<n_sb * splits, THREADS, smem, st>>>(p);      // no-op unless the embedding needed operand scaling
   B2_CHECK_LAUNCH("gae_sym_kernel<scaled>");
   return B2_OK;
 }

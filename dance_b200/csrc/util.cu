@@ -40,7 +40,7 @@ static int g_path[B2_PATH_COUNT] = {0, 0, 0};
 int path_mode(int which) { return (which >= 0 && which < B2_PATH_COUNT) ? g_path[which] : 0; }
 
 // scheduling knobs of the tensor-core decoder (b2_set_tuning): they move work in time, never change a result
-static int g_tune[B2_TUNE_COUNT] = {1500, 1};
+static int g_tune[B2_TUNE_COUNT] = {1500, 1, 0};
 int tuning(int which) { return (which >= 0 && which < B2_TUNE_COUNT) ? g_tune[which] : 0; }
 
 }  // namespace b2

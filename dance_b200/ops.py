@@ -138,8 +138,8 @@ def set_path(which: str, mode: str = "auto") -> None:
 
 
 def set_tuning(knob: str, value: int) -> None:
-    """Scheduling knobs of the symmetric decoder ("gae_stagger" cycles, "gae_late_gempty" 0/1): timing experiments only."""
-    check(lib().b2_set_tuning({"gae_stagger": 0, "gae_late_gempty": 1}[knob], int(value)), "b2_set_tuning")
+    """Scheduling knobs of the symmetric decoder ("gae_stagger" cycles, "gae_late_gempty" 0/1, "gae_splits" CTAs per super-block, 0 = automatic): timing experiments only."""
+    check(lib().b2_set_tuning({"gae_stagger": 0, "gae_late_gempty": 1, "gae_splits": 2}[knob], int(value)), "b2_set_tuning")
 
 
 def get_path(which: str) -> str:

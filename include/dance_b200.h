@@ -56,7 +56,8 @@ int b2_get_path(int which);
 /* Scheduling knobs of the symmetric decoder (timing experiments; results do not depend on them). */
 #define B2_TUNE_GAE_STAGGER 0     /* initial delay (cycles) of the second elementwise group, default 1500 */
 #define B2_TUNE_GAE_LATE_GEMPTY 1 /* 1 (default): the elementwise group waits for its G buffer after the first half's math; 0: before loading S */
-#define B2_TUNE_COUNT 2
+#define B2_TUNE_GAE_SPLITS 2      /* CTAs per super-block of the symmetric decoder (0 = automatic: fill whole waves of SMs) */
+#define B2_TUNE_COUNT 3
 int b2_set_tuning(int which, int value);
 
 const char* b2_last_error(void);

@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-timeout -k 5 200 python -m pytest tests/test_gpu_kernels.py -m gpu -q -k "symmetric or large_embedding or pair_sharded or spmm or gae" --tb=short -rf -p no:cacheprovider --timeout 90 > gpurun_out/r_tests.log 2>&1
+timeout -k 5 200 python -m pytest tests/test_gpu_kernels.py -m gpu -q -k "symmetric or large_embedding or pair_sharded or spmm or gae or step_splits" --tb=short -rf -p no:cacheprovider --timeout 90 > gpurun_out/r_tests.log 2>&1
 rc=$?; tail -8 gpurun_out/r_tests.log | cut -c1-300
 if [ $rc -ne 0 ]; then echo "GATE FAILED rc=$rc"; exit 1; fi
 timeout -k 5 100 python scripts/sym_tune.py 200000 2>&1 | tail -6

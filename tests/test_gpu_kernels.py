@@ -469,6 +469,33 @@ def test_gae_symmetric_decoder_small_graphs(cuda, n, d):
     assert rel_err(dz, dz_r) < 2e-5 and abs(loss.item() - loss_r.item()) < 2e-6 * abs(ref_loss)
 
 
+@pytest.mark.parametrize("n,splits", [(1537, 2), (2049, 3), (2049, 5), (8200, 2), (8200, 3), (8200, 8)])
+def test_gae_symmetric_decoder_step_splits(cuda, n, splits):
+    """A super-block's J sweep cut into `splits` step ranges, one CTA each (what fills whole waves of SMs under sharding): the same
+    loss and gradient as the unsplit sweep and as the fp64 closed form — including parts of one or two steps, parts that start in
+    the middle of an accumulation segment, and more parts than some super-blocks have steps."""
+    from dance_b200 import ops
+    gen = torch.Generator(device=cuda).manual_seed(n + splits)
+    z = (torch.randn(n, 16, device=cuda, generator=gen) * 0.5).contiguous()
+    idx = torch.randint(0, n, (n, 6), device=cuda, dtype=torch.int32, generator=gen)
+    A = ops.knn_graph_build(idx.contiguous())
+    L = ops.CSR(A.rowptr, A.colidx, None, A.shape)
+    norm, pw = 0.5, 55.0
+    rows = torch.arange(n, device=cuda) if n <= 2049 else torch.randint(0, n, (300, ), device=cuda, generator=gen)
+    _, ref_rows = gae_reference_rows(z, A.rowptr, A.colidx, norm, pw, rows)
+    ops.set_path("gae", "sym")
+    try:
+        ops.set_tuning("gae_splits", 1)
+        loss1, dz1, _, _ = ops.gae_loss_grad(z, L, norm, pw)
+        ops.set_tuning("gae_splits", splits)
+        loss, dz, _, _ = ops.gae_loss_grad(z, L, norm, pw)
+    finally:
+        ops.set_tuning("gae_splits", 0)
+        ops.set_path("gae", "auto")
+    assert rel_err(dz[rows], ref_rows) < 2e-5 and rel_err(dz, dz1) < 2e-6
+    assert abs(loss.item() - loss1.item()) < 2e-6 * abs(loss1.item())
+
+
 @pytest.mark.parametrize("n,path,scale", [(4500, "sym", 3.0e4), (4500, "sym", 40.0), (3000, "f16", 3.0e4), (3000, "cuda", 3.0e4)])
 def test_gae_decoder_large_embedding(cuda, n, path, scale):
     """Embeddings far beyond the fp16 operand range (an untrained Graph-AE at 1 M cells draws z = mu + eps·exp(logvar) with logvar ≈ 14,
