@@ -418,9 +418,9 @@ def main():
                 ts.append(s_.elapsed_time(e_))
         ms16 = float(np.median(ts))
         b16 = A.nnz * 8 + (n_loc + 1) * 4 + N * 32 * 2 + n_loc * 32 * 4
-        spmm16 = {"kernel": "spmm_csr_x16_kernel (Â·support, F=32, bf16 operand, fp32 accumulate/output)", "bound": "hbm",
+        spmm16 = {"kernel": "spmm_stream_kernel<bf16, 64 B rows> (Â·support, F=32, bf16 operand, fp32 accumulate/output)", "bound": "hbm",
                   "achieved": b16 / (ms16 * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                  "frac": b16 / (ms16 * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": traffic_from_profiles("spmm_csr_x16_kernel"),
+                  "frac": b16 / (ms16 * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": traffic_from_profiles("spmm_stream_kernel<bf16>"),
                   "ms_per_launch": ms16, "algorithmic_bytes": b16, "l2_policy": "256 MB flush between launches", "peak_source": peaks["source"]}
         del flush, S16, out
 
@@ -528,8 +528,8 @@ def main():
     roof_spmm = None
     if spmm_ms:
         ach = spmm_bytes / (spmm_ms * 1e-3) / 1e9
-        roof_spmm = {"kernel": "spmm_csr_kernel (Â·support, F=32, fp32 operand)", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": ach / peaks["hbm_gbs"], "traffic": traffic_from_profiles("spmm_csr_kernel"), "launches": spmm_n, "ms_per_launch": spmm_ms,
+        roof_spmm = {"kernel": "spmm_stream_kernel<f32, 128 B rows> (Â·support, F=32, fp32 operand; nnz-stream pipeline, cp.async-staged gathers)", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": ach / peaks["hbm_gbs"], "traffic": traffic_from_profiles("spmm_stream_kernel<f32>"), "launches": spmm_n, "ms_per_launch": spmm_ms,
                      "algorithmic_bytes": spmm_bytes, "gather_bytes_through_l2": nnz_loc * F * 4, "peak_source": peaks["source"]}
     gemm_ms, gemm_n, gemm_total = kt("gemm_f32")
     fae_flops = 6.0 * n_loc * (G * 512 + 512 * 128 + 128 * 512 + 512 * G)       # fwd + dX + dW, 2 flops per MAC

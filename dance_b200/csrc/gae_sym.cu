@@ -54,7 +54,7 @@ constexpr uint32_t TM_S = 0, TM_D1 = 256, TM_D2 = 384, TM_COLS = 512;   // S: 2Ã
 // (â‰¤ 128 accumulations), double-buffered in TMEM; the flush warps add each finished segment to global memory (round-to-nearest
 // atomics) while the next one accumulates.  dZ_J is flushed every step anyway.
 constexpr int SEG_STEPS = 8;
-constexpr float G_SCALE = 32768.f;        // the MMAs see G = 2^15Â·Ïƒ (fp16 planes; see chunk_math)
+constexpr float G_SCALE = 2048.f;
 constexpr int STAGGER_CYCLES = 1500;
 
 struct Params {
@@ -190,6 +190,23 @@ __global__ void linear_term_kernel(const double* __restrict__ zsum, int d, float
 
 __device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2a(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// packed fp32 pairs (Blackwell FFMA2 / FMUL2): one issue slot for two lanes' worth of a pair â€” the elementwise warps are bound by issue slots
+__device__ __forceinline__ unsigned long long pk2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(unsigned long long r, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+__device__ __forceinline__ unsigned long long ffma2p(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long fmul2p(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 __device__ __forceinline__ float rcpa(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -465,55 +482,67 @@ gae_sym_kernel(const __grid_constant__ Params p) {
             if (lane == 0) mbar_arrive(s_empty + 8 * q);                   // S[q] is in registers
           }
           uint32_t hi0[8], lo0[8], hi1[8], lo1[8];
-          // G = Ïƒ(x) leaves this lambda as two fp16 planes of 2^15Â·Ïƒ (hi: the top 11 significant bits, lo: the next 11) WITHOUT a
-          // floatâ†’half conversion: F2FP runs on the XU pipe (half the MUFU rate), and with 2 MUFU per logit that pipe is the
-          // kernel's bound (82 % busy once the MMA issue was fixed).  Ïƒ is produced at the scale 2^31 â€” g = 2^31Â·Ïƒ âˆˆ [2^2, 2^31] after
-          // clamping Ïƒ at 2^-29 â€” so that its fp32 exponent field E âˆˆ [129, 158] has bit 5 clear and E mod 32 âˆˆ [1, 30] = the fp16
-          // exponent field of 2^15Â·Ïƒ: bits 13..28 of the fp32 word ARE the fp16 word (sign 0, 5 exponent bits, 10 mantissa bits).
-          // Two shifts and a byte permute per pair replace the conversion; the residual g âˆ’ hi goes the same way (residuals below
-          // 2^2, i.e. 2^-29 of the largest Ïƒ, saturate there â€” exponent field 0 would read as an fp16 subnormal).  Per entry both
-          // clamps move Ïƒ by < 2e-9.
+          // (Tried: building the two fp16 planes by bit extraction from a 2^31-scaled Ïƒ â€” no F2FP, 4 fewer XU cycles per warp-logit â€”
+          // correct, but 11 % SLOWER: the elementwise warps are bound by issue slots, not by the XU pipe; the conversion instructions
+          // were cheaper than the shifts, permutes and clamps that replaced them.)
           auto chunk_math = [&](auto full_tag, const uint32_t (&v)[16], int c0, uint32_t (&hi)[8], uint32_t (&lo)[8]) {
             constexpr bool FULL = decltype(full_tag)::value;
-            constexpr float QS = 4.656612873e-10f;     // 2^-31: q = 2^-31Â·(1 + e), r = 1 / q = 2^31Â·Ïƒ(|x|)
-            constexpr float G_MIN = 4.f;               // 2^31 Â· 2^-29
-            constexpr float L_MIN = 4.f;
-            float prod[4] = {1.f, 1.f, 1.f, 1.f};      // four factors each: â‰¥ 2^-124 (normal)
+            if (FULL) {
+              // interior tiles: the four FMA-pipe operations per logit that have no per-lane modifier are issued as packed pairs
+              const unsigned long long ginv2 = pk2(1.f / G_SCALE, 1.f / G_SCALE), mone2 = pk2(-1.f, -1.f);
+              unsigned long long prod2 = pk2(1.f, 1.f);
+#pragma unroll
+              for (int c = 0; c < 16; c += 2) {
+                const float x0 = SCALED ? __uint_as_float(v[c]) * vs : __uint_as_float(v[c]);
+                const float x1 = SCALED ? __uint_as_float(v[c + 1]) * vs : __uint_as_float(v[c + 1]);
+                const unsigned long long e2 = pk2(ex2a(-fabsf(x0)), ex2a(-fabsf(x1)));
+                const unsigned long long q2 = ffma2p(e2, ginv2, ginv2);           // (1 + e) / G
+                float q0, q1, er0, er1;
+                upk2(q2, q0, q1);
+                const float r0 = rcpa(q0), r1 = rcpa(q1);                          // G / (1 + e)
+                upk2(fmul2p(e2, pk2(r0, r1)), er0, er1);
+                const float g0 = x0 >= 0.f ? r0 : er0, g1 = x1 >= 0.f ? r1 : er1; // GÂ·Ïƒ(x)
+                abs_t += fabsf(x0);
+                abs_t += fabsf(x1);
+                prod2 = fmul2p(prod2, q2);
+                const float h0 = __uint_as_float(__float_as_uint(g0) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(g1) & 0xFFFFE000u);
+                float l0, l1;
+                upk2(ffma2p(pk2(h0, h1), mone2, pk2(g0, g1)), l0, l1);            // g âˆ’ hi, exact
+                const __half2 h2 = __floats2half2_rn(h0, h1);
+                const __half2 l2 = __floats2half2_rn(l0, l1);
+                hi[c >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                lo[c >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+              }
+              float p0, p1;
+              upk2(prod2, p0, p1);
+              lg_t += lg2a(p0) + lg2a(p1);
+              return;
+            }
+            float prod0 = 1.f, prod1 = 1.f;
             float gg[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
               const float x = SCALED ? __uint_as_float(v[c]) * vs : __uint_as_float(v[c]);
               const float e = ex2a(-fabsf(x));
-              const float q = fmaf(e, QS, QS);
+              const float q = fmaf(e, 1.f / G_SCALE, 1.f / G_SCALE);
               const float r = rcpa(q);
               const float er = e * r;
-              float gc = fmaxf(x >= 0.f ? r : er, G_MIN);
-              if (FULL) {
-                abs_t += fabsf(x);
-                prod[c & 3] *= q;
-              } else {
-                const bool valid = row_ok && (c0 + c < col_end);
-                abs_t += valid ? fabsf(x) : 0.f;
-                prod[c & 3] *= valid ? q : QS;
-                gc = valid ? gc : 0.f;
-              }
-              gg[c] = gc;
+              float gc = x >= 0.f ? r : er;
+              const bool valid = row_ok && (c0 + c < col_end);
+              abs_t += valid ? fabsf(x) : 0.f;
+              const float f = valid ? q : 1.f / G_SCALE;
+              if (c & 1) prod1 *= f; else prod0 *= f;
+              gg[c] = valid ? gc : 0.f;
             }
 #pragma unroll
             for (int c = 0; c < 16; c += 2) {
-              const uint32_t b0 = __float_as_uint(gg[c]), b1 = __float_as_uint(gg[c + 1]);
-              hi[c >> 1] = __byte_perm(b0 << 3, b1 << 3, 0x7632);
-              float l0 = gg[c] - __uint_as_float(b0 & 0xFFFFE000u), l1 = gg[c + 1] - __uint_as_float(b1 & 0xFFFFE000u);
-              if (FULL) {
-                l0 = fmaxf(l0, L_MIN);
-                l1 = fmaxf(l1, L_MIN);
-              } else {
-                l0 = b0 ? fmaxf(l0, L_MIN) : 0.f;      // masked entries stay exactly zero
-                l1 = b1 ? fmaxf(l1, L_MIN) : 0.f;
-              }
-              lo[c >> 1] = __byte_perm(__float_as_uint(l0) << 3, __float_as_uint(l1) << 3, 0x7632);
+              const float h0 = __uint_as_float(__float_as_uint(gg[c]) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(gg[c + 1]) & 0xFFFFE000u);
+              const __half2 h2 = __floats2half2_rn(h0, h1);
+              const __half2 l2 = __floats2half2_rn(gg[c] - h0, gg[c + 1] - h1);
+              hi[c >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+              lo[c >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
             }
-            lg_t += (lg2a(prod[0]) + lg2a(prod[1])) + (lg2a(prod[2]) + lg2a(prod[3]));
+            lg_t += lg2a(prod0) + lg2a(prod1);
           };
           if (!masked) {
             chunk_math(std::true_type{}, v0, cofs, hi0, lo0);
@@ -549,8 +578,8 @@ gae_sym_kernel(const __grid_constant__ Params p) {
       }
     }
     // Î£ softplus over this thread's logits (both orientations of off-diagonal tiles) = ln2Â·[Â½Î£|v| + Î£log2(1+e)], the Â½Î£v half is
-    // added in closed form by linear_term_kernel; every logit carried a 2^-31 factor inside the products
-    double loss = (double)LN2 * (0.5 * (double)abs_w + (double)lg_w + 31.0 * 16.0 * (double)chunks_w);
+    // added in closed form by linear_term_kernel; every logit carried a 2^-11 factor inside the products
+    double loss = (double)LN2 * (0.5 * (double)abs_w + (double)lg_w + 11.0 * 16.0 * (double)chunks_w);
     loss = warp_sum(loss);
     if (lane == 0 && loss != 0.0) atomicAdd(p.loss_acc, loss * (double)p.coef);
   } else {
