@@ -190,23 +190,6 @@ __global__ void linear_term_kernel(const double* __restrict__ zsum, int d, float
 
 __device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2a(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-// packed fp32 pairs (Blackwell FFMA2 / FMUL2): one issue slot for two lanes' worth of a pair — the elementwise warps are bound by issue slots
-__device__ __forceinline__ unsigned long long pk2(float a, float b) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void upk2(unsigned long long r, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
-__device__ __forceinline__ unsigned long long ffma2p(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ unsigned long long fmul2p(unsigned long long a, unsigned long long b) {
-  unsigned long long d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
 __device__ __forceinline__ float rcpa(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -482,42 +465,12 @@ gae_sym_kernel(const __grid_constant__ Params p) {
             if (lane == 0) mbar_arrive(s_empty + 8 * q);                   // S[q] is in registers
           }
           uint32_t hi0[8], lo0[8], hi1[8], lo1[8];
-          // (Tried: building the two fp16 planes by bit extraction from a 2^31-scaled σ — no F2FP, 4 fewer XU cycles per warp-logit —
-          // correct, but 11 % SLOWER: the elementwise warps are bound by issue slots, not by the XU pipe; the conversion instructions
-          // were cheaper than the shifts, permutes and clamps that replaced them.)
+          // Two variants of this math were measured and dropped (both correct): (a) the fp16 planes by bit extraction from a 2^31-scaled σ
+          // — no F2FP, 4 fewer XU cycles per warp-logit — was 11 % SLOWER: the shifts, permutes and clamps cost more issue slots than
+          // the conversions; (b) the four modifier-free FMA-pipe operations per logit as packed FFMA2 / FMUL2 pairs was 5 % slower
+          // (packed fp32 only issues to one half of the FMA pipe).
           auto chunk_math = [&](auto full_tag, const uint32_t (&v)[16], int c0, uint32_t (&hi)[8], uint32_t (&lo)[8]) {
             constexpr bool FULL = decltype(full_tag)::value;
-            if (FULL) {
-              // interior tiles: the four FMA-pipe operations per logit that have no per-lane modifier are issued as packed pairs
-              const unsigned long long ginv2 = pk2(1.f / G_SCALE, 1.f / G_SCALE), mone2 = pk2(-1.f, -1.f);
-              unsigned long long prod2 = pk2(1.f, 1.f);
-#pragma unroll
-              for (int c = 0; c < 16; c += 2) {
-                const float x0 = SCALED ? __uint_as_float(v[c]) * vs : __uint_as_float(v[c]);
-                const float x1 = SCALED ? __uint_as_float(v[c + 1]) * vs : __uint_as_float(v[c + 1]);
-                const unsigned long long e2 = pk2(ex2a(-fabsf(x0)), ex2a(-fabsf(x1)));
-                const unsigned long long q2 = ffma2p(e2, ginv2, ginv2);           // (1 + e) / G
-                float q0, q1, er0, er1;
-                upk2(q2, q0, q1);
-                const float r0 = rcpa(q0), r1 = rcpa(q1);                          // G / (1 + e)
-                upk2(fmul2p(e2, pk2(r0, r1)), er0, er1);
-                const float g0 = x0 >= 0.f ? r0 : er0, g1 = x1 >= 0.f ? r1 : er1; // G·σ(x)
-                abs_t += fabsf(x0);
-                abs_t += fabsf(x1);
-                prod2 = fmul2p(prod2, q2);
-                const float h0 = __uint_as_float(__float_as_uint(g0) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(g1) & 0xFFFFE000u);
-                float l0, l1;
-                upk2(ffma2p(pk2(h0, h1), mone2, pk2(g0, g1)), l0, l1);            // g − hi, exact
-                const __half2 h2 = __floats2half2_rn(h0, h1);
-                const __half2 l2 = __floats2half2_rn(l0, l1);
-                hi[c >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
-                lo[c >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
-              }
-              float p0, p1;
-              upk2(prod2, p0, p1);
-              lg_t += lg2a(p0) + lg2a(p1);
-              return;
-            }
             float prod0 = 1.f, prod1 = 1.f;
             float gg[16];
 #pragma unroll
@@ -528,11 +481,17 @@ gae_sym_kernel(const __grid_constant__ Params p) {
               const float r = rcpa(q);
               const float er = e * r;
               float gc = x >= 0.f ? r : er;
-              const bool valid = row_ok && (c0 + c < col_end);
-              abs_t += valid ? fabsf(x) : 0.f;
-              const float f = valid ? q : 1.f / G_SCALE;
-              if (c & 1) prod1 *= f; else prod0 *= f;
-              gg[c] = valid ? gc : 0.f;
+              if (FULL) {
+                abs_t += fabsf(x);
+                if (c & 1) prod1 *= q; else prod0 *= q;
+              } else {
+                const bool valid = row_ok && (c0 + c < col_end);
+                abs_t += valid ? fabsf(x) : 0.f;
+                const float f = valid ? q : 1.f / G_SCALE;
+                if (c & 1) prod1 *= f; else prod0 *= f;
+                gc = valid ? gc : 0.f;
+              }
+              gg[c] = gc;
             }
 #pragma unroll
             for (int c = 0; c < 16; c += 2) {
@@ -752,7 +711,7 @@ int launch(const float* z, int64_t ldz, int32_t n, int32_t d, int32_t sb_begin, 
       if (cand[c] > 1 && n_steps_min / cand[c] < 4 * SEG_STEPS) break;
       const double waves = (double)n_sb * cand[c] / sm_count();
       const double eff = waves / ceil(waves);
-      if (eff > best + 0.015) { best = eff; splits = cand[c]; }
+      if (eff > best + 0.03) { best = eff; splits = cand[c]; }       // measured: 125 k cells 7.5 → 6.6 ms with 2–8 parts, 1 M cells neutral
     }
   }
   if (splits > 1 && n_steps_min / splits < 1) splits = 1;
