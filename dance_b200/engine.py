@@ -77,6 +77,7 @@ class FeatureAEEngine:
         self.params = FlatParams([("fc1.weight", (H, dim)), ("fc1.bias", (H, )), ("fc2.weight", (E, H)), ("fc2.bias", (E, )),
                                   ("fc3.weight", (H, E)), ("fc3.bias", (H, )), ("fc4.weight", (dim, H)), ("fc4.bias", (dim, ))],
                                  self.device)
+        self.seed = seed
         gen = torch.Generator().manual_seed(seed) if seed is not None else None
         for i in (1, 2, 3, 4):
             _linear_init_(self.params.p[f"fc{i}.weight"], self.params.p[f"fc{i}.bias"], gen)
@@ -106,6 +107,16 @@ class FeatureAEEngine:
         return bufs
 
     # -- forward ----------------------------------------------------------------
+    def input_dropout(self, x: torch.Tensor, p: float) -> torch.Tensor:
+        """``F.dropout(x, p)`` with this engine's device generator (inverted dropout: kept entries scaled by 1 / (1 - p))."""
+        if not 0.0 <= p < 1.0:
+            raise ValueError("dropout probability must be in [0, 1)")
+        if getattr(self, "_drop_gen", None) is None:
+            self._drop_gen = torch.Generator(device=self.device)
+            self._drop_gen.manual_seed(int(self.seed) + 7919 if getattr(self, "seed", None) is not None else torch.seed() % (2**31))
+        keep = torch.rand(x.shape, device=self.device, generator=self._drop_gen) >= p
+        return x * keep.to(torch.float32).mul_(1.0 / (1.0 - p))
+
     def forward(self, x: torch.Tensor, bufs=None):
         """Returns (z, recon) like Feature_AE.forward (scgnn2.py:368-370)."""
         P, pr = self.params.p, self.precision
@@ -119,14 +130,17 @@ class FeatureAEEngine:
     # -- one optimiser step -------------------------------------------------------
     def train_step(self, x: torch.Tensor, ltmg: Optional[torch.Tensor] = None, regu_strength: float = 0.9,
                    regularizer_type: str = "noregu", slot: int = 0, row_weight: Optional[torch.Tensor] = None,
-                   x_dropout: Optional[torch.Tensor] = None):
+                   x_dropout: Optional[torch.Tensor] = None, x_input: Optional[torch.Tensor] = None):
         """One mini-batch of train_handler (scgnn2.py:1256-1281): forward, loss_function_graph
         ('noregu' | 'LTMG'), backward, Adam.  The batch loss is accumulated into ``self.loss_acc``.
+        ``x_input``: what the network sees when it differs from the loss target ``x`` — ``F.dropout(data, p=masked_prob)`` of
+        train_handler (scgnn2.py:1256); the first layer's weight gradient is taken against it.
         Returns (z, recon) views into the engine's buffers (valid until the next call with the same batch size)."""
         P, G, pr = self.params.p, self.params.g, self.precision
         B = x.shape[0]
         b = self._buffers(B, slot)
-        z, r = self.forward(x, b)
+        x_in = x if x_input is None else x_input
+        z, r = self.forward(x_in, b)
         if regularizer_type == "noregu":
             ops.mse_sum_loss_grad(r, x, None, 0.0, relu_mask=True, grad=b["dr"], loss_out=self.loss_acc)
         elif regularizer_type == "LTMG":
@@ -151,7 +165,7 @@ class FeatureAEEngine:
         ops.colsum(b["dz"], out=G["fc2.bias"])
         ops.gemm(b["dz"], P["fc2.weight"], mask=b["h1"], out=b["dh1"], precision=pr)
         # layer 1
-        ops.gemm(b["dh1"], x, transA=True, out=G["fc1.weight"], precision=pr)
+        ops.gemm(b["dh1"], x_in, transA=True, out=G["fc1.weight"], precision=pr)
         ops.colsum(b["dh1"], out=G["fc1.bias"])
         if regularizer_type == "Celltype":
             # `loss = loss + 1 * l1 + 0 * l2` over all parameters (train_handler, scgnn2.py:1268-1274)

@@ -25,8 +25,8 @@ class ScDeepSort:
 
     def __init__(self, dim_in: int, dim_hid: int, num_layers: int, species: str = "", tissue: str = "", *, dropout: int = 0,
                  batch_size: int = 500, device: str = "cuda", precision: Optional[str] = None, seed: Optional[int] = None):
-        if num_layers != 1:
-            raise NotImplementedError("only num_layers=1 (the example default, scdeepsort.py(ex):25) is built")
+        if num_layers < 1:
+            raise ValueError("num_layers must be >= 1")
         if not 0.0 <= float(dropout) < 1.0:
             raise ValueError("dropout must be in [0, 1)")
         self.dense_dim, self.hidden_dim, self.n_layers = dim_in, dim_hid, num_layers
@@ -43,13 +43,19 @@ class ScDeepSort:
     def _build(self, num_genes: int, num_labels: int):
         gen = torch.Generator().manual_seed(self.seed) if self.seed is not None else None
         self.num_genes, self.num_labels = int(num_genes), int(num_labels)
-        self.params = FlatParams([("alpha", (self.num_genes + 2, 1)), ("layers.0.layers.1.weight", (self.hidden_dim, self.dense_dim)),
-                                  ("layers.0.layers.1.bias", (self.hidden_dim, )), ("linear.weight", (self.num_labels, self.hidden_dim)),
-                                  ("linear.bias", (self.num_labels, ))], self.device)
+        # n_layers AdaptiveSAGE layers (dense_dim → hidden, then hidden → hidden; scdeepsort.py:77-80) and the output Linear.  Every layer's
+        # output depends on the destination node's own features only (module docstring), so the stack is an MLP on the cell features.
+        spec = [("alpha", (self.num_genes + 2, 1))]
+        for i in range(self.n_layers):
+            spec += [(f"layers.{i}.layers.1.weight", (self.hidden_dim, self.dense_dim if i == 0 else self.hidden_dim)),
+                     (f"layers.{i}.layers.1.bias", (self.hidden_dim, ))]
+        spec += [("linear.weight", (self.num_labels, self.hidden_dim)), ("linear.bias", (self.num_labels, ))]
+        self.params = FlatParams(spec, self.device)
         P = self.params.p
         P["alpha"].fill_(1.0)                                                           # scdeepsort.py:72
         gain = 2.0**0.5                                                                 # calculate_gain("relu")
-        for w, b in ((P["layers.0.layers.1.weight"], P["layers.0.layers.1.bias"]), (P["linear.weight"], P["linear.bias"])):
+        for w, b in [(P[f"layers.{i}.layers.1.weight"], P[f"layers.{i}.layers.1.bias"]) for i in range(self.n_layers)] + \
+                [(P["linear.weight"], P["linear.bias"])]:
             fan_out, fan_in = w.shape
             w.copy_((torch.rand(w.shape, generator=gen) * 2 - 1) * gain * (6.0 / (fan_in + fan_out))**0.5)   # xavier_uniform_(gain)
             b.copy_((torch.rand(b.shape, generator=gen) * 2 - 1) / fan_in**0.5)                              # nn.Linear default
@@ -57,43 +63,61 @@ class ScDeepSort:
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         sd = {k: v.detach().clone() for k, v in self.params.p.items()}
-        sd["layers.0.alpha"] = sd["alpha"].clone()     # the same Parameter is registered twice in the reference (gnn.py:50)
+        for i in range(self.n_layers):
+            sd[f"layers.{i}.alpha"] = sd["alpha"].clone()     # the same Parameter is registered in every layer of the reference (gnn.py:50)
         return sd
 
     def load_state_dict(self, sd):
         for k, dst in self.params.p.items():
             dst.copy_(torch.as_tensor(sd[k], dtype=torch.float32).reshape(dst.shape))
 
-    def _forward(self, x: torch.Tensor):
+    def _forward(self, x: torch.Tensor, keep=None):
+        """Returns (layer inputs [x_0 … x_{L-1}] after dropout, last hidden h, logits).  ``keep``: per-layer dropout scale tensors
+        (training) or None (evaluation)."""
         P = self.params.p
-        h = ops.gemm(x, P["layers.0.layers.1.weight"], transB=True, bias=P["layers.0.layers.1.bias"], act="relu", precision=self.precision)
+        inputs, h = [], x
+        for i in range(self.n_layers):
+            if keep is not None:
+                h = h * keep[i]
+            inputs.append(h)
+            h = ops.gemm(h, P[f"layers.{i}.layers.1.weight"], transB=True, bias=P[f"layers.{i}.layers.1.bias"], act="relu",
+                         precision=self.precision)
         logits = ops.gemm(h, P["linear.weight"], transB=True, bias=P["linear.bias"], precision=self.precision)
-        return h, logits
+        return inputs, h, logits
 
     def _train_batch(self, x: torch.Tensor, y: torch.Tensor, lr: float, weight_decay: float, loss_acc: torch.Tensor):
         P, G = self.params.p, self.params.g
+        keep = None
         if self.dropout > 0.0:
-            # nn.Dropout in front of the AdaptiveSAGE linear (gnn.py:56,92-94): the layer sees only the destination features,
-            # so the mask acts on x; the backward below uses the same dropped-out input.  Masks come from a device generator.
+            # nn.Dropout in front of every AdaptiveSAGE linear (gnn.py:56,92-94): the layer sees only the destination features, so
+            # the mask acts on the layer's input; the backward below uses the same masks.  Masks come from a device generator.
             if self._drop_gen is None:
                 self._drop_gen = torch.Generator(device=self.device)
                 self._drop_gen.manual_seed(int(self.seed) if self.seed is not None else torch.seed() % (2**31))
-            keep = (torch.rand(x.shape, device=self.device, generator=self._drop_gen) >= self.dropout).to(torch.float32)
-            x = x * (keep / (1.0 - self.dropout))
-        h, logits = self._forward(x)
+            widths = [self.dense_dim] + [self.hidden_dim] * (self.n_layers - 1)
+            keep = [(torch.rand((x.shape[0], w), device=self.device, generator=self._drop_gen) >= self.dropout).to(torch.float32) /
+                    (1.0 - self.dropout) for w in widths]
+        inputs, h, logits = self._forward(x, keep)
         _, dlogits = ops.softmax_ce_sum(logits, y, loss_out=loss_acc)                                       # CrossEntropyLoss(sum)
         ops.gemm(dlogits, h, transA=True, out=G["linear.weight"], precision=self.precision)
         ops.colsum(dlogits, out=G["linear.bias"])
         dh = ops.gemm(dlogits, P["linear.weight"], mask=h, precision=self.precision)                        # ⊙ relu'(h)
-        ops.gemm(dh, x, transA=True, out=G["layers.0.layers.1.weight"], precision=self.precision)
-        ops.colsum(dh, out=G["layers.0.layers.1.bias"])
+        for i in reversed(range(self.n_layers)):
+            ops.gemm(dh, inputs[i], transA=True, out=G[f"layers.{i}.layers.1.weight"], precision=self.precision)
+            ops.colsum(dh, out=G[f"layers.{i}.layers.1.bias"])
+            if i > 0:
+                # gradient w.r.t. this layer's (dropped-out) input = the previous layer's ReLU output times its dropout scale
+                prev = inputs[i] if keep is None else None
+                if keep is None:
+                    dh = ops.gemm(dh, P[f"layers.{i}.layers.1.weight"], mask=prev, precision=self.precision)
+                else:
+                    # mask by the ReLU of the previous layer (its output is > 0 exactly where inputs[i] / keep is), then the dropout scale
+                    dh = ops.gemm(dh, P[f"layers.{i}.layers.1.weight"], mask=inputs[i], precision=self.precision) * keep[i]
         G["alpha"].zero_()
         a = self.params.p["alpha"].clone() if weight_decay else None
         self.params.adam_step(lr, weight_decay=weight_decay)
         if a is not None:
             self.params.p["alpha"].copy_(a)    # Adam skips parameters whose grad is None: alpha never moves, not even by weight decay
-        else:
-            pass                               # zero grad, zero moments → zero update
 
     # ---- reference API ------------------------------------------------------------------------
     def fit(self, graph: GraphLite, labels: torch.Tensor, epochs: int = 300, lr: float = 1e-3, weight_decay: float = 0,
@@ -146,7 +170,7 @@ class ScDeepSort:
         if len(idx) == 0:
             return 0, 0, 0.0
         idx = torch.as_tensor(idx, dtype=torch.int64, device=self.device)
-        _, logits = self._forward(self._feat.index_select(0, idx))
+        _, _, logits = self._forward(self._feat.index_select(0, idx))
         mx, arg = logits.max(1)
         unsure = mx < unsure_rate / self.num_labels
         correct = (~unsure) & (arg == self._lab.index_select(0, idx))
@@ -158,7 +182,7 @@ class ScDeepSort:
         feat = graph.ndata["features"].to(self.device, torch.float32)[cell_mask.to(self.device)]
         out = []
         for i in range(0, feat.shape[0], self.batch_size):
-            out.append(self._forward(feat[i:i + self.batch_size])[1])
+            out.append(self._forward(feat[i:i + self.batch_size])[2])
         return torch.softmax(torch.cat(out), dim=-1).cpu().numpy()
 
     def predict(self, graph: GraphLite, unsure_rate: float = 2.0, return_unsure: bool = False):

@@ -53,8 +53,7 @@ def feature_AE_handler(X, TRS, args, param, model_state=None):
     dev = param["device"]
     batch_size = args.feature_AE_batch_size
     total_epoch = args.feature_AE_epoch[param["epoch_num"] > 0]
-    if args.feature_AE_dropout_prob:
-        raise NotImplementedError("feature_AE_dropout_prob > 0 (input masking, scgnn2.py:1260) is not built")
+    p_drop = float(args.feature_AE_dropout_prob or 0.0)        # train_handler's masked_prob: F.dropout on the network input (scgnn2.py:1256)
     if getattr(args, "feature_AE_concat_prev_embed", None) and param["epoch_num"] > 0:
         raise NotImplementedError("feature_AE_concat_prev_embed is not built")
     pool = param.get("io_pool")
@@ -100,7 +99,8 @@ def feature_AE_handler(X, TRS, args, param, model_state=None):
             if slot_busy[slot] is not None:               # the download of batch b-2's reconstruction has left this buffer set
                 main.wait_event(slot_busy[slot])
                 slot_busy[slot] = None
-            z, r = eng.train_step(Xd[b0:b1], None if ltmg is None else ltmg[b0:b1], args.feature_AE_regu_strength, regu, slot=slot)
+            z, r = eng.train_step(Xd[b0:b1], None if ltmg is None else ltmg[b0:b1], args.feature_AE_regu_strength, regu, slot=slot,
+                                  x_input=eng.input_dropout(Xd[b0:b1], p_drop) if p_drop > 0.0 else None)
             if last:
                 z_all[b0:b1].copy_(z)
                 if keep_dev:
@@ -385,8 +385,7 @@ def cluster_AE_handler(X_recon, TRS, clusterIndexList, args, param, model_state)
     logger.info("Starting Cluster AE")
     dev = param["device"]
     bs, epochs = args.cluster_AE_batch_size, args.cluster_AE_epoch
-    if args.cluster_AE_dropout_prob:
-        raise NotImplementedError("cluster_AE_dropout_prob > 0 is not built (the example default is 0)")
+    p_drop = float(args.cluster_AE_dropout_prob or 0.0)        # train_handler's masked_prob (scgnn2.py:1256) for the Cluster-AE runs
     to_dev = lambda a: a.float().contiguous() if (isinstance(a, torch.Tensor) and a.is_cuda) else hostio.as_host_tensor(a).to(dev)
     Xr = to_dev(X_recon)
     xd = param.get("_x_dropout_dev")
@@ -412,7 +411,7 @@ def cluster_AE_handler(X_recon, TRS, clusterIndexList, args, param, model_state)
             for b0 in range(0, m, bs):
                 b1 = min(m, b0 + bs)
                 _, r = eng.train_step(xc[b0:b1], None, args.cluster_AE_regu_strength, "Celltype", row_weight=wc[b0:b1],
-                                      x_dropout=xdc[b0:b1])
+                                      x_dropout=xdc[b0:b1], x_input=eng.input_dropout(xc[b0:b1], p_drop) if p_drop > 0.0 else None)
                 if epoch == epochs - 1:
                     rc[b0:b1].copy_(r)
         out[rows] = rc

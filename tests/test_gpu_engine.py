@@ -142,3 +142,41 @@ def test_gat_engine_matches_reference(cuda, golden, precision):
     for k, v in eng.state_dict().items():
         want = gg["after." + k]
         assert rel_err(v.cpu().numpy().reshape(want.shape), want) < 1e-4, k
+
+
+def test_feature_ae_input_dropout_step_matches_autograd(cuda):
+    """train_handler's masked_prob (scgnn2.py:1256): the network sees F.dropout(data), the loss target is data.  One optimiser step
+    with an explicit dropped-out input against torch autograd on the CPU restatement; the handler option runs and is reproducible."""
+    import argparse
+    from dance_b200.engine import FeatureAEEngine
+    from dance_b200.modules.scgnn2 import feature_AE_handler
+    from oracle import port
+    X = torch.from_numpy(port.synthetic_expression(256, 96, density=0.3, seed=4))
+    keep = (torch.rand(X.shape, generator=torch.Generator().manual_seed(1)) >= 0.25).float() / 0.75
+    Xin = X * keep
+    eng = FeatureAEEngine(96, device=cuda, lr=1e-3, precision="fp32", seed=3)
+    ref = port.FeatureAE(96)
+    ref.load_state_dict({k: v.cpu() for k, v in eng.state_dict().items()})
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    opt.zero_grad()
+    z_ref, r_ref = ref(Xin)
+    loss = port.feature_ae_loss(r_ref, X, "LTMG", 0.9, torch.zeros_like(X))
+    loss.backward()
+    opt.step()
+    eng.loss_acc.zero_()
+    z, r = eng.train_step(X.to(cuda), None, 0.9, "LTMG", x_input=Xin.to(cuda))
+    assert rel_err(r, r_ref.detach().numpy()) < 1e-5 and abs(eng.loss_acc.item() - loss.item()) < 1e-5 * loss.item()
+    for k, v in eng.state_dict().items():
+        assert rel_err(v.cpu().numpy(), ref.state_dict()[k].numpy()) < 1e-4, k
+    d = eng.input_dropout(X.to(cuda), 0.25)
+    kept = d != 0
+    assert 0.6 < kept.float().mean().item() / (X != 0).float().mean().item() < 0.9
+    assert torch.allclose(d[kept], (X.to(cuda) / 0.75)[kept])
+    args = argparse.Namespace(feature_AE_epoch=[2, 1], feature_AE_batch_size=128, feature_AE_learning_rate=1e-3, feature_AE_regu_strength=0.9,
+                              feature_AE_dropout_prob=0.2, feature_AE_concat_prev_embed=None)
+    outs = [feature_AE_handler(X.numpy(), None, args, {"device": cuda, "epoch_num": 0, "total_epoch": 0, "n_feature_orig": 96, "seed": 5})
+            for _ in range(2)]
+    assert np.isfinite(outs[0][1]).all() and np.array_equal(outs[0][0], outs[1][0])          # same seed → same masks → same result
+    args.feature_AE_dropout_prob = 0
+    plain = feature_AE_handler(X.numpy(), None, args, {"device": cuda, "epoch_num": 0, "total_epoch": 0, "n_feature_orig": 96, "seed": 5})
+    assert rel_err(plain[0], outs[0][0]) > 1e-3

@@ -149,3 +149,56 @@ def test_scdeepsort_example_flow_end_to_end(cuda):
     assert acc > 0.9, acc
     pred, unsure = model.predict(g_test, return_unsure=True)
     assert pred.shape == (300, ) and unsure.dtype == bool
+
+
+@pytest.mark.parametrize("dropout", [0.0, 0.3])
+def test_scdeepsort_two_layers_matches_torch_mlp(cuda, dropout):
+    """GNN(n_layers = 2) (scdeepsort.py:26-88): every AdaptiveSAGE layer maps the destination node's own features (module
+    docstring), so two layers are Linear-ReLU-Linear-ReLU-Linear on the cell features.  Two epochs of explicit mini-batches against
+    torch autograd on the CPU with the same initial weights; with dropout the run is compared through its own recorded masks."""
+    from dance_b200.modules.scdeepsort import ScDeepSort
+    n, g, F, H, C = 400, 30, 64, 48, 5
+    rng = np.random.default_rng(3)
+    feats = torch.from_numpy(rng.normal(size=(n + g, F)).astype(np.float32))
+    labels = torch.from_numpy(rng.integers(0, C, size=n))
+    full_labels = torch.cat([-torch.ones(g, dtype=torch.long), labels])
+    cells = np.arange(g, g + n)
+    batches = [[rng.permutation(cells)[i:i + 100] for i in range(0, n, 100)] for _ in range(2)]
+    model = ScDeepSort(F, H, 2, device="cuda", batch_size=100, precision="fp32", seed=0, dropout=dropout)
+    model._build(g, C)
+    sd = model.state_dict()
+    assert "layers.1.layers.1.weight" in sd and sd["layers.1.layers.1.weight"].shape == (H, H) and "layers.1.alpha" in sd
+    lin = [torch.nn.Linear(F, H), torch.nn.Linear(H, H), torch.nn.Linear(H, C)]
+    with torch.no_grad():
+        for i in (0, 1):
+            lin[i].weight.copy_(sd[f"layers.{i}.layers.1.weight"].cpu()); lin[i].bias.copy_(sd[f"layers.{i}.layers.1.bias"].cpu())
+        lin[2].weight.copy_(sd["linear.weight"].cpu()); lin[2].bias.copy_(sd["linear.bias"].cpu())
+    opt = torch.optim.Adam([p for l in lin for p in l.parameters()], lr=1e-3)
+    model._feat, model._lab = feats.to(cuda), full_labels.to(cuda)
+    masks = []
+    if dropout:                       # record the masks the model draws (same generator, same call order) for the reference
+        gen = torch.Generator(device=cuda)
+        gen.manual_seed(0)
+        for ep in batches:
+            for b in ep:
+                masks.append([(torch.rand((len(b), w), device=cuda, generator=gen) >= dropout).float().cpu() / (1 - dropout) for w in (F, H)])
+    losses, ref_losses, k = [], [], 0
+    for ep in batches:
+        losses.append(model.cal_loss(ep, 1e-3, 0.0))
+        tot = cnt = 0.0
+        for b in ep:
+            x, y = feats[b], full_labels[b]
+            m0, m1 = (masks[k] if dropout else (1.0, 1.0))
+            k += 1
+            opt.zero_grad()
+            h = torch.relu(lin[1](torch.relu(lin[0](x * m0)) * m1))
+            loss = torch.nn.functional.cross_entropy(lin[2](h), y, reduction="sum")
+            loss.backward()
+            opt.step()
+            tot += loss.item() * len(b); cnt += len(b)
+        ref_losses.append(tot / cnt)
+    assert np.allclose(losses, ref_losses, rtol=1e-4)
+    sd = model.state_dict()
+    for i in (0, 1):
+        assert rel_err(sd[f"layers.{i}.layers.1.weight"].cpu().numpy(), lin[i].weight.detach().numpy()) < 1e-4, i
+    assert rel_err(sd["linear.weight"].cpu().numpy(), lin[2].weight.detach().numpy()) < 1e-4
