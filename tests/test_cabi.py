@@ -97,3 +97,24 @@ def test_header_is_plain_c(tmp_path):
     code = re.sub(r"/\*.*?\*/", "", (hdr / "dance_b200.h").read_text(), flags=re.S)      # declarations only, comments stripped
     for banned in ("std::", "template", "class ", "Tensor", "cudaStream_t", "torch"):
         assert banned not in code, banned
+
+
+def test_selector_tables_match_the_header():
+    """ops.set_path / ops.set_tuning index the library's selector arrays by the header's constants: the Python tables must name
+    every B2_PATH_* / B2_TUNE_* selector with the header's number, and an out-of-range selector is refused by the library."""
+    import re
+    from pathlib import Path
+    from dance_b200 import _lib, ops
+    hdr = (Path(__file__).resolve().parent.parent / "include" / "dance_b200.h").read_text()
+    consts = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(B2_(?:PATH|TUNE)_[A-Z_]+)\s+(\d+)", hdr)}
+    assert consts["B2_PATH_COUNT"] == 3 and consts["B2_TUNE_COUNT"] == 3
+    assert {k: v[0] for k, v in ops._PATHS.items()} == {"gae": consts["B2_PATH_GAE_DECODER"], "knn": consts["B2_PATH_KNN_FILTER"],
+                                                         "spmm": consts["B2_PATH_SPMM"]}
+    lib = _lib.lib()
+    assert lib.b2_set_path(consts["B2_PATH_COUNT"], 0) != 0 and lib.b2_set_tuning(consts["B2_TUNE_COUNT"], 0) != 0
+    assert lib.b2_set_path(consts["B2_PATH_SPMM"], 1) == 0 and lib.b2_get_path(consts["B2_PATH_SPMM"]) == 1
+    assert lib.b2_set_path(consts["B2_PATH_SPMM"], 0) == 0
+    for knob, idx in (("gae_stagger", consts["B2_TUNE_GAE_STAGGER"]), ("gae_late_gempty", consts["B2_TUNE_GAE_LATE_GEMPTY"]),
+                      ("gae_splits", consts["B2_TUNE_GAE_SPLITS"])):
+        assert lib.b2_set_tuning(idx, 1) == 0
+    ops.set_tuning("gae_stagger", 1500), ops.set_tuning("gae_late_gempty", 1), ops.set_tuning("gae_splits", 0)   # the defaults
