@@ -20,8 +20,10 @@
 // (deterministic, independent of the launch geometry).
 //
 // Measured (B200, 1 M cells, nnz 28.1 M, F = 32, cold L2; scripts/lab/gather_lab.cu is the harness the design was selected with):
-// fp32 operand 0.46 ms vs 1.21 ms for spmm_csr_kernel<8,1>; bf16 operand 0.44 ms vs 0.96 ms.  TMA tile::gather4 and per-row
-// cp.async.bulk staging of the same pipeline were slower (0.64–1.05 ms): the copies are too small for the TMA unit to pay off.
+// fp32 operand 0.49 ms vs 1.21 ms for spmm_csr_kernel<8,1>; bf16 operand 0.49 ms vs 0.96 ms (lab versions without the C-ABI's
+// options: 0.46 / 0.44 ms).  TMA tile::gather4 and per-row cp.async.bulk staging of the same pipeline were slower (0.64–1.05 ms):
+// the copies are too small for the TMA unit to pay off.  ncu: issue slots 76 % busy (14 instructions per non-zero) — the kernel is
+// issue-bound, which is why the bf16 operand is no faster (profiles/r02_ncu_spmm.md).
 #include "common.cuh"
 
 #include <cuda_bf16.h>
