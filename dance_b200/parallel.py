@@ -68,6 +68,49 @@ def sym_schedule(n_blocks: int, super_block: int) -> List[Tuple[int, int]]:
     return out
 
 
+def sym_steps(n_blocks: int, super_block: int) -> List[List[Tuple[int, int]]]:
+    """The same tiles grouped by J-step: step s of super-block sb stages Z_J for J = (2·sb + s) mod nb and evaluates the tiles of its
+    one or two owned blocks against it (block 2·sb at offset o = s, block 2·sb+1 at o = s − 1).  Trailing empty steps are dropped,
+    as in ``gsym::Sweep::n_steps``."""
+    nb, h = n_blocks, n_blocks // 2
+    even = nb % 2 == 0
+    steps = []
+    for s in range(h + 2):
+        tiles = []
+        for g, I in enumerate((2 * super_block, 2 * super_block + 1)):
+            o = s - g
+            if I >= nb or o < 0 or o > h or (o == h and o > 0 and even and I + h >= nb):
+                continue
+            tiles.append((I, (I + o) % nb))
+        steps.append(tiles)
+    while steps and not steps[-1]:
+        steps.pop()
+    return steps
+
+
+def sym_step_range(n_steps: int, part: int, splits: int) -> Tuple[int, int]:
+    """Steps [s0, s1) of a super-block's sweep that CTA ``part`` of ``splits`` runs (``gsym::Sweep::s0 / s1``): the decoder cuts
+    sweeps into step ranges so that a rank's grid fills whole waves of SMs."""
+    return n_steps * part // splits, n_steps * (part + 1) // splits
+
+
+def spmm_stream_partition(rowptr, n_warps: int) -> List[Tuple[int, int]]:
+    """Row ranges [R0, R1) the warps of the nnz-stream aggregate own (csrc/spmm_stream.cu): warp w takes the rows whose key
+    rowptr[r] + r lies in [w·T/W, (w+1)·T/W), T = nnz + n_rows — balanced by non-zeros AND rows, so empty rows and hub rows cost
+    what they cost.  Host restatement for tests; the kernel finds the boundaries with a warp-cooperative 32-ary search."""
+    import numpy as np
+    rp = np.asarray(rowptr, dtype=np.int64)
+    n_rows = len(rp) - 1
+    key = rp + np.arange(n_rows + 1)
+    total = int(key[-1])
+    out = []
+    for w in range(n_warps):
+        r0 = 0 if w == 0 else int(np.searchsorted(key, w * total // n_warps, side="left"))
+        r1 = n_rows if w == n_warps - 1 else int(np.searchsorted(key, (w + 1) * total // n_warps, side="left"))
+        out.append((r0, max(r0, r1)))
+    return out
+
+
 def sym_super_blocks(n: int, block: int = 128) -> int:
     return ((n + block - 1) // block + 1) // 2
 

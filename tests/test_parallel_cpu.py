@@ -283,3 +283,39 @@ def test_uneven_shards_issue_equal_collectives_gloo():
 
 def test_data_parallel_feature_ae_gradients_gloo():
     assert max(_run("_dp_feature_ae_case").values()) < 1e-5
+
+
+def test_symmetric_decoder_step_ranges_cover_every_tile_once():
+    """The decoder cuts each super-block's J sweep into step ranges (one CTA each): for every block count and every number of
+    parts the union of the parts' tiles is the super-block's tile list, without overlap — including more parts than steps."""
+    from dance_b200.parallel import sym_schedule, sym_step_range, sym_steps, sym_super_blocks
+    for nb in (1, 2, 3, 8, 13, 16, 17, 64, 65):
+        seen = set()
+        for sb in range(sym_super_blocks(nb * 128)):
+            steps = sym_steps(nb, sb)
+            flat = [t for st in steps for t in st]
+            assert sorted(flat) == sorted(sym_schedule(nb, sb)) and all(steps[i] for i in range(len(steps)))
+            for splits in (1, 2, 3, 5, 8, len(steps) + 3):
+                parts = [sym_step_range(len(steps), p, splits) for p in range(splits)]
+                assert parts[0][0] == 0 and parts[-1][1] == len(steps) and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+                got = [t for s0, s1 in parts for st in steps[s0:s1] for t in st]
+                assert got == flat
+            seen.update((min(i, j), max(i, j)) for i, j in flat)
+        assert len(seen) == nb * (nb + 1) // 2          # every unordered block pair exactly once over all super-blocks
+
+
+def test_spmm_stream_partition_balances_rows_and_nonzeros():
+    """Row ranges of the nnz-stream aggregate's warps: a partition of the rows in order, balanced by (non-zeros + rows) up to one
+    row — for uniform degrees, hub rows, long runs of empty rows and an all-empty matrix."""
+    from dance_b200.parallel import spmm_stream_partition
+    rng = np.random.default_rng(0)
+    cases = [rng.integers(20, 40, 5000), np.r_[rng.integers(0, 5, 3000), 9000, rng.integers(0, 5, 3000)], np.r_[np.zeros(4000, int), rng.integers(1, 60, 500), np.zeros(700, int)],
+             np.zeros(300, int), np.array([5])]
+    for deg in cases:
+        rp = np.r_[0, np.cumsum(deg)]
+        for W in (1, 7, 64, 1000):
+            parts = spmm_stream_partition(rp, W)
+            assert parts[0][0] == 0 and parts[-1][1] == len(deg) and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            load = np.array([rp[r1] - rp[r0] + (r1 - r0) for r0, r1 in parts])
+            assert load.sum() == deg.sum() + len(deg)
+            assert load.max() <= (deg.sum() + len(deg)) / W + deg.max() + 2      # at most one row over the even share
