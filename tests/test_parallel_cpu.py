@@ -319,3 +319,50 @@ def test_spmm_stream_partition_balances_rows_and_nonzeros():
             load = np.array([rp[r1] - rp[r0] + (r1 - r0) for r0, r1 in parts])
             assert load.sum() == deg.sum() + len(deg)
             assert load.max() <= (deg.sum() + len(deg)) / W + deg.max() + 2      # at most one row over the even share
+
+
+def test_spmm_stream_traversal_emulation_matches_csr_product():
+    """Control flow of spmm_stream_kernel restated on the host — per warp: 32-entry blocks of its non-zero stream, consumed in
+    order with a (row, row_end) cursor that emits a row whenever row_end ≤ position, NPI lane groups splitting each run, tail emission
+    of rows that end at the stream's end — against the CSR product.  Guards the algorithm (block / row boundary cases), not the CUDA."""
+    import scipy.sparse as sp
+    from dance_b200.parallel import spmm_stream_partition
+    rng = np.random.default_rng(1)
+    n, c, F, BLK, NPI = 700, 300, 8, 32, 4
+    deg = rng.integers(0, 50, n)
+    deg[50:120] = 0; deg[300] = 900; deg[400:432] = 32; deg[-40:] = 0
+    rows = np.repeat(np.arange(n), deg)
+    m = sp.csr_matrix((rng.normal(size=rows.size), (rows, rng.integers(0, c, rows.size))), shape=(n, c))
+    m.sum_duplicates(); m.sort_indices()
+    X = rng.normal(size=(c, F))
+    rp, ci, va = m.indptr.astype(np.int64), m.indices, m.data
+    Y = np.full((n, F), np.nan)
+    for R0, R1 in spmm_stream_partition(rp, 13):
+        if R0 >= R1:
+            continue
+        E0, E1 = rp[R0], rp[R1]
+        nblk = -(-(E1 - E0) // BLK)
+        r, rend = R0, rp[R0 + 1]
+        acc = np.zeros((NPI, F))                       # one partial sum per lane group
+
+        def emit():
+            nonlocal r, rend, acc
+            Y[r] = acc.sum(0)
+            acc = np.zeros((NPI, F))
+            r += 1
+            rend = rp[min(r + 1, n)]
+        for b in range(nblk):
+            eb, eend = E0 + b * BLK, min(E1, E0 + (b + 1) * BLK)
+            e = eb
+            while True:
+                while r < R1 and rend <= e:
+                    emit()
+                if e >= eend or r >= R1:
+                    break
+                run_end = min(rend, eend)
+                for k in range(e, run_end):
+                    acc[(k - e) % NPI] += va[k] * X[ci[k]]
+                e = run_end
+        while r < R1:
+            emit()
+    assert not np.isnan(Y).any() and np.allclose(Y, m @ X, rtol=1e-12, atol=1e-12)
